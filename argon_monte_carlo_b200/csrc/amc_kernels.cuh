@@ -1,0 +1,552 @@
+// amc_kernels.cuh -- the kernels of libamc.so.
+//   k_advect        K1+K4: drift, wall cases, recapture, owner-cell key + in-cell rank   (HBM streaming)
+//   k_scan_*        exclusive scan of the owner-cell histogram                          (tiny)
+//   k_scatter       counting-sort scatter of the SoA state into owner-cell order        (HBM streaming)
+//   k_pairs_group   K2+K3: one CTA per reference cell of a colour group                 (fp64 / latency)
+//   k_cube_sweep    the serial lexicographic cell sweep of the cube stage               (latency)
+//   k_case_*        per-case wall kernels for the host-RNG parity mode
+#pragma once
+#include "amc_device.cuh"
+
+#define ADVECT_THREADS 256
+#define PAIR_THREADS 256
+#define SWEEP_THREADS 512
+
+__device__ __forceinline__ void load_part(const Arrays &a, int64_t s, Part &q)
+{
+    q.x = a.x[s]; q.y = a.y[s]; q.z = a.z[s]; q.vx = a.vx[s]; q.vy = a.vy[s]; q.vz = a.vz[s];
+    q.d = a.d[s]; q.dx = a.dx[s]; q.dy = a.dy[s]; q.dz = a.dz[s]; q.flag = a.flag[s];
+}
+__device__ __forceinline__ void store_part(const Arrays &a, int64_t s, const Part &q)
+{
+    a.x[s] = q.x; a.y[s] = q.y; a.z[s] = q.z; a.vx[s] = q.vx; a.vy[s] = q.vy; a.vz[s] = q.vz;
+    a.d[s] = q.d; a.dx[s] = q.dx; a.dy[s] = q.dy; a.dz[s] = q.dz; a.flag[s] = (uint8_t)q.flag;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1 + K4.  One thread per particle slot; `phase` selects the parts of the step to run so the same
+// code serves the fused step and the phase-level parity entry points.
+//   drift         Pore:427-437 / Temp:673-683 / Cube:180-187
+//   walls         Pore:442-485 / Temp:693-753 (device RNG) / Cube:192-226
+//   recapture     Pore:354-375 / Temp:560-616
+//   keys          owner cell of the final position + rank inside that cell (counting sort, pass 1)
+__global__ void __launch_bounds__(ADVECT_THREADS) k_advect(const __grid_constant__ P p, const int phase)
+{
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= p.n) return;
+    Part q;
+    load_part(p.a, s, q);
+    q.flag &= AMC_FLAG_PATH;
+    int32_t id = p.a.id[s];
+    if (phase & PH_RECAP_POST) { // recapture that closes the previous step's pair pass (Pore:550 / Temp:843-845)
+        int cnt = p.kind == AMC_KIND_TEMP ? temp_oob(p.g, q) : 0;
+        int moved = p.kind == AMC_KIND_TEMP ? temp_recapture(p.g, q) : pore_recapture(p.g, q);
+        if (p.kind != AMC_KIND_TEMP) cnt = moved;
+        if (cnt) atomicAdd(&p.stats->oob_pp, (unsigned long long)cnt);
+    }
+    if (phase & PH_DRIFT) {
+        q.px = q.x; q.py = q.y; q.pz = q.z;
+        double ax = p.dt * q.vx, ay = p.dt * q.vy, az = p.dt * q.vz;
+        q.x += ax; q.y += ay; q.z += az;
+        q.d += fabs(sqrt((ax * ax + ay * ay) + az * az));
+        q.dx += fabs(ax); q.dy += fabs(ay); q.dz += fabs(az);
+        if (phase & PH_SAVE_PRIOR) { p.px[s] = q.px; p.py[s] = q.py; p.pz[s] = q.pz; }
+    } else if (phase & PH_LOAD_PRIOR) {
+        q.px = p.px[s]; q.py = p.py[s]; q.pz = p.pz[s];
+    }
+    if (phase & PH_WALLS) {
+        uint32_t bits = p.kind == AMC_KIND_PORE ? pore_walls(p, q) : (p.kind == AMC_KIND_TEMP ? temp_walls_device(p, q, id) : cube_walls(p, q));
+        if (bits) {
+            for (uint32_t b = bits; b; b &= b - 1) atomicAdd(&p.stats->wall_hits[__ffs(b) - 1], 1ull);
+        }
+        if (p.wall_bits) p.wall_bits[id] = (uint16_t)bits;
+    }
+    if (phase & PH_RECAP) {
+        if (p.kind == AMC_KIND_PORE) {
+            int cnt = pore_recapture(p.g, q);
+            if (cnt) atomicAdd(&p.stats->oob_walls, (unsigned long long)cnt);
+        } else if (p.kind == AMC_KIND_TEMP) {
+            int cnt = temp_oob(p.g, q);
+            if (cnt) atomicAdd(&p.stats->oob_walls, (unsigned long long)cnt);
+            temp_recapture(p.g, q);
+        }
+    }
+    if (phase & (PH_DRIFT | PH_WALLS | PH_RECAP | PH_RECAP_POST)) store_part(p.a, s, q);
+    if (phase & PH_KEYS) {
+        int o[3];
+        int32_t k = owner_key(p, q.x, q.y, q.z, o);
+        p.key[s] = k;
+        p.rank[s] = atomicAdd(&p.cell_count[k], 1);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// exclusive scan of cell_count[0..m) -> cell_start[0..m], three small kernels (m <= a few million)
+#define SCAN_THREADS 1024
+#define SCAN_ITEMS 4
+#define SCAN_TILE (SCAN_THREADS * SCAN_ITEMS)
+
+__device__ __forceinline__ int block_exclusive_scan(int v, int *total)
+{
+    __shared__ int warp_sums[32];
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) warp_sums[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        int ws = warp_sums[lane], wi = ws;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += t; }
+        warp_sums[lane] = wi - ws;
+        if (lane == 31) *total = wi;
+    }
+    __syncthreads();
+    int r = warp_sums[w] + inc - v;
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_tiles(const int32_t *in, int32_t *out, int32_t *tile_sums, int m)
+{
+    __shared__ int total;
+    int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    int v[SCAN_ITEMS], sum = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) { v[k] = base + k < m ? in[base + k] : 0; sum += v[k]; }
+    int ex = block_exclusive_scan(sum, &total);
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) { if (base + k < m) out[base + k] = ex; ex += v[k]; }
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_sums(int32_t *tile_sums, int ntiles)
+{
+    __shared__ int total;
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < ntiles; base += SCAN_THREADS) {
+        int i = base + threadIdx.x;
+        int v = i < ntiles ? tile_sums[i] : 0;
+        int ex = block_exclusive_scan(v, &total);
+        if (i < ntiles) tile_sums[i] = ex + carry;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += total;
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_add(int32_t *out, const int32_t *tile_sums, int m, int32_t n_total)
+{
+    int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    int add = tile_sums[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) if (base + k < m) out[base + k] += add;
+    if (blockIdx.x == 0 && threadIdx.x == 0) out[m] = n_total;
+}
+
+// counting-sort scatter: slot s of the old layout moves to cell_start[key] + rank
+__global__ void __launch_bounds__(ADVECT_THREADS) k_scatter(const __grid_constant__ P p)
+{
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= p.n) return;
+    int64_t t = (int64_t)p.cell_start[p.key[s]] + p.rank[s];
+    p.b.x[t] = p.a.x[s]; p.b.y[t] = p.a.y[s]; p.b.z[t] = p.a.z[s];
+    p.b.vx[t] = p.a.vx[s]; p.b.vy[t] = p.a.vy[s]; p.b.vz[t] = p.a.vz[s];
+    p.b.d[t] = p.a.d[s]; p.b.dx[t] = p.a.dx[s]; p.b.dy[t] = p.a.dy[s]; p.b.dz[t] = p.a.dz[s];
+    p.b.flag[t] = p.a.flag[s] & AMC_FLAG_PATH;
+    p.b.id[t] = p.a.id[s];
+}
+
+// gather back to original index order (amc_get_state)
+__global__ void __launch_bounds__(ADVECT_THREADS) k_unsort(const __grid_constant__ P p)
+{
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= p.n) return;
+    int64_t t = p.a.id[s];
+    p.b.x[t] = p.a.x[s]; p.b.y[t] = p.a.y[s]; p.b.z[t] = p.a.z[s];
+    p.b.vx[t] = p.a.vx[s]; p.b.vy[t] = p.a.vy[s]; p.b.vz[t] = p.a.vz[s];
+    p.b.d[t] = p.a.d[s]; p.b.dx[t] = p.a.dx[s]; p.b.dy[t] = p.a.dy[s]; p.b.dz[t] = p.a.dz[s];
+    p.b.flag[t] = p.a.flag[s] & AMC_FLAG_PATH;
+    p.b.id[t] = (int32_t)t;
+}
+
+// start of a pair pass: forget the escaped-particle list of the previous pass (single block, so
+// every thread reads the old count before it is cleared; unused entries always hold -1)
+__global__ void k_pp_begin(const __grid_constant__ P p)
+{
+    int n = *p.esc_count;
+    if (n > p.esc_cap) n = p.esc_cap;
+    for (int i = threadIdx.x; i < n * 8; i += blockDim.x) p.esc_cell[i] = -1;
+    __syncthreads();
+    if (threadIdx.x == 0) *p.esc_count = 0;
+}
+
+// recapture that closes a pair pass (Pore:550 / Temp:843-845): positions only
+__global__ void __launch_bounds__(ADVECT_THREADS) k_recapture_post(const __grid_constant__ P p)
+{
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= p.n) return;
+    Part q;
+    q.x = p.a.x[s]; q.y = p.a.y[s]; q.z = p.a.z[s];
+    double x0 = q.x, y0 = q.y, z0 = q.z;
+    int cnt = p.kind == AMC_KIND_TEMP ? temp_oob(p.g, q) : 0;
+    int moved = p.kind == AMC_KIND_TEMP ? temp_recapture(p.g, q) : pore_recapture(p.g, q);
+    if (p.kind != AMC_KIND_TEMP) cnt = moved;
+    if (cnt) atomicAdd(&p.stats->oob_pp, (unsigned long long)cnt);
+    if (q.x != x0) p.a.x[s] = q.x;
+    if (q.y != y0) p.a.y[s] = q.y;
+    if (q.z != z0) p.a.z[s] = q.z;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2 + K3: one reference cell.
+//
+// The reference visits the members of a cell in ascending global index and tests (i, j<i) against
+// the live cell-local arrays, so a collision is visible to every later pair of the same cell
+// (Pore:168-241).  "Earlier/later" is the lexicographic order of (larger id, smaller id), so the
+// members need not be sorted: the CTA (1) tests all unordered member pairs in parallel and keeps
+// the overlapping ones as candidates, (2) repeatedly resolves the candidate with the smallest key
+// above a cursor, drops every candidate that involves one of the two moved particles and re-tests
+// those two against all members for keys above the cursor.  That reproduces the sequential sweep
+// exactly: pairs below the cursor were already passed, pairs not involving a moved particle keep
+// their first-scan verdict.
+struct CellShared {
+    double x[AMC_MAX_MEMBERS], y[AMC_MAX_MEMBERS], z[AMC_MAX_MEMBERS];
+    int32_t id[AMC_MAX_MEMBERS], slot[AMC_MAX_MEMBERS], src[AMC_MAX_MEMBERS];
+    unsigned long long cand_key[AMC_MAX_CAND];
+    int32_t cand_ab[AMC_MAX_CAND]; /* a | b << 16 */
+    int n, ncand, sel, done;
+    unsigned long long cursor;
+    int moved_a, moved_b;
+    int kx, ky, kz; /* 0-based cell indices of this visit (colour-group mode) */
+};
+
+__device__ __forceinline__ unsigned long long pair_key(int32_t ia, int32_t ib)
+{
+    uint32_t hi = ia > ib ? ia : ib, lo = ia > ib ? ib : ia;
+    return ((unsigned long long)hi << 32) | lo;
+}
+__device__ __forceinline__ bool overlap(const P &p, double xa, double ya, double za, double xb, double yb, double zb)
+{
+    double ddx = xb - xa, ddy = yb - ya, ddz = zb - za;
+    return (ddx * ddx + ddy * ddy) + ddz * ddz < p.overlap_sq; /* == sqrt(...) < collision_range, Pore:173-174 */
+}
+__device__ __forceinline__ void push_cand(CellShared &S, const P &p, int a, int b)
+{
+    int k = atomicAdd(&S.ncand, 1);
+    if (k < AMC_MAX_CAND) { S.cand_key[k] = pair_key(S.id[a], S.id[b]); S.cand_ab[k] = a | (b << 16); }
+    else atomicAdd(&p.stats->cand_overflow, 1ull);
+}
+
+// elastic exchange of one overlapping pair, executed by one thread (Pore:176-241).
+// m1 = member with the smaller global index (the reference's particle "1" = j), m2 the larger.
+__device__ __noinline__ void resolve_pair(const P &p, CellShared &S, int m1, int m2, int group, int cell)
+{
+    const Arrays &A = p.a;
+    int s1 = S.slot[m1], s2 = S.slot[m2];
+    double x1 = S.x[m1], y1 = S.y[m1], z1 = S.z[m1], x2 = S.x[m2], y2 = S.y[m2], z2 = S.z[m2];
+    double vx1 = A.vx[s1], vy1 = A.vy[s1], vz1 = A.vz[s1], vx2 = A.vx[s2], vy2 = A.vy[s2], vz2 = A.vz[s2];
+    double ddx = x2 - x1, ddy = y2 - y1, ddz = z2 - z1;
+    double rx = -vx2 + vx1, ry = -vy2 + vy1, rz = -vz2 + vz1;
+    double a = (rx * rx + ry * ry) + rz * rz;
+    double b = 2 * ((ddx * rx + ddy * ry) + ddz * rz);
+    double c = ((ddx * ddx + ddy * ddy) + ddz * ddz) - p.cr * p.cr;
+    double disc = b * b - (4 * a) * c;
+    if (!(disc >= 0.0) || a == 0.0) { atomicAdd(&p.stats->errors, 1ull); return; }
+    double root = sqrt(disc);
+    double t1 = (-b + root) / (2 * a), t2 = (-b - root) / (2 * a);
+    double t = t1 > t2 ? t1 : t2;
+    uint32_t f1 = A.flag[s1], f2 = A.flag[s2];
+    mfp_record(p, A.d[s1], A.dx[s1], A.dy[s1], A.dz[s1], f1, vx1, vy1, vz1, t);
+    mfp_record(p, A.d[s2], A.dx[s2], A.dy[s2], A.dz[s2], f2, vx2, vy2, vz2, t);
+    double nx1 = x1 - vx1 * t, ny1 = y1 - vy1 * t, nz1 = z1 - vz1 * t;
+    double nx2 = x2 - vx2 * t, ny2 = y2 - vy2 * t, nz2 = z2 - vz2 * t;
+    double n0 = (nx2 - nx1) / p.cr, n1 = (ny2 - ny1) / p.cr, n2 = (nz2 - nz1) / p.cr;
+    double pp = (((vx1 * n0 + vy1 * n1) + vz1 * n2) - ((vx2 * n0 + vy2 * n1) + vz2 * n2)) / p.mass;
+    double pm = pp * p.mass;
+    double wx1 = vx1 - pm * n0, wy1 = vy1 - pm * n1, wz1 = vz1 - pm * n2;
+    double wx2 = vx2 + pm * n0, wy2 = vy2 + pm * n1, wz2 = vz2 + pm * n2;
+    x1 = nx1 + wx1 * t; y1 = ny1 + wy1 * t; z1 = nz1 + wz1 * t;
+    x2 = nx2 + wx2 * t; y2 = ny2 + wy2 * t; z2 = nz2 + wz2 * t;
+    S.x[m1] = x1; S.y[m1] = y1; S.z[m1] = z1; S.x[m2] = x2; S.y[m2] = y2; S.z[m2] = z2;
+    A.x[s1] = x1; A.y[s1] = y1; A.z[s1] = z1; A.x[s2] = x2; A.y[s2] = y2; A.z[s2] = z2;
+    A.vx[s1] = wx1; A.vy[s1] = wy1; A.vz[s1] = wz1; A.vx[s2] = wx2; A.vy[s2] = wy2; A.vz[s2] = wz2;
+    A.d[s2] = fabs(sqrt((wx2 * wx2 + wy2 * wy2) + wz2 * wz2) * t);
+    A.d[s1] = fabs(sqrt((wx1 * wx1 + wy1 * wy1) + wz1 * wz1) * t);
+    A.dx[s2] = fabs(wx2 * t); A.dy[s2] = fabs(wy2 * t); A.dz[s2] = fabs(wz2 * t);
+    A.dx[s1] = fabs(wx1 * t); A.dy[s1] = fabs(wy1 * t); A.dz[s1] = fabs(wz1 * t);
+    atomicAdd(&p.stats->pp, 1ull);
+    if (p.pair_count) {
+        unsigned long long k = atomicAdd(p.pair_count, 1ull);
+        if ((int64_t)k < p.pair_cap) { p.pair_hi[k] = S.id[m2]; p.pair_lo[k] = S.id[m1]; p.pair_group[k] = group; p.pair_cell[k] = cell; }
+    }
+    if (p.pp_mode == AMC_PP_GROUPS) {
+        // A moved particle whose owner cell changed can no longer be found through the sorted
+        // layout: publish its member cell for every later colour group in the escaped list.
+        for (int w = 0; w < 2; w++) {
+            int m = w ? m2 : m1, s = w ? s2 : s1;
+            double x = w ? x2 : x1, y = w ? y2 : y1, z = w ? z2 : z1;
+            uint32_t &f = w ? f2 : f1;
+            int o[3];
+            int32_t k = owner_key(p, x, y, z, o);
+            int e = S.src[m];
+            if (e < 0) { /* found through the sorted layout: src = -1 - (low-side neighbour code) */
+                int nb = -1 - e;
+                int oc = ((S.kx + 1 - (nb >> 2)) * p.pnc[1] + (S.ky + 1 - ((nb >> 1) & 1))) * p.pnc[2] + (S.kz + 1 - (nb & 1));
+                if (k == oc) continue; /* still in its sorted owner cell */
+            }
+            if (e < 0) {
+                e = atomicAdd(p.esc_count, 1);
+                if (e >= p.esc_cap) { atomicAdd(&p.stats->esc_overflow, 1ull); continue; }
+                p.esc_slot[e] = s;
+                S.src[m] = e;
+                f |= AMC_FLAG_ESC;
+            }
+            for (int g2 = group + 1; g2 < 8; g2++) {
+                int cx = member_axis(p.edge[0], p.lo[0], p.nc[0], o[0], (g2 >> 2) & 1, x);
+                int cy = member_axis(p.edge[1], p.lo[1], p.nc[1], o[1], (g2 >> 1) & 1, y);
+                int cz = member_axis(p.edge[2], p.lo[2], p.nc[2], o[2], g2 & 1, z);
+                int32_t cc = (cx < 0 || cy < 0 || cz < 0) ? -1 : ((cx >> 1) * (p.nc[1] >> 1) + (cy >> 1)) * (p.nc[2] >> 1) + (cz >> 1);
+                p.esc_cell[e * 8 + g2] = cc;
+            }
+        }
+    }
+    A.flag[s1] = (uint8_t)f1; A.flag[s2] = (uint8_t)f2;
+}
+
+// members are in S.{x,y,z,id,slot,src}[0..S.n); all threads of the block call this
+__device__ void cell_process(const P &p, CellShared &S, int group, int cell)
+{
+    const int n = S.n, tid = threadIdx.x, nthreads = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
+    if (tid == 0) {
+        unsigned long long c = (unsigned long long)n * (n - 1) / 2;
+        atomicAdd(&p.stats->checks_ref, c);
+        atomicAdd(&p.stats->checks_exec, c);
+    }
+    for (int a = warp; a < n - 1; a += nwarps) {
+        double xa = S.x[a], ya = S.y[a], za = S.z[a];
+        for (int b = a + 1 + lane; b < n; b += 32)
+            if (overlap(p, xa, ya, za, S.x[b], S.y[b], S.z[b])) push_cand(S, p, a, b);
+    }
+    __syncthreads();
+    if (S.ncand == 0) return;
+    if (tid == 0) { S.cursor = 0; S.done = 0; if (S.ncand > AMC_MAX_CAND) S.ncand = AMC_MAX_CAND; }
+    __syncthreads();
+    while (true) {
+        if (tid == 0) {
+            int best = -1;
+            unsigned long long bk = ~0ull;
+            for (int k = 0; k < S.ncand; k++)
+                if (S.cand_key[k] < bk) { bk = S.cand_key[k]; best = k; } /* all stored keys are above the cursor */
+            if (best < 0) S.done = 1;
+            else {
+                int a = S.cand_ab[best] & 0xffff, b = S.cand_ab[best] >> 16;
+                int m1 = S.id[a] < S.id[b] ? a : b, m2 = S.id[a] < S.id[b] ? b : a;
+                resolve_pair(p, S, m1, m2, group, cell);
+                S.cursor = bk; S.moved_a = a; S.moved_b = b;
+                int w = 0;
+                for (int k = 0; k < S.ncand; k++) {
+                    int ka = S.cand_ab[k] & 0xffff, kb = S.cand_ab[k] >> 16;
+                    if (ka == a || ka == b || kb == a || kb == b) continue;
+                    S.cand_key[w] = S.cand_key[k]; S.cand_ab[w] = S.cand_ab[k]; w++;
+                }
+                S.ncand = w;
+            }
+        }
+        __syncthreads();
+        if (S.done) break;
+        {
+            int a = S.moved_a, b = S.moved_b;
+            unsigned long long cur = S.cursor;
+            double xa = S.x[a], ya = S.y[a], za = S.z[a], xb = S.x[b], yb = S.y[b], zb = S.z[b];
+            for (int k = tid; k < n; k += nthreads) {
+                if (k == a || k == b) continue;
+                double xk = S.x[k], yk = S.y[k], zk = S.z[k];
+                if (pair_key(S.id[a], S.id[k]) > cur && overlap(p, xa, ya, za, xk, yk, zk)) push_cand(S, p, a, k);
+                if (pair_key(S.id[b], S.id[k]) > cur && overlap(p, xb, yb, zb, xk, yk, zk)) push_cand(S, p, b, k);
+            }
+            if (tid == 0) atomicAdd(&p.stats->checks_exec, (unsigned long long)(2 * (n - 2)));
+        }
+        __syncthreads();
+        if (tid == 0 && S.ncand > AMC_MAX_CAND) S.ncand = AMC_MAX_CAND;
+        __syncthreads();
+    }
+}
+
+// one colour group (Pore:522-549): grid = all reference cells of the group, x-major / z-minor
+__global__ void __launch_bounds__(PAIR_THREADS) k_pairs_group(const __grid_constant__ P p, const int group)
+{
+    __shared__ CellShared S;
+    const int tid = threadIdx.x;
+    const int nhy = p.nc[1] >> 1, nhz = p.nc[2] >> 1;
+    const int cell = blockIdx.x;
+    const int hz = cell % nhz, hy = (cell / nhz) % nhy, hx = cell / (nhz * nhy);
+    const int kx = 2 * hx + ((group >> 2) & 1), ky = 2 * hy + ((group >> 1) & 1), kz = 2 * hz + (group & 1);
+    if (tid == 0) { S.n = 0; S.ncand = 0; S.kx = kx; S.ky = ky; S.kz = kz; }
+    __syncthreads();
+    const double lox = p.lo[0][kx], hix = p.edge[0][kx + 1];
+    const double loy = p.lo[1][ky], hiy = p.edge[1][ky + 1];
+    const double loz = p.lo[2][kz], hiz = p.edge[2][kz + 1];
+    const Arrays &A = p.a;
+    // members: the owner cell itself plus the low-side band of its 7 lower neighbours (padded owner
+    // index = cell index + 1), membership decided on the live position (Pore:527-530)
+#pragma unroll 1
+    for (int nb = 0; nb < 8; nb++) {
+        int ox = kx + 1 - (nb >> 2), oy = ky + 1 - ((nb >> 1) & 1), oz = kz + 1 - (nb & 1);
+        int oc = (ox * p.pnc[1] + oy) * p.pnc[2] + oz;
+        int beg = p.cell_start[oc], end = p.cell_start[oc + 1];
+        for (int s = beg + tid; s < end; s += PAIR_THREADS) {
+            if (A.flag[s] & AMC_FLAG_ESC) continue;
+            double x = A.x[s], y = A.y[s], z = A.z[s];
+            if (lox < x && x < hix && loy < y && y < hiy && loz < z && z < hiz) {
+                int k = atomicAdd(&S.n, 1);
+                if (k < AMC_MAX_MEMBERS) { S.x[k] = x; S.y[k] = y; S.z[k] = z; S.id[k] = A.id[s]; S.slot[k] = s; S.src[k] = -1 - nb; }
+            }
+        }
+    }
+    {
+        int ne = *p.esc_count;
+        if (ne > p.esc_cap) ne = p.esc_cap;
+        for (int e = tid; e < ne; e += PAIR_THREADS) {
+            if (p.esc_cell[e * 8 + group] != cell) continue;
+            int s = p.esc_slot[e];
+            int k = atomicAdd(&S.n, 1);
+            if (k < AMC_MAX_MEMBERS) { S.x[k] = A.x[s]; S.y[k] = A.y[s]; S.z[k] = A.z[s]; S.id[k] = A.id[s]; S.slot[k] = s; S.src[k] = e; }
+        }
+    }
+    __syncthreads();
+    if (S.n > AMC_MAX_MEMBERS) {
+        if (tid == 0) { atomicAdd(&p.stats->cell_overflow, 1ull); }
+        __syncthreads();
+        if (tid == 0) S.n = AMC_MAX_MEMBERS;
+        __syncthreads();
+    }
+    if (S.n < 2) return;
+    cell_process(p, S, group, cell);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Cube stage: serial sweep x -> y -> z over the cells with write-back after every cell; the x-layer
+// membership is taken once per x layer, the y-layer membership once per column and the z-layer
+// membership per cell, each from the positions live at that moment (Cube:232-238, 326-336).
+// One CTA walks the cells in reference order; the particle state stays in original index order.
+__global__ void __launch_bounds__(SWEEP_THREADS) k_cube_sweep(const __grid_constant__ P p)
+{
+    __shared__ CellShared S;
+    __shared__ int nx, nxy;
+    const int tid = threadIdx.x;
+    const Arrays &A = p.a;
+    int32_t *lx = p.key, *lxy = p.rank;
+    for (int xl = 0; xl < p.nc[0]; xl++) {
+        if (tid == 0) nx = 0;
+        __syncthreads();
+        {
+            double lo = p.lo[0][xl], hi = p.edge[0][xl + 1];
+            for (int i = tid; i < p.n; i += SWEEP_THREADS) {
+                double v = A.x[i];
+                if (lo < v && v < hi) lx[atomicAdd(&nx, 1)] = i;
+            }
+        }
+        __syncthreads();
+        for (int yl = 0; yl < p.nc[1]; yl++) {
+            if (tid == 0) nxy = 0;
+            __syncthreads();
+            {
+                double lo = p.lo[1][yl], hi = p.edge[1][yl + 1];
+                for (int k = tid; k < nx; k += SWEEP_THREADS) {
+                    int i = lx[k];
+                    double v = A.y[i];
+                    if (lo < v && v < hi) lxy[atomicAdd(&nxy, 1)] = i;
+                }
+            }
+            __syncthreads();
+            for (int zl = 0; zl < p.nc[2]; zl++) {
+                if (tid == 0) { S.n = 0; S.ncand = 0; }
+                __syncthreads();
+                {
+                    double lo = p.lo[2][zl], hi = p.edge[2][zl + 1];
+                    for (int k = tid; k < nxy; k += SWEEP_THREADS) {
+                        int i = lxy[k];
+                        double v = A.z[i];
+                        if (lo < v && v < hi) {
+                            int m = atomicAdd(&S.n, 1);
+                            if (m < AMC_MAX_MEMBERS) { S.x[m] = A.x[i]; S.y[m] = A.y[i]; S.z[m] = v; S.id[m] = i; S.slot[m] = i; S.src[m] = -1; }
+                        }
+                    }
+                }
+                __syncthreads();
+                if (S.n > AMC_MAX_MEMBERS) {
+                    if (tid == 0) { atomicAdd(&p.stats->cell_overflow, 1ull); S.n = AMC_MAX_MEMBERS; }
+                    __syncthreads();
+                }
+                if (S.n >= 2) cell_process(p, S, 0, (xl * p.nc[1] + yl) * p.nc[2] + zl);
+                __syncthreads();
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-RNG parity mode (AMC_KIND_TEMP): one wall case at a time (Temp:693-753)
+// specular cases 1, 2a, 2b applied directly; returns the hit count in stats->wall_hits[c]
+__global__ void __launch_bounds__(ADVECT_THREADS) k_case_specular(const __grid_constant__ P p, const int c)
+{
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= p.n) return;
+    Part q;
+    load_part(p.a, s, q);
+    q.px = p.px[s]; q.py = p.py[s]; q.pz = p.pz[s];
+    if (!temp_mask(p.g, c, q)) return;
+    atomicAdd(&p.stats->wall_hits[c], 1ull);
+    if (p.wall_bits) p.wall_bits[p.a.id[s]] |= (uint16_t)(1u << c);
+    temp_specular(p, c, q);
+    store_part(p.a, s, q);
+}
+// energized cases: list the hits (slot, id, normal, contact height); order fixed up on the host
+__global__ void __launch_bounds__(ADVECT_THREADS) k_case_detect(const __grid_constant__ P p, const int c, int32_t *count,
+                                                                int32_t cap, int32_t *out_slot, int32_t *out_id,
+                                                                double *out_nrm, double *out_colz)
+{
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= p.n) return;
+    Part q;
+    load_part(p.a, s, q);
+    q.px = p.px[s]; q.py = p.py[s]; q.pz = p.pz[s];
+    if (!temp_mask(p.g, c, q)) return;
+    int k = atomicAdd(count, 1);
+    if (k >= cap) return;
+    double t, col[3], nrm[3];
+    if (!temp_contact(p.g, c, q, t, col, nrm)) { nrm[0] = nrm[1] = nrm[2] = col[2] = __longlong_as_double(0x7ff8000000000000ll); }
+    out_slot[k] = (int32_t)s; out_id[k] = p.a.id[s];
+    out_nrm[3 * k] = nrm[0]; out_nrm[3 * k + 1] = nrm[1]; out_nrm[3 * k + 2] = nrm[2];
+    out_colz[k] = col[2];
+}
+__global__ void __launch_bounds__(ADVECT_THREADS) k_case_apply(const __grid_constant__ P p, const int c, int32_t nh,
+                                                               const int32_t *slots, const double *dirs,
+                                                               const double *surf_e, double *out_dpz, double *out_de)
+{
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nh) return;
+    int64_t s = slots[k];
+    Part q;
+    load_part(p.a, s, q);
+    q.px = p.px[s]; q.py = p.py[s]; q.pz = p.pz[s];
+    out_dpz[k] = 0.0; out_de[k] = 0.0;
+    atomicAdd(&p.stats->wall_hits[c], 1ull);
+    if (p.wall_bits) p.wall_bits[p.a.id[s]] |= (uint16_t)(1u << c);
+    double t, col[3], nrm[3], dpz, dE;
+    if (!temp_contact(p.g, c, q, t, col, nrm)) { atomicAdd(&p.stats->errors, 1ull); return; }
+    double dir[3] = {dirs[3 * k], dirs[3 * k + 1], dirs[3 * k + 2]};
+    double Es = c == AMC_CASE_4 ? surf_e[k] : (temp_is_cold(c) ? p.g.E_cold : p.g.E_hot);
+    double alpha = c == AMC_CASE_4 ? p.g.alpha_g : p.g.alpha_c;
+    temp_energized(p, q, t, col, dir, Es, alpha, dpz, dE);
+    out_dpz[k] = dpz; out_de[k] = c == AMC_CASE_4 ? 0.0 : dE;
+    store_part(p.a, s, q);
+}
+__global__ void k_clear_bits(uint16_t *bits, int64_t n)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) bits[i] = 0;
+}

@@ -1,0 +1,183 @@
+/*
+ * amc.h -- C ABI of libamc.so, the B200 (sm_100a) implementation of Argon_Monte_Carlo's
+ * per-timestep hot path (drift -> wall collisions -> recapture -> cell-binned particle-particle
+ * collisions -> mean-free-path / momentum bookkeeping).
+ *
+ * The upstream project is pure Python and has no FFI layer; its de-facto operator boundary is
+ *   (1) the worker entry point  pairwise_particles_in_cell(...)      Open_Air_Pore_MC.py:160-255
+ *       dispatched by pool.starmap over the cells of a colour group  Open_Air_Pore_MC.py:522-549
+ *   (2) the wall operators taking an N-long boolean mask             Open_Air_Pore_MC.py:257-348,
+ *                                                                    Temperature_Pore_MC.py:311-553
+ *   (3) the step loop of each script                                 Open_Air_Pore_MC.py:416-557,
+ *       Temperature_Pore_MC.py:662-853, Open_Air_Cube_MC.py:175-338
+ * Each entry point below names the reference code it replaces.  Plain pointers and sizes only;
+ * host arrays are owned by the caller and copied in/out, all device memory is owned by the handle
+ * and no pointer is retained after a call returns.  Every function returns 0 on success or a
+ * negative AMC_E_* code; amc_last_error() gives the message.  A handle is not thread-safe.
+ * INTEGRATION.md shows the ctypes binding a maintainer of the reference would add.
+ */
+#ifndef AMC_H
+#define AMC_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AMC_ABI_VERSION 1
+
+enum { AMC_OK = 0, AMC_E_INVALID = -1, AMC_E_CUDA = -2, AMC_E_NOMEM = -3, AMC_E_CAPACITY = -4, AMC_E_STATE = -5 };
+
+/* wall geometry (amc_config.kind) */
+enum { AMC_KIND_CUBE = 0,  /* six specular planes, no MFP bookkeeping     Open_Air_Cube_MC.py:192-226 */
+       AMC_KIND_PORE = 1,  /* specular pore walls with MFP bookkeeping    Open_Air_Pore_MC.py:442-485 */
+       AMC_KIND_TEMP = 2   /* specular + energized (accommodating) walls  Temperature_Pore_MC.py:693-753 */ };
+/* particle-particle schedule (amc_config.pp_mode) */
+enum { AMC_PP_GROUPS = 0,  /* 8 colour groups, cells of a group independent   Open_Air_Pore_MC.py:522-549 */
+       AMC_PP_SWEEP = 1    /* serial lexicographic sweep, write-back per cell  Open_Air_Cube_MC.py:232-336 */ };
+/* random directions at energized walls (amc_config.rng_mode) */
+enum { AMC_RNG_DEVICE = 0, /* counter-based Philox4x32-10 on the device (throughput mode) */
+       AMC_RNG_HOST = 1    /* parity mode: host draws via amc_wall_hits_pending / amc_wall_apply_directions */ };
+/* debug taps (amc_config.taps, OR-ed) */
+enum { AMC_TAP_PAIRS = 1, AMC_TAP_WALL_BITS = 2, AMC_TAP_PATHS = 4 };
+
+/* Temp wall cases in evaluation order (Temperature_Pore_MC.py:693-753).  Pore uses the first nine
+ * slots in its own order 1, 2a, 2b, 3cold, 3hot, 4, 5bottom, 5top, 6 (Open_Air_Pore_MC.py:442-485);
+ * Cube uses six: +x, -x, +y, -y, +z, -z (Open_Air_Cube_MC.py:192-226). */
+enum { AMC_CASE_1 = 0, AMC_CASE_2A, AMC_CASE_2B, AMC_CASE_3C, AMC_CASE_3H, AMC_CASE_4, AMC_CASE_5B, AMC_CASE_5T,
+       AMC_CASE_6H, AMC_CASE_6C, AMC_NUM_CASES };
+
+#define AMC_NUM_BINS 200
+
+/* Thresholds of the wall masks, evaluated on the host with the reference's own expressions. */
+typedef struct amc_geom {
+    double argon_mass, argon_radius, collision_range;
+    double R_oa, R_oa_c;   /* open_air_radius, open_air_collision_radius                  Pore:35,67 */
+    double R_p, R_p_c;     /* pore_coated_radius, pore_collision_radius                   Pore:25,69 */
+    double R_g, R_g_c;     /* gap_radius, gap_collision_radius                            Pore:26,68 */
+    double H, oah;         /* total_height, open_air_height                               Pore:39,36 */
+    double z_cold;         /* total_height - open_air_height                              Pore:457 */
+    double z_gb;           /* open_air_height + hot_coating_height                        Pore:465 */
+    double z_gt_pore;      /* total_height - open_air_height - cold_coating_height        Pore:465 */
+    double z_gt;           /* open_air_height + hot_coating_height + gap_height           Pore:371 */
+    double ten_a;          /* 10*argon_radius                                             Pore:358 */
+    double R_oa_sq, R_g_sq, R_p_sq;     /* radii ** 2                                     Pore:363-371 */
+    double zc3, zh3;       /* (H - oah) + a, oah - a                                      Temp:708,713 */
+    double zgt_m, zgb_p;   /* gap_top_height - a, gap_bottom_height + a                   Temp:720 */
+    double R_g_c_sq, R_p_c_sq;          /* collision radii ** 2                           Temp:721,728 */
+    double recap_lo, recap_hi;          /* 50e-9, H - 50e-9                               Temp:599,602 */
+    double E_cold, E_hot;  /* surface_energy_cold / _hot (Debye integrals, host mpmath)   Temp:83-84 */
+    double alpha_c, alpha_g;            /* accommodation coefficients                     Temp:76-77 */
+    double cos85;          /* cos(85*pi/180)                                              Temp:136 */
+} amc_geom;
+
+typedef struct amc_config {
+    int32_t abi_version;   /* AMC_ABI_VERSION */
+    int32_t kind, pp_mode, rng_mode, taps;
+    double dt;             /* timestep                                                    Pore:76 */
+    double cube[3];        /* cube_x, cube_y, cube_z (AMC_KIND_CUBE)                      Cube:26-28 */
+    amc_geom geom;
+    /* collision-cell grid: axis a has nc[a] cells, first cell index c0[a];
+     * edge[a][k] = (c0+k)*d (nc+1 entries) and lo[a][k] = edge[a][k] - band (nc entries) are the two
+     * sides of the reference's strict layer masks                      Pore:527-529, Cube:233-237 */
+    int32_t nc[3], c0[3];
+    const double *edge[3];
+    const double *lo[3];
+    double overlap_sq;     /* smallest double t with sqrt(t) >= collision_range: `sqrt(d2) < cr` <=> `d2 < t` */
+    uint64_t seed;         /* Philox key (AMC_RNG_DEVICE) */
+    const double *cheb_coef; /* Chebyshev fit of surface_energy_gap(z)  Temp:143-152 (AMC_RNG_DEVICE) */
+    int32_t cheb_n;
+    double cheb_zmid, cheb_inv_half;
+    double hist_first, hist_last; /* histogram range (0, 1e-6)                            Pore:575 */
+    const double *hist_edges;     /* np.linspace(first, last, AMC_NUM_BINS+1) */
+    int64_t max_particles;
+    int64_t pair_capacity; /* AMC_TAP_PAIRS: max logged collisions between two amc_clear_taps() calls */
+    int64_t path_capacity; /* AMC_TAP_PATHS: max logged completed paths */
+} amc_config;
+
+/* per-timestep counters: the numbers the reference prints every step (Pore:512-557, Temp:803-853) */
+typedef struct amc_step_stats {
+    int64_t wall_hits[AMC_NUM_CASES]; /* hits per wall case */
+    int64_t wall_collisions;  /* "Num collisions from walls" (Pore: all cases; Temp: energized only) */
+    int64_t pp_collisions;    /* particle-particle collisions resolved */
+    int64_t pair_checks_ref;  /* reference-equivalent distance tests: sum over visited cells of n(n-1)/2 */
+    int64_t pair_checks_exec; /* distance tests actually executed on the device */
+    int64_t oob_after_walls;  /* "particles out of bounds after handling wall collisions" */
+    int64_t oob_after_pp;     /* "... after particle-particle collisions" */
+    int64_t errors;           /* floating-point anomalies (negative discriminant, zero relative speed) */
+    int64_t completed_paths;  /* free paths completed during this step */
+    double dpz, e_cold, e_hot; /* momentum_z_change / energy_transfer_{cold,hot} of this step  Temp:756-758 */
+} amc_step_stats;
+
+typedef struct amc_handle amc_handle;
+
+/* lifetime.  `device`: CUDA ordinal. */
+int amc_create(const amc_config *cfg, int device, amc_handle **out);
+int amc_destroy(amc_handle *h);
+const char *amc_last_error(const amc_handle *h); /* h may be NULL: last error of a failed amc_create */
+int amc_abi_version(void);
+
+/* particle state = the reference's module-global arrays (Pore:385-400), original index order.
+ * dist*, flag may be NULL in amc_set_state (zeros); any output may be NULL in amc_get_state. */
+int amc_set_state(amc_handle *h, int64_t n, const double *x, const double *y, const double *z, const double *vx,
+                  const double *vy, const double *vz, const double *dist, const double *dist_x,
+                  const double *dist_y, const double *dist_z, const uint8_t *flag);
+int amc_get_state(amc_handle *h, double *x, double *y, double *z, double *vx, double *vy, double *vz, double *dist,
+                  double *dist_x, double *dist_y, double *dist_z, uint8_t *flag);
+int64_t amc_num_particles(const amc_handle *h);
+
+/* production entry point: n_steps whole timesteps (body of the loops Pore:416-557 / Temp:662-853 /
+ * Cube:175-338) without host round trips.  stats: n_steps entries or NULL.  AMC_RNG_HOST handles
+ * must be stepped phase by phase instead (see below). */
+int amc_step(amc_handle *h, int32_t n_steps, amc_step_stats *stats);
+
+/* phase-level entry points, for per-phase parity checks (each is synchronous):
+ *   amc_drift      Pore:427-437 / Temp:673-683 / Cube:180-187
+ *   amc_walls      all wall cases in order: Pore:442-485 / Temp:693-753 (device RNG) / Cube:192-226
+ *   amc_recapture  Pore num_out_of_bounds() 354-375 / Temp num_out_of_bounds()+recapture 560-616;
+ *                  *count = Pore: particles teleported; Temp: the report count taken before recapture
+ *   amc_pairs      the whole particle-particle pass Pore:522-549 / Temp:815-842 / Cube:232-336
+ * stats (nullable) receives the counters the phase produces; other fields are zero. */
+int amc_drift(amc_handle *h);
+int amc_walls(amc_handle *h, amc_step_stats *stats);
+int amc_recapture(amc_handle *h, int64_t *count);
+int amc_pairs(amc_handle *h, amc_step_stats *stats);
+
+/* parity hooks for the energized walls (AMC_KIND_TEMP): one wall case at a time, in AMC_CASE_*
+ * order, after amc_drift.  Specular cases (AMC_CASE_1, _2A, _2B): call amc_wall_case.
+ * Energized cases: amc_wall_hits_pending reports the hits in ascending particle index with the
+ * vector the reference hands to random_inbounds_direction (Temp:375,444,514; NaN = the hit raised a
+ * floating-point error in the reference and draws nothing) and the contact height (argument of
+ * surface_energy_gap for AMC_CASE_4, Temp:519); the host draws one direction per valid hit from
+ * its Mersenne-Twister streams (Temp:132-141) and calls amc_wall_apply_directions, which returns
+ * per-hit momentum / energy contributions (dpz[k], de[k]) so the host can sum them in the
+ * reference's sequential order (Temp:385,389).  surf_e: per-hit surface energy, AMC_CASE_4 only. */
+int amc_wall_case(amc_handle *h, int32_t case_id, int64_t *n_hits);
+int amc_wall_hits_pending(amc_handle *h, int32_t case_id, int64_t cap, int64_t *n_hits, int64_t *idx, double *normal3,
+                          double *col_z);
+int amc_wall_apply_directions(amc_handle *h, int32_t case_id, int64_t n_hits, const int64_t *idx, const double *dir3,
+                              const double *surf_e, double *dpz, double *de, int64_t *errors);
+
+/* outputs: completed free paths (the four lists Pore:410-413) as device-side histograms with
+ * np.histogram's uniform-bin rule (Pore:575-596), their count and sums (for the printed means
+ * Pore:565-568).  counts: [4][AMC_NUM_BINS] in the order total, x, y, z. */
+int amc_get_histograms(amc_handle *h, uint64_t *counts, uint64_t *n_paths, double *sums4);
+
+/* debug taps (enabled through amc_config.taps) */
+int amc_get_pair_list(amc_handle *h, int64_t cap, int64_t *n, int64_t *hi, int64_t *lo, int32_t *group, int32_t *cell);
+int amc_get_wall_bits(amc_handle *h, uint16_t *bits);  /* bit c set: AMC_CASE c hit in the last wall phase */
+int amc_get_completed_paths(amc_handle *h, int64_t cap, int64_t *n, double *total, double *cx, double *cy, double *cz);
+int amc_clear_taps(amc_handle *h);
+
+/* set the step counter that keys the device RNG (default: counts amc_step / amc_walls calls from 0) */
+int amc_set_step_index(amc_handle *h, int64_t step);
+
+/* device time (ms, CUDA events on the handle's stream) of the kernels of the last amc_step call:
+ * [0] advect+walls  [1] cell sort (scan+scatter)  [2] pair kernels  [3] recapture/other  [4] whole call.
+ * launches: number of kernel launches in that call. */
+int amc_last_timing(amc_handle *h, double ms[5], int64_t *launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AMC_H */
