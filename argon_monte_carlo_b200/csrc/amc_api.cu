@@ -1,0 +1,664 @@
+// amc_api.cu -- host side of libamc.so: handle, memory, kernel sequencing, the C ABI of include/amc.h.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false -shared -Xcompiler -fPIC
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include "amc_kernels.cuh"
+
+static thread_local std::string g_create_error;
+
+struct amc_handle {
+    amc_config cfg;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    P p;                        // kernel parameter block (device pointers)
+    int64_t cap = 0, n = 0;
+    std::vector<void *> allocs; // every cudaMalloc, freed in amc_destroy
+    StatsDev *d_stats = nullptr; // [stats_cap]
+    int stats_cap = 0;
+    StatsDev *h_stats = nullptr; // pinned
+    int32_t *d_tile_sums = nullptr;
+    int n_buckets = 0;          // padded owner cells + OUT
+    bool have_prior = false;
+    int64_t step_index = 0;
+    // host-RNG parity mode: pending hits of the last amc_wall_hits_pending call
+    int32_t *d_pend_count = nullptr, *d_pend_slot = nullptr, *d_pend_id = nullptr;
+    double *d_pend_nrm = nullptr, *d_pend_colz = nullptr, *d_pend_dirs = nullptr, *d_pend_se = nullptr, *d_pend_dpz = nullptr, *d_pend_de = nullptr;
+    int32_t pend_cap = 0;
+    std::vector<int32_t> pend_slot;
+    std::vector<int64_t> pend_id;
+    int pend_case = -1;
+    // timing
+    std::vector<cudaEvent_t> events;
+    double last_ms[5] = {0, 0, 0, 0, 0};
+    int64_t last_launches = 0;
+    std::string error;
+
+    int fail(int code, const std::string &msg)
+    {
+        error = msg;
+        return code;
+    }
+};
+
+#define CK(call)                                                                                              \
+    do {                                                                                                      \
+        cudaError_t e_ = (call);                                                                              \
+        if (e_ != cudaSuccess)                                                                                \
+            return h->fail(AMC_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));                   \
+    } while (0)
+
+template <typename T> static int dev_alloc(amc_handle *h, T **ptr, size_t count)
+{
+    void *q = nullptr;
+    cudaError_t e = cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T));
+    if (e != cudaSuccess) return h->fail(AMC_E_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    h->allocs.push_back(q);
+    *ptr = (T *)q;
+    return AMC_OK;
+}
+#define ALLOC(ptr, count)                                 \
+    do {                                                  \
+        int rc_ = dev_alloc(h, &(ptr), (size_t)(count));  \
+        if (rc_ != AMC_OK) return rc_;                    \
+    } while (0)
+
+static int alloc_arrays(amc_handle *h, Arrays &a, int64_t n)
+{
+    ALLOC(a.x, n); ALLOC(a.y, n); ALLOC(a.z, n); ALLOC(a.vx, n); ALLOC(a.vy, n); ALLOC(a.vz, n);
+    ALLOC(a.d, n); ALLOC(a.dx, n); ALLOC(a.dy, n); ALLOC(a.dz, n); ALLOC(a.flag, n); ALLOC(a.id, n);
+    return AMC_OK;
+}
+
+static inline unsigned grid_for(int64_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+
+static void stats_to_host(const amc_handle *h, const StatsDev &s, amc_step_stats *o)
+{
+    memset(o, 0, sizeof(*o));
+    int64_t all = 0, energized = 0;
+    for (int c = 0; c < AMC_NUM_CASES; c++) {
+        o->wall_hits[c] = (int64_t)s.wall_hits[c];
+        all += o->wall_hits[c];
+        if (c >= AMC_CASE_3C) energized += o->wall_hits[c];
+    }
+    o->wall_collisions = h->cfg.kind == AMC_KIND_TEMP ? energized : all;
+    o->pp_collisions = (int64_t)s.pp;
+    o->pair_checks_ref = (int64_t)s.checks_ref;
+    o->pair_checks_exec = (int64_t)s.checks_exec;
+    o->oob_after_walls = (int64_t)s.oob_walls;
+    o->oob_after_pp = (int64_t)s.oob_pp;
+    o->errors = (int64_t)s.errors;
+    o->completed_paths = (int64_t)s.paths;
+    o->dpz = ldexp((double)(long long)s.dpz[0], -116) + ldexp((double)(long long)s.dpz[1], -156);
+    o->e_cold = ldexp((double)(long long)s.ecold[0], -108) + ldexp((double)(long long)s.ecold[1], -148);
+    o->e_hot = ldexp((double)(long long)s.ehot[0], -108) + ldexp((double)(long long)s.ehot[1], -148);
+}
+
+static int check_overflow(amc_handle *h, const StatsDev &s)
+{
+    if (s.cell_overflow) return h->fail(AMC_E_CAPACITY, "a collision cell holds more than AMC_MAX_MEMBERS particles");
+    if (s.cand_overflow) return h->fail(AMC_E_CAPACITY, "more than AMC_MAX_CAND simultaneously overlapping pairs in one cell");
+    if (s.esc_overflow) return h->fail(AMC_E_CAPACITY, "escaped-particle list overflow");
+    return AMC_OK;
+}
+
+extern "C" int amc_abi_version(void) { return AMC_ABI_VERSION; }
+
+extern "C" const char *amc_last_error(const amc_handle *h) { return h ? h->error.c_str() : g_create_error.c_str(); }
+
+extern "C" int64_t amc_num_particles(const amc_handle *h) { return h ? h->n : 0; }
+
+extern "C" int amc_destroy(amc_handle *h)
+{
+    if (!h) return AMC_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (void *q : h->allocs) cudaFree(q);
+    for (cudaEvent_t e : h->events) cudaEventDestroy(e);
+    if (h->h_stats) cudaFreeHost(h->h_stats);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return AMC_OK;
+}
+
+static int create_impl(amc_handle *h, const amc_config *cfg, int device)
+{
+    if (cfg->abi_version != AMC_ABI_VERSION) return h->fail(AMC_E_INVALID, "amc_config.abi_version mismatch");
+    if (cfg->kind < AMC_KIND_CUBE || cfg->kind > AMC_KIND_TEMP) return h->fail(AMC_E_INVALID, "bad kind");
+    if (cfg->pp_mode != AMC_PP_GROUPS && cfg->pp_mode != AMC_PP_SWEEP) return h->fail(AMC_E_INVALID, "bad pp_mode");
+    if (cfg->max_particles <= 0 || cfg->max_particles > 0x7fffffffLL) return h->fail(AMC_E_INVALID, "max_particles out of range");
+    for (int a = 0; a < 3; a++) {
+        if (cfg->nc[a] < 1 || !cfg->edge[a] || !cfg->lo[a]) return h->fail(AMC_E_INVALID, "grid tables missing");
+        if (cfg->pp_mode == AMC_PP_GROUPS && (cfg->nc[a] & 1)) return h->fail(AMC_E_INVALID, "colour groups need an even cell count per axis");
+    }
+    if (!cfg->hist_edges) return h->fail(AMC_E_INVALID, "hist_edges missing");
+    if (cfg->kind == AMC_KIND_TEMP && cfg->rng_mode == AMC_RNG_DEVICE && (!cfg->cheb_coef || cfg->cheb_n < 1))
+        return h->fail(AMC_E_INVALID, "device RNG mode needs the Chebyshev table of surface_energy_gap");
+    h->cfg = *cfg;
+    h->device = device;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) return h->fail(AMC_E_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e));
+    CK(cudaSetDevice(device));
+    CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    P &p = h->p;
+    memset(&p, 0, sizeof(p));
+    h->cap = cfg->max_particles;
+    int rc;
+    if ((rc = alloc_arrays(h, p.a, h->cap)) != AMC_OK) return rc;
+    if ((rc = alloc_arrays(h, p.b, h->cap)) != AMC_OK) return rc;
+    ALLOC(p.key, h->cap); ALLOC(p.rank, h->cap);
+    p.kind = cfg->kind; p.pp_mode = cfg->pp_mode; p.dt = cfg->dt;
+    for (int a = 0; a < 3; a++) p.cube[a] = cfg->cube[a];
+    p.g = cfg->geom;
+    p.cr = cfg->geom.collision_range; p.mass = cfg->geom.argon_mass; p.overlap_sq = cfg->overlap_sq;
+    int64_t ncell = 1;
+    for (int a = 0; a < 3; a++) {
+        p.nc[a] = cfg->nc[a]; p.pnc[a] = cfg->nc[a] + 1;
+        ncell *= p.pnc[a];
+        double *de = nullptr, *dl = nullptr;
+        ALLOC(de, cfg->nc[a] + 1); ALLOC(dl, cfg->nc[a]);
+        CK(cudaMemcpy(de, cfg->edge[a], (cfg->nc[a] + 1) * sizeof(double), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(dl, cfg->lo[a], cfg->nc[a] * sizeof(double), cudaMemcpyHostToDevice));
+        p.edge[a] = de; p.lo[a] = dl;
+        p.e0[a] = cfg->edge[a][0];
+        p.inv_d[a] = (double)cfg->nc[a] / (cfg->edge[a][cfg->nc[a]] - cfg->edge[a][0]);
+    }
+    if (ncell + 2 > 0x7fffffffLL) return h->fail(AMC_E_INVALID, "too many cells");
+    p.ncell_pad = (int32_t)ncell;
+    h->n_buckets = (int)ncell + 1;
+    ALLOC(p.cell_count, h->n_buckets + 1); ALLOC(p.cell_start, h->n_buckets + 1);
+    ALLOC(h->d_tile_sums, (h->n_buckets + SCAN_TILE - 1) / SCAN_TILE + 1);
+    p.key0 = (uint32_t)cfg->seed; p.key1 = (uint32_t)(cfg->seed >> 32);
+    if (cfg->cheb_coef && cfg->cheb_n > 0) {
+        double *dc = nullptr;
+        ALLOC(dc, cfg->cheb_n);
+        CK(cudaMemcpy(dc, cfg->cheb_coef, cfg->cheb_n * sizeof(double), cudaMemcpyHostToDevice));
+        p.cheb = dc; p.cheb_n = cfg->cheb_n; p.cheb_zmid = cfg->cheb_zmid; p.cheb_inv_half = cfg->cheb_inv_half;
+    }
+    {
+        double *dh = nullptr;
+        ALLOC(dh, AMC_NUM_BINS + 1);
+        CK(cudaMemcpy(dh, cfg->hist_edges, (AMC_NUM_BINS + 1) * sizeof(double), cudaMemcpyHostToDevice));
+        p.hist_edges = dh; p.hist_first = cfg->hist_first; p.hist_last = cfg->hist_last;
+    }
+    ALLOC(p.hist, 4 * AMC_NUM_BINS); ALLOC(p.path_count, 1); ALLOC(p.path_sums, 8);
+    CK(cudaMemset(p.hist, 0, 4 * AMC_NUM_BINS * sizeof(unsigned long long)));
+    CK(cudaMemset(p.path_count, 0, sizeof(unsigned long long)));
+    CK(cudaMemset(p.path_sums, 0, 8 * sizeof(unsigned long long)));
+    if (cfg->taps & AMC_TAP_PAIRS) {
+        p.pair_cap = std::max<int64_t>(cfg->pair_capacity, 1);
+        ALLOC(p.pair_count, 1); ALLOC(p.pair_hi, p.pair_cap); ALLOC(p.pair_lo, p.pair_cap);
+        ALLOC(p.pair_group, p.pair_cap); ALLOC(p.pair_cell, p.pair_cap);
+        CK(cudaMemset(p.pair_count, 0, sizeof(unsigned long long)));
+    }
+    if (cfg->taps & AMC_TAP_PATHS) {
+        p.path_cap = std::max<int64_t>(cfg->path_capacity, 1);
+        ALLOC(p.tap_path_count, 1);
+        for (int k = 0; k < 4; k++) ALLOC(p.tap_paths[k], p.path_cap);
+        CK(cudaMemset(p.tap_path_count, 0, sizeof(unsigned long long)));
+    }
+    if (cfg->taps & AMC_TAP_WALL_BITS) {
+        ALLOC(p.wall_bits, h->cap);
+        CK(cudaMemset(p.wall_bits, 0, h->cap * sizeof(uint16_t)));
+    }
+    p.esc_cap = (int32_t)std::min<int64_t>(std::max<int64_t>(h->cap / 64, 4096), 1 << 22);
+    ALLOC(p.esc_count, 1); ALLOC(p.esc_slot, p.esc_cap); ALLOC(p.esc_cell, (size_t)p.esc_cap * 8);
+    CK(cudaMemset(p.esc_count, 0, sizeof(int32_t)));
+    CK(cudaMemset(p.esc_cell, 0xff, (size_t)p.esc_cap * 8 * sizeof(int32_t)));
+    h->stats_cap = 256;
+    ALLOC(h->d_stats, h->stats_cap);
+    CK(cudaMallocHost((void **)&h->h_stats, h->stats_cap * sizeof(StatsDev)));
+    p.stats = h->d_stats;
+    if (cfg->kind == AMC_KIND_TEMP && cfg->rng_mode == AMC_RNG_HOST) {
+        h->pend_cap = (int32_t)std::min<int64_t>(h->cap, 1 << 22);
+        ALLOC(h->d_pend_count, 1); ALLOC(h->d_pend_slot, h->pend_cap); ALLOC(h->d_pend_id, h->pend_cap);
+        ALLOC(h->d_pend_nrm, (size_t)h->pend_cap * 3); ALLOC(h->d_pend_colz, h->pend_cap);
+        ALLOC(h->d_pend_dirs, (size_t)h->pend_cap * 3); ALLOC(h->d_pend_se, h->pend_cap);
+        ALLOC(h->d_pend_dpz, h->pend_cap); ALLOC(h->d_pend_de, h->pend_cap);
+    }
+    CK(cudaDeviceSynchronize());
+    return AMC_OK;
+}
+
+extern "C" int amc_create(const amc_config *cfg, int device, amc_handle **out)
+{
+    if (!cfg || !out) { g_create_error = "null argument"; return AMC_E_INVALID; }
+    amc_handle *h = new amc_handle();
+    int rc = create_impl(h, cfg, device);
+    if (rc != AMC_OK) {
+        g_create_error = h->error;
+        amc_destroy(h);
+        *out = nullptr;
+        return rc;
+    }
+    *out = h;
+    return AMC_OK;
+}
+
+static int ensure_prior(amc_handle *h)
+{
+    if (h->have_prior) return AMC_OK;
+    ALLOC(h->p.px, h->cap); ALLOC(h->p.py, h->cap); ALLOC(h->p.pz, h->cap);
+    h->have_prior = true;
+    return AMC_OK;
+}
+
+extern "C" int amc_set_state(amc_handle *h, int64_t n, const double *x, const double *y, const double *z,
+                             const double *vx, const double *vy, const double *vz, const double *dist,
+                             const double *dist_x, const double *dist_y, const double *dist_z, const uint8_t *flag)
+{
+    if (!h) return AMC_E_INVALID;
+    if (n < 0 || n > h->cap) return h->fail(AMC_E_INVALID, "n exceeds max_particles");
+    if (n && (!x || !y || !z || !vx || !vy || !vz)) return h->fail(AMC_E_INVALID, "null position/velocity array");
+    CK(cudaSetDevice(h->device));
+    Arrays &a = h->p.a;
+    const double *src[10] = {x, y, z, vx, vy, vz, dist, dist_x, dist_y, dist_z};
+    double *dst[10] = {a.x, a.y, a.z, a.vx, a.vy, a.vz, a.d, a.dx, a.dy, a.dz};
+    for (int k = 0; k < 10; k++) {
+        if (src[k]) CK(cudaMemcpyAsync(dst[k], src[k], n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        else CK(cudaMemsetAsync(dst[k], 0, n * sizeof(double), h->stream));
+    }
+    if (flag) CK(cudaMemcpyAsync(a.flag, flag, n, cudaMemcpyHostToDevice, h->stream));
+    else CK(cudaMemsetAsync(a.flag, 0, n, h->stream));
+    h->n = n;
+    h->p.n = n;
+    // id = slot: run the un-sort kernel's identity via a tiny fill
+    std::vector<int32_t> ids((size_t)n);
+    for (int64_t i = 0; i < n; i++) ids[(size_t)i] = (int32_t)i;
+    CK(cudaMemcpyAsync(a.id, ids.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return AMC_OK;
+}
+
+// bring the state back to original index order (slot == id); b arrays are scratch between phases
+static int unsort(amc_handle *h)
+{
+    if (h->n == 0) return AMC_OK;
+    k_unsort<<<grid_for(h->n, ADVECT_THREADS), ADVECT_THREADS, 0, h->stream>>>(h->p);
+    CK(cudaGetLastError());
+    std::swap(h->p.a, h->p.b);
+    return AMC_OK;
+}
+
+extern "C" int amc_get_state(amc_handle *h, double *x, double *y, double *z, double *vx, double *vy, double *vz,
+                             double *dist, double *dist_x, double *dist_y, double *dist_z, uint8_t *flag)
+{
+    if (!h) return AMC_E_INVALID;
+    CK(cudaSetDevice(h->device));
+    int rc = unsort(h);
+    if (rc != AMC_OK) return rc;
+    Arrays &a = h->p.a;
+    double *dst[10] = {x, y, z, vx, vy, vz, dist, dist_x, dist_y, dist_z};
+    const double *src[10] = {a.x, a.y, a.z, a.vx, a.vy, a.vz, a.d, a.dx, a.dy, a.dz};
+    for (int k = 0; k < 10; k++)
+        if (dst[k]) CK(cudaMemcpyAsync(dst[k], src[k], h->n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (flag) CK(cudaMemcpyAsync(flag, a.flag, h->n, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return AMC_OK;
+}
+
+// counting sort of the state into owner-cell order; keys/ranks/cell_count must be filled
+static int sort_scatter(amc_handle *h, int64_t *launches)
+{
+    P &p = h->p;
+    int m = h->n_buckets;
+    int ntiles = (m + SCAN_TILE - 1) / SCAN_TILE;
+    k_scan_tiles<<<ntiles, SCAN_THREADS, 0, h->stream>>>(p.cell_count, p.cell_start, h->d_tile_sums, m);
+    k_scan_sums<<<1, SCAN_THREADS, 0, h->stream>>>(h->d_tile_sums, ntiles);
+    k_scan_add<<<ntiles, SCAN_THREADS, 0, h->stream>>>(p.cell_start, h->d_tile_sums, m, (int32_t)h->n);
+    k_scatter<<<grid_for(h->n, ADVECT_THREADS), ADVECT_THREADS, 0, h->stream>>>(p);
+    CK(cudaGetLastError());
+    std::swap(p.a, p.b);
+    if (launches) *launches += 4;
+    return AMC_OK;
+}
+
+static int run_pairs(amc_handle *h, int64_t *launches)
+{
+    P &p = h->p;
+    if (p.pp_mode == AMC_PP_SWEEP) {
+        k_cube_sweep<<<1, SWEEP_THREADS, 0, h->stream>>>(p);
+        if (launches) *launches += 1;
+    } else {
+        k_pp_begin<<<1, 256, 0, h->stream>>>(p);
+        unsigned ncells = (unsigned)((p.nc[0] / 2) * (p.nc[1] / 2) * (p.nc[2] / 2));
+        for (int g = 0; g < 8; g++) k_pairs_group<<<ncells, PAIR_THREADS, 0, h->stream>>>(p, g);
+        if (launches) *launches += 9;
+    }
+    CK(cudaGetLastError());
+    return AMC_OK;
+}
+
+static int ensure_events(amc_handle *h, size_t count)
+{
+    while (h->events.size() < count) {
+        cudaEvent_t e;
+        CK(cudaEventCreate(&e));
+        h->events.push_back(e);
+    }
+    return AMC_OK;
+}
+
+extern "C" int amc_step(amc_handle *h, int32_t n_steps, amc_step_stats *stats)
+{
+    if (!h) return AMC_E_INVALID;
+    if (n_steps < 0) return h->fail(AMC_E_INVALID, "n_steps < 0");
+    if (h->cfg.kind == AMC_KIND_TEMP && h->cfg.rng_mode == AMC_RNG_HOST)
+        return h->fail(AMC_E_STATE, "host-RNG handles are stepped through the phase-level entry points");
+    CK(cudaSetDevice(h->device));
+    P &p = h->p;
+    const bool sweep = p.pp_mode == AMC_PP_SWEEP;
+    const bool has_recap = p.kind != AMC_KIND_CUBE;
+    memset(h->last_ms, 0, sizeof(h->last_ms));
+    h->last_launches = 0;
+    int done = 0;
+    if (sweep && h->n) { // the sweep kernel addresses particles by id: keep slot == id
+        int rc = unsort(h);
+        if (rc != AMC_OK) return rc;
+    }
+    while (done < n_steps) {
+        int chunk = std::min(n_steps - done, h->stats_cap);
+        int rc = ensure_events(h, (size_t)chunk * 4 + 1);
+        if (rc != AMC_OK) return rc;
+        CK(cudaMemsetAsync(h->d_stats, 0, chunk * sizeof(StatsDev), h->stream));
+        CK(cudaEventRecord(h->events[0], h->stream));
+        for (int s = 0; s < chunk; s++) {
+            p.stats = h->d_stats + s;
+            p.step = h->step_index++;
+            if (h->n > 0) {
+                int phase = PH_DRIFT | PH_WALLS | (has_recap ? PH_RECAP : 0) | (sweep ? 0 : PH_KEYS);
+                if (!sweep) CK(cudaMemsetAsync(p.cell_count, 0, (h->n_buckets + 1) * sizeof(int32_t), h->stream));
+                k_advect<<<grid_for(h->n, ADVECT_THREADS), ADVECT_THREADS, 0, h->stream>>>(p, phase);
+                h->last_launches += 1;
+                CK(cudaEventRecord(h->events[4 * s + 1], h->stream));
+                if (!sweep) { rc = sort_scatter(h, &h->last_launches); if (rc != AMC_OK) return rc; }
+                CK(cudaEventRecord(h->events[4 * s + 2], h->stream));
+                rc = run_pairs(h, &h->last_launches);
+                if (rc != AMC_OK) return rc;
+                CK(cudaEventRecord(h->events[4 * s + 3], h->stream));
+                if (has_recap) {
+                    k_recapture_post<<<grid_for(h->n, ADVECT_THREADS), ADVECT_THREADS, 0, h->stream>>>(p);
+                    h->last_launches += 1;
+                }
+                CK(cudaEventRecord(h->events[4 * s + 4], h->stream));
+            }
+        }
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(h->h_stats, h->d_stats, chunk * sizeof(StatsDev), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        if (h->n > 0)
+            for (int s = 0; s < chunk; s++) {
+                float ms;
+                for (int k = 0; k < 4; k++) {
+                    CK(cudaEventElapsedTime(&ms, h->events[4 * s + k], h->events[4 * s + k + 1]));
+                    h->last_ms[k] += ms;
+                }
+            }
+        for (int s = 0; s < chunk; s++) {
+            rc = check_overflow(h, h->h_stats[s]);
+            if (rc != AMC_OK) return rc;
+            if (stats) stats_to_host(h, h->h_stats[s], stats + done + s);
+        }
+        done += chunk;
+    }
+    h->last_ms[4] = h->last_ms[0] + h->last_ms[1] + h->last_ms[2] + h->last_ms[3];
+    p.stats = h->d_stats;
+    return AMC_OK;
+}
+
+// ---- phase-level entry points -------------------------------------------------------------------
+static int phase_begin(amc_handle *h)
+{
+    CK(cudaSetDevice(h->device));
+    h->p.stats = h->d_stats;
+    CK(cudaMemsetAsync(h->d_stats, 0, sizeof(StatsDev), h->stream));
+    return AMC_OK;
+}
+static int phase_end(amc_handle *h, amc_step_stats *stats)
+{
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(h->h_stats, h->d_stats, sizeof(StatsDev), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    int rc = check_overflow(h, h->h_stats[0]);
+    if (rc != AMC_OK) return rc;
+    if (stats) stats_to_host(h, h->h_stats[0], stats);
+    return AMC_OK;
+}
+
+extern "C" int amc_drift(amc_handle *h)
+{
+    if (!h) return AMC_E_INVALID;
+    int rc = phase_begin(h);
+    if (rc != AMC_OK) return rc;
+    if ((rc = ensure_prior(h)) != AMC_OK) return rc;
+    if (h->n) k_advect<<<grid_for(h->n, ADVECT_THREADS), ADVECT_THREADS, 0, h->stream>>>(h->p, PH_DRIFT | PH_SAVE_PRIOR);
+    if (h->p.wall_bits) CK(cudaMemsetAsync(h->p.wall_bits, 0, h->cap * sizeof(uint16_t), h->stream));
+    return phase_end(h, nullptr);
+}
+
+extern "C" int amc_walls(amc_handle *h, amc_step_stats *stats)
+{
+    if (!h) return AMC_E_INVALID;
+    if (h->cfg.kind == AMC_KIND_TEMP && h->cfg.rng_mode == AMC_RNG_HOST)
+        return h->fail(AMC_E_STATE, "host-RNG handles apply walls case by case (amc_wall_case / amc_wall_hits_pending)");
+    int rc = phase_begin(h);
+    if (rc != AMC_OK) return rc;
+    if ((rc = ensure_prior(h)) != AMC_OK) return rc;
+    h->p.step = h->step_index++;
+    if (h->n) k_advect<<<grid_for(h->n, ADVECT_THREADS), ADVECT_THREADS, 0, h->stream>>>(h->p, PH_WALLS | PH_LOAD_PRIOR);
+    return phase_end(h, stats);
+}
+
+extern "C" int amc_recapture(amc_handle *h, int64_t *count)
+{
+    if (!h) return AMC_E_INVALID;
+    int rc = phase_begin(h);
+    if (rc != AMC_OK) return rc;
+    if (h->n && h->cfg.kind != AMC_KIND_CUBE)
+        k_recapture_post<<<grid_for(h->n, ADVECT_THREADS), ADVECT_THREADS, 0, h->stream>>>(h->p);
+    amc_step_stats st;
+    rc = phase_end(h, &st);
+    if (count) *count = st.oob_after_pp;
+    return rc;
+}
+
+extern "C" int amc_pairs(amc_handle *h, amc_step_stats *stats)
+{
+    if (!h) return AMC_E_INVALID;
+    int rc = phase_begin(h);
+    if (rc != AMC_OK) return rc;
+    P &p = h->p;
+    if (h->n) {
+        if (p.pp_mode == AMC_PP_SWEEP) {
+            if ((rc = unsort(h)) != AMC_OK) return rc;
+        } else {
+            CK(cudaMemsetAsync(p.cell_count, 0, (h->n_buckets + 1) * sizeof(int32_t), h->stream));
+            k_advect<<<grid_for(h->n, ADVECT_THREADS), ADVECT_THREADS, 0, h->stream>>>(p, PH_KEYS);
+            if ((rc = sort_scatter(h, nullptr)) != AMC_OK) return rc;
+        }
+        if ((rc = run_pairs(h, nullptr)) != AMC_OK) return rc;
+    }
+    return phase_end(h, stats);
+}
+
+// ---- host-RNG parity hooks ----------------------------------------------------------------------
+extern "C" int amc_wall_case(amc_handle *h, int32_t c, int64_t *n_hits)
+{
+    if (!h) return AMC_E_INVALID;
+    if (h->cfg.kind != AMC_KIND_TEMP) return h->fail(AMC_E_STATE, "amc_wall_case: AMC_KIND_TEMP only");
+    if (c < AMC_CASE_1 || c > AMC_CASE_2B) return h->fail(AMC_E_INVALID, "amc_wall_case handles the specular cases 1, 2a, 2b");
+    if (!h->have_prior) return h->fail(AMC_E_STATE, "call amc_drift first");
+    int rc = phase_begin(h);
+    if (rc != AMC_OK) return rc;
+    if (h->n) k_case_specular<<<grid_for(h->n, ADVECT_THREADS), ADVECT_THREADS, 0, h->stream>>>(h->p, c);
+    amc_step_stats st;
+    rc = phase_end(h, &st);
+    if (n_hits) *n_hits = st.wall_hits[c];
+    return rc;
+}
+
+extern "C" int amc_wall_hits_pending(amc_handle *h, int32_t c, int64_t cap, int64_t *n_hits, int64_t *idx,
+                                     double *normal3, double *col_z)
+{
+    if (!h) return AMC_E_INVALID;
+    if (h->cfg.kind != AMC_KIND_TEMP || h->cfg.rng_mode != AMC_RNG_HOST) return h->fail(AMC_E_STATE, "not a host-RNG Temp handle");
+    if (c < AMC_CASE_3C || c >= AMC_NUM_CASES) return h->fail(AMC_E_INVALID, "energized cases only");
+    if (!h->have_prior) return h->fail(AMC_E_STATE, "call amc_drift first");
+    int rc = phase_begin(h);
+    if (rc != AMC_OK) return rc;
+    CK(cudaMemsetAsync(h->d_pend_count, 0, sizeof(int32_t), h->stream));
+    if (h->n)
+        k_case_detect<<<grid_for(h->n, ADVECT_THREADS), ADVECT_THREADS, 0, h->stream>>>(h->p, c, h->d_pend_count, h->pend_cap, h->d_pend_slot,
+                                                                                      h->d_pend_id, h->d_pend_nrm, h->d_pend_colz);
+    CK(cudaGetLastError());
+    int32_t cnt = 0;
+    CK(cudaMemcpyAsync(&cnt, h->d_pend_count, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (cnt > h->pend_cap) return h->fail(AMC_E_CAPACITY, "pending-hit list overflow");
+    std::vector<int32_t> slot(cnt), id(cnt);
+    std::vector<double> nrm((size_t)cnt * 3), colz(cnt);
+    if (cnt) {
+        CK(cudaMemcpy(slot.data(), h->d_pend_slot, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(id.data(), h->d_pend_id, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(nrm.data(), h->d_pend_nrm, (size_t)cnt * 3 * sizeof(double), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(colz.data(), h->d_pend_colz, cnt * sizeof(double), cudaMemcpyDeviceToHost));
+    }
+    std::vector<int32_t> order(cnt);
+    for (int k = 0; k < cnt; k++) order[k] = k;
+    std::sort(order.begin(), order.end(), [&](int a, int b) { return id[a] < id[b]; }); // ascending particle index
+    h->pend_slot.assign(cnt, 0);
+    h->pend_id.assign(cnt, 0);
+    h->pend_case = c;
+    if (n_hits) *n_hits = cnt;
+    if (cnt > cap) return h->fail(AMC_E_CAPACITY, "caller buffers too small for the pending hits");
+    for (int k = 0; k < cnt; k++) {
+        int o = order[k];
+        h->pend_slot[k] = slot[o];
+        h->pend_id[k] = id[o];
+        if (idx) idx[k] = id[o];
+        if (normal3) { normal3[3 * k] = nrm[3 * o]; normal3[3 * k + 1] = nrm[3 * o + 1]; normal3[3 * k + 2] = nrm[3 * o + 2]; }
+        if (col_z) col_z[k] = colz[o];
+    }
+    return AMC_OK;
+}
+
+extern "C" int amc_wall_apply_directions(amc_handle *h, int32_t c, int64_t n_hits, const int64_t *idx, const double *dir3,
+                                         const double *surf_e, double *dpz, double *de, int64_t *errors)
+{
+    if (!h) return AMC_E_INVALID;
+    if (h->pend_case != c || (int64_t)h->pend_id.size() != n_hits) return h->fail(AMC_E_STATE, "apply does not match the last amc_wall_hits_pending call");
+    for (int64_t k = 0; k < n_hits; k++)
+        if (idx && idx[k] != h->pend_id[k]) return h->fail(AMC_E_STATE, "hit indices differ from the pending list");
+    if (c == AMC_CASE_4 && n_hits && !surf_e) return h->fail(AMC_E_INVALID, "case 4 needs per-hit surface energies");
+    int rc = phase_begin(h);
+    if (rc != AMC_OK) return rc;
+    h->pend_case = -1;
+    if (n_hits) {
+        CK(cudaMemcpyAsync(h->d_pend_slot, h->pend_slot.data(), n_hits * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->d_pend_dirs, dir3, (size_t)n_hits * 3 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        if (surf_e) CK(cudaMemcpyAsync(h->d_pend_se, surf_e, n_hits * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        k_case_apply<<<grid_for(n_hits, ADVECT_THREADS), ADVECT_THREADS, 0, h->stream>>>(h->p, c, (int32_t)n_hits, h->d_pend_slot, h->d_pend_dirs,
+                                                                                        h->d_pend_se, h->d_pend_dpz, h->d_pend_de);
+        if (dpz) CK(cudaMemcpyAsync(dpz, h->d_pend_dpz, n_hits * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        if (de) CK(cudaMemcpyAsync(de, h->d_pend_de, n_hits * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    }
+    amc_step_stats st;
+    rc = phase_end(h, &st);
+    if (errors) *errors = st.errors;
+    return rc;
+}
+
+// ---- outputs and taps ---------------------------------------------------------------------------
+extern "C" int amc_get_histograms(amc_handle *h, uint64_t *counts, uint64_t *n_paths, double *sums4)
+{
+    if (!h) return AMC_E_INVALID;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    if (counts) CK(cudaMemcpy(counts, h->p.hist, 4 * AMC_NUM_BINS * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    if (n_paths) CK(cudaMemcpy(n_paths, h->p.path_count, sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    if (sums4) {
+        unsigned long long limbs[8];
+        CK(cudaMemcpy(limbs, h->p.path_sums, sizeof(limbs), cudaMemcpyDeviceToHost));
+        for (int k = 0; k < 4; k++)
+            sums4[k] = ldexp((double)(long long)limbs[2 * k], -49) + ldexp((double)(long long)limbs[2 * k + 1], -89);
+    }
+    return AMC_OK;
+}
+
+extern "C" int amc_get_pair_list(amc_handle *h, int64_t cap, int64_t *n, int64_t *hi, int64_t *lo, int32_t *group, int32_t *cell)
+{
+    if (!h) return AMC_E_INVALID;
+    if (!h->p.pair_count) return h->fail(AMC_E_STATE, "AMC_TAP_PAIRS not enabled");
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    unsigned long long cnt = 0;
+    CK(cudaMemcpy(&cnt, h->p.pair_count, sizeof(cnt), cudaMemcpyDeviceToHost));
+    if (n) *n = (int64_t)cnt;
+    if ((int64_t)cnt > h->p.pair_cap) return h->fail(AMC_E_CAPACITY, "pair tap overflow (raise pair_capacity)");
+    if ((int64_t)cnt > cap) return h->fail(AMC_E_CAPACITY, "caller buffers too small for the pair list");
+    if (cnt) {
+        if (hi) CK(cudaMemcpy(hi, h->p.pair_hi, cnt * sizeof(int64_t), cudaMemcpyDeviceToHost));
+        if (lo) CK(cudaMemcpy(lo, h->p.pair_lo, cnt * sizeof(int64_t), cudaMemcpyDeviceToHost));
+        if (group) CK(cudaMemcpy(group, h->p.pair_group, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        if (cell) CK(cudaMemcpy(cell, h->p.pair_cell, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    }
+    return AMC_OK;
+}
+
+extern "C" int amc_get_wall_bits(amc_handle *h, uint16_t *bits)
+{
+    if (!h) return AMC_E_INVALID;
+    if (!h->p.wall_bits) return h->fail(AMC_E_STATE, "AMC_TAP_WALL_BITS not enabled");
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(bits, h->p.wall_bits, h->n * sizeof(uint16_t), cudaMemcpyDeviceToHost));
+    return AMC_OK;
+}
+
+extern "C" int amc_get_completed_paths(amc_handle *h, int64_t cap, int64_t *n, double *total, double *cx, double *cy, double *cz)
+{
+    if (!h) return AMC_E_INVALID;
+    if (!h->p.tap_path_count) return h->fail(AMC_E_STATE, "AMC_TAP_PATHS not enabled");
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    unsigned long long cnt = 0;
+    CK(cudaMemcpy(&cnt, h->p.tap_path_count, sizeof(cnt), cudaMemcpyDeviceToHost));
+    if (n) *n = (int64_t)cnt;
+    if ((int64_t)cnt > h->p.path_cap) return h->fail(AMC_E_CAPACITY, "path tap overflow (raise path_capacity)");
+    if ((int64_t)cnt > cap) return h->fail(AMC_E_CAPACITY, "caller buffers too small for the path list");
+    double *dst[4] = {total, cx, cy, cz};
+    for (int k = 0; k < 4; k++)
+        if (dst[k] && cnt) CK(cudaMemcpy(dst[k], h->p.tap_paths[k], cnt * sizeof(double), cudaMemcpyDeviceToHost));
+    return AMC_OK;
+}
+
+extern "C" int amc_clear_taps(amc_handle *h)
+{
+    if (!h) return AMC_E_INVALID;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->p.pair_count) CK(cudaMemset(h->p.pair_count, 0, sizeof(unsigned long long)));
+    if (h->p.tap_path_count) CK(cudaMemset(h->p.tap_path_count, 0, sizeof(unsigned long long)));
+    if (h->p.wall_bits) CK(cudaMemset(h->p.wall_bits, 0, h->cap * sizeof(uint16_t)));
+    return AMC_OK;
+}
+
+extern "C" int amc_set_step_index(amc_handle *h, int64_t step)
+{
+    if (!h) return AMC_E_INVALID;
+    h->step_index = step;
+    return AMC_OK;
+}
+
+extern "C" int amc_last_timing(amc_handle *h, double ms[5], int64_t *launches)
+{
+    if (!h) return AMC_E_INVALID;
+    if (ms) memcpy(ms, h->last_ms, sizeof(h->last_ms));
+    if (launches) *launches = h->last_launches;
+    return AMC_OK;
+}
