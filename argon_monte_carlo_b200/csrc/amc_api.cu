@@ -267,10 +267,8 @@ extern "C" int amc_set_state(amc_handle *h, int64_t n, const double *x, const do
     else CK(cudaMemsetAsync(a.flag, 0, n, h->stream));
     h->n = n;
     h->p.n = n;
-    // id = slot: run the un-sort kernel's identity via a tiny fill
-    std::vector<int32_t> ids((size_t)n);
-    for (int64_t i = 0; i < n; i++) ids[(size_t)i] = (int32_t)i;
-    CK(cudaMemcpyAsync(a.id, ids.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    if (n) k_iota<<<grid_for(n, ADVECT_THREADS), ADVECT_THREADS, 0, h->stream>>>(a.id, n); // slot == particle index
+    CK(cudaGetLastError());
     CK(cudaStreamSynchronize(h->stream));
     return AMC_OK;
 }

@@ -545,8 +545,8 @@ __global__ void __launch_bounds__(ADVECT_THREADS) k_case_apply(const __grid_cons
     out_dpz[k] = dpz; out_de[k] = c == AMC_CASE_4 ? 0.0 : dE;
     store_part(p.a, s, q);
 }
-__global__ void k_clear_bits(uint16_t *bits, int64_t n)
+__global__ void k_iota(int32_t *ids, int64_t n)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) bits[i] = 0;
+    if (i < n) ids[i] = (int32_t)i;
 }

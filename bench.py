@@ -1,0 +1,303 @@
+#!/usr/bin/env python
+"""Benchmark of the per-timestep hard-sphere collision loop (BASELINE.json metric:
+collision-resolved particle-steps/s at 1/2/4/8 B200 + fraction of the HBM roofline).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                  [--workload temp_pore|pore_ref] [--particles-per-gpu M]
+
+One "step" = one whole timestep (drift, walls, recapture, cell sort, the 8-colour-group
+particle-particle pass, recapture, MFP / momentum bookkeeping) over all particles of the job.
+
+Workload (config.workload): a synthetic Maxwellian argon gas in the energized thruster-pore
+geometry of Temperature_Pore_MC.py, every length scaled so that each GPU holds
+--particles-per-gpu particles (default 12.5 M; at 8 GPUs that is BASELINE.json's 100 M-particle
+config 5).  The state (1 GB per GPU at fp64) is far larger than the 126 MB L2, so consecutive
+steps never re-read a warm cache.  `also` carries the same measurement for config 2
+(Open_Air_Pore_MC.py at the reference particle count, L2 flushed between timed steps).
+
+--impl reference: the reference's CPU implementation of the path, timed on the host cores.  The
+upstream project is pure Python and cannot travel to the GPU box, so this arm times the C port of
+its algorithm (oracle/amc_oracle.c, OpenMP over the cells of a colour group) on a bounded sample
+of the same workload; its measured Python multiprocessing rate is quoted in BASELINE.md.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+B_STEP = 162.0      # algorithmic bytes per particle-step, fp64 state read + written once
+B_PAIR = 32.0       # algorithmic bytes per particle for the pair kernel: 3 x f64 position + cell header
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for k, nm in enumerate(names):
+                    if r[3 + k].lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def scaled_temp_config(total_particles):
+    from argon_monte_carlo_b200 import config
+    base = 557649
+    scale = (total_particles / base) ** (1.0 / 3.0)
+    cfg = config.pore_config(True, scale=scale)
+    return cfg, scale
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from argon_monte_carlo_b200 import amc, config, init_state
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    hbm_peak, peak_src = measured_peaks()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---------------------------------------------------------------- main workload
+    m = args.particles_per_gpu
+    cfg, scale = scaled_temp_config(m)          # each rank: one domain of m particles (weak scaling)
+    state = init_state.synthetic_pore_state(cfg, seed=17 + rank)
+    n = len(state[0])
+    sim = amc.Simulation(cfg, seed=17 + rank, device=local, max_particles=n)
+    sim.set_state(*state)
+    for _ in range(args.warmup):
+        sim.step_quiet(1)
+    clocks = ClockSampler(local)
+    barrier()
+    clocks.start()
+    t0 = time.perf_counter()
+    stats = sim.step(args.steps)
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    ms, launches = sim.last_timing()
+    barrier()
+    clk = clocks.stop()
+    dev_ms = max_over_ranks(ms[4])
+    total_particles = sum_over_ranks(float(n))
+    value = total_particles * args.steps / (dev_ms * 1e-3)
+    pair_ms = ms[2] / args.steps
+    checks_ref = float(np.mean([s["pair_checks_ref"] for s in stats]))
+    collisions = float(np.mean([s["collisions"] for s in stats]))
+    roofline = {"bound": "hbm", "kernel": "k_pairs_group (8 launches per step)",
+                "achieved": B_PAIR * n / (pair_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                "peak_source": peak_src, "traffic": None}
+    roofline["frac"] = roofline["achieved"] / hbm_peak
+    whole = {"achieved": B_STEP * n * args.steps / (ms[4] * 1e-3) / 1e9, "unit": "GB/s"}
+    whole["frac"] = whole["achieved"] / hbm_peak
+
+    # ---------------------------------------------------------------- e2e: host buffers in and out every step
+    keys = ("x", "y", "z", "vx", "vy", "vz", "dist", "dist_x", "dist_y", "dist_z")
+    pinned = {k: torch.empty(n, dtype=torch.float64).pin_memory() for k in keys}
+    pinned["flag"] = torch.empty(n, dtype=torch.uint8).pin_memory()
+    host = {k: v.numpy() for k, v in pinned.items()}
+    sim.get_state(host)
+    e2e_steps = max(1, min(args.steps, 5))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        sim.set_state(*[host[k] for k in keys], flag=host["flag"])
+        sim.step_quiet(1)
+        sim.get_state(host)
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    bytes_io = n * 81
+    e2e = {"value": total_particles * e2e_steps / e2e_s, "unit": "particle-steps/s", "steps": e2e_steps,
+           "h2d_bytes_per_step": bytes_io, "d2h_bytes_per_step": bytes_io}
+    sim.close()
+
+    out = {
+        "metric": "collision-resolved particle-steps/s", "value": value, "unit": "particle-steps/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "temp_pore_scaled: energized thruster pore (Temperature_Pore_MC geometry x %.3f), "
+                               "%d particles per GPU, device RNG; state %.2f GB per GPU > L2" % (scale, n, n * 85 / 1e9),
+                   "particles_total": int(total_particles), "cells": list(cfg.grid.nc),
+                   "parallelism": "1 domain per GPU" if world == 1 else "%d independent domains (replicas)" % world,
+                   "l2": "inputs larger than L2"},
+        "clocks": clk, "e2e": e2e, "gpu_launches": launches,
+        "roofline": roofline, "roofline_whole_step": whole,
+        "phases_ms_per_step": {"advect_walls": ms[0] / args.steps, "cell_sort": ms[1] / args.steps,
+                               "pairs": ms[2] / args.steps, "recapture": ms[3] / args.steps},
+        "collision_checks_per_s": {"reference_equivalent": checks_ref * world / (dev_ms / args.steps * 1e-3)},
+        "collisions_per_step": collisions, "wall_s": wall,
+    }
+
+    # ---------------------------------------------------------------- config 2 beside it (rank 0, N = 1 only)
+    if rank == 0 and world == 1 and not args.no_also:
+        out["also"] = bench_pore_ref(args, hbm_peak)
+    if rank == 0 and world == 1 and not args.no_cpu:
+        out["cpu_baseline"] = cpu_baseline(steps=8, warmup=2)
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_pore_ref(args, hbm_peak):
+    """BASELINE.json config 2: Open_Air_Pore_MC.py, reference particle count, reference seeds."""
+    import torch
+    from argon_monte_carlo_b200 import amc, config, init_state
+    cfg = config.pore_config(False)
+    state = init_state.pore_initial_state(cfg)
+    sim = amc.Simulation(cfg)
+    sim.set_state(*state)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
+    for _ in range(max(args.warmup, 3)):
+        sim.step_quiet(1)
+    tot = np.zeros(5)
+    k = max(args.steps, 10)
+    for _ in range(k):
+        flush.fill_(1)                      # write 512 MB > 126 MB L2 between timed steps
+        torch.cuda.synchronize()
+        sim.step_quiet(1)
+        ms, launches = sim.last_timing()
+        tot += np.array(ms)
+    n = len(state[0])
+    sim.close()
+    return {"workload": "pore_ref: Open_Air_Pore_MC.py, N=%d, seeds 17, L2 flushed between timed steps" % n,
+            "value": n * k / (tot[4] * 1e-3), "unit": "particle-steps/s", "ms_per_step": tot[4] / k,
+            "phases_ms_per_step": {"advect_walls": tot[0] / k, "cell_sort": tot[1] / k, "pairs": tot[2] / k,
+                                   "recapture": tot[3] / k},
+            "launches_per_step": launches, "steps": k}
+
+
+def cpu_baseline(steps, warmup, particles=None):
+    """The oracle port on the host cores, on a bounded sample of the workload: the energized pore at
+    the reference particle count (same density, cell size and step as the GPU run)."""
+    from oracle import oracle as O, steps as S
+    from argon_monte_carlo_b200 import config, init_state
+    O.set_ref_mode(False)
+    cfg = config.pore_config(True)
+    cheb = config.gap_energy_chebyshev(cfg, 16)
+    st = O.ParticleState(*init_state.synthetic_pore_state(cfg, seed=17))
+    for k in range(warmup):
+        S.temp_step_philox(st, cfg, 17, k, cheb)
+    t0 = time.perf_counter()
+    for k in range(steps):
+        S.temp_step_philox(st, cfg, 17, warmup + k, cheb)
+    dt = time.perf_counter() - t0
+    return {"value": st.n * steps / dt, "unit": "particle-steps/s", "cores": O.num_threads(), "kind": "port",
+            "sample": "C port of the reference algorithm (oracle/amc_oracle.c, OpenMP over cells), energized pore at "
+                      "%d particles, %d steps; the unmodified Python reference measured 6.4-7.1e3 particle-steps/s "
+                      "on 8 cores (BASELINE.md)" % (st.n, steps), "ms_per_step": dt / steps * 1e3}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    steps = max(1, min(args.steps, 20))
+    cb = cpu_baseline(steps=steps, warmup=min(args.warmup, 3))
+    cfg, scale = scaled_temp_config(args.particles_per_gpu)
+    out = {"impl": "reference", "metric": "collision-resolved particle-steps/s", "value": cb["value"],
+           "unit": "particle-steps/s", "n_gpus": world, "steps": steps, "warmup": min(args.warmup, 3),
+           "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f64", "data": "synthetic",
+           "config": {"workload": "temp_pore_scaled (bounded sample: the same energized pore at the reference size, "
+                                  "557,649 particles; throughput per particle is size-independent at fixed density)"},
+           "cpu_baseline": cb,
+           "e2e": {"value": cb["value"], "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--particles-per-gpu", type=int, default=12_500_000)
+    ap.add_argument("--no-also", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
