@@ -25,6 +25,7 @@ struct amc_handle {
     int n_buckets = 0;          // padded owner cells + OUT
     bool have_prior = false;
     int64_t step_index = 0;
+    int pair_grid = 148 * 5;    // persistent CTAs of k_pairs_group: SMs x resident CTAs per SM
     // host-RNG parity mode: pending hits of the last amc_wall_hits_pending call
     int32_t *d_pend_count = nullptr, *d_pend_slot = nullptr, *d_pend_id = nullptr;
     double *d_pend_nrm = nullptr, *d_pend_colz = nullptr, *d_pend_dirs = nullptr, *d_pend_se = nullptr, *d_pend_dpz = nullptr, *d_pend_de = nullptr;
@@ -206,6 +207,13 @@ static int create_impl(amc_handle *h, const amc_config *cfg, int device)
         ALLOC(p.wall_bits, h->cap);
         CK(cudaMemset(p.wall_bits, 0, h->cap * sizeof(uint16_t)));
     }
+    {
+        int64_t per_group = (int64_t)(cfg->nc[0] / 2 + 1) * (cfg->nc[1] / 2 + 1) * (cfg->nc[2] / 2 + 1);
+        p.wl_stride = (int32_t)per_group;
+        ALLOC(p.wl, per_group * 8); ALLOC(p.wl_count, 8); ALLOC(p.cell_active, per_group * 8);
+        CK(cudaMemset(p.wl_count, 0, 8 * sizeof(int32_t)));
+        CK(cudaMemset(p.cell_active, 0, per_group * 8 * sizeof(int32_t)));
+    }
     p.esc_cap = (int32_t)std::min<int64_t>(std::max<int64_t>(h->cap / 64, 4096), 1 << 22);
     ALLOC(p.esc_count, 1); ALLOC(p.esc_slot, p.esc_cap); ALLOC(p.esc_cell, (size_t)p.esc_cap * 8);
     CK(cudaMemset(p.esc_count, 0, sizeof(int32_t)));
@@ -220,6 +228,13 @@ static int create_impl(amc_handle *h, const amc_config *cfg, int device)
         ALLOC(h->d_pend_nrm, (size_t)h->pend_cap * 3); ALLOC(h->d_pend_colz, h->pend_cap);
         ALLOC(h->d_pend_dirs, (size_t)h->pend_cap * 3); ALLOC(h->d_pend_se, h->pend_cap);
         ALLOC(h->d_pend_dpz, h->pend_cap); ALLOC(h->d_pend_de, h->pend_cap);
+    }
+    {
+        int sms = 0, per_sm = 0;
+        CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+        CK(cudaFuncSetAttribute(k_pairs_group, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pairs_group, PAIR_THREADS, 0));
+        h->pair_grid = std::max(1, sms * std::max(per_sm, 1));
     }
     CK(cudaDeviceSynchronize());
     return AMC_OK;
@@ -324,9 +339,12 @@ static int run_pairs(amc_handle *h, int64_t *launches)
         if (launches) *launches += 1;
     } else {
         k_pp_begin<<<1, 256, 0, h->stream>>>(p);
-        unsigned ncells = (unsigned)((p.nc[0] / 2) * (p.nc[1] / 2) * (p.nc[2] / 2));
-        for (int g = 0; g < 8; g++) k_pairs_group<<<ncells, PAIR_THREADS, 0, h->stream>>>(p, g);
-        if (launches) *launches += 9;
+        CK(cudaMemsetAsync(p.wl_count, 0, 8 * sizeof(int32_t), h->stream));
+        int ncell = p.nc[0] * p.nc[1] * p.nc[2];
+        k_build_worklist<<<grid_for(ncell, ADVECT_THREADS), ADVECT_THREADS, 0, h->stream>>>(p);
+        unsigned grid = (unsigned)std::min<int64_t>((int64_t)h->pair_grid, std::max<int64_t>(ncell / 8, 1));
+        for (int g = 0; g < 8; g++) k_pairs_group<<<grid, PAIR_THREADS, 0, h->stream>>>(p, g);
+        if (launches) *launches += 10;
     }
     CK(cudaGetLastError());
     return AMC_OK;

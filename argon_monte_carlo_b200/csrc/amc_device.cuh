@@ -12,8 +12,10 @@
 #define AMC_FLAG_PATH 1u /* full_path_traveled (Pore:392) */
 #define AMC_FLAG_ESC 2u  /* transient: particle left its sorted owner cell during the pair pass */
 
-#define AMC_MAX_MEMBERS 1024 /* particles per reference cell incl. overlap band */
+#define AMC_MAX_MEMBERS 768  /* particles per reference cell incl. overlap band (reference: <= 308) */
 #define AMC_MAX_CAND 256     /* simultaneously overlapping pairs per cell visit */
+#define AMC_SUBGRID 8        /* sub-cells per axis of the in-CTA neighbour search */
+#define AMC_SUB_MIN_N 48     /* below this many members the plain all-pairs scan is cheaper */
 
 enum { PH_DRIFT = 1, PH_WALLS = 2, PH_RECAP = 4, PH_KEYS = 8, PH_SAVE_PRIOR = 16, PH_LOAD_PRIOR = 32, PH_RECAP_POST = 64 };
 
@@ -65,6 +67,10 @@ struct P {
     unsigned long long *tap_path_count;
     double *tap_paths[4];
     uint16_t *wall_bits;
+    int32_t *wl;          /* [8][wl_stride] reference cells of each colour group that can hold a pair */
+    int32_t *wl_count;    /* [8] */
+    int32_t *cell_active; /* [8][wl_stride] 1 = cell is in its group's worklist */
+    int32_t wl_stride;    /* reference cells per colour group */
     int32_t esc_cap;
     int32_t *esc_count;
     int32_t *esc_slot;

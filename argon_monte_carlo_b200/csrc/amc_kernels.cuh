@@ -220,6 +220,15 @@ struct CellShared {
     unsigned long long cursor;
     int moved_a, moved_b;
     int kx, ky, kz; /* 0-based cell indices of this visit (colour-group mode) */
+    /* sub-cell neighbour search */
+    double lo[3], inv_s[3];
+    int sub_ok;
+    unsigned int nexec;          /* distance tests executed by this CTA since the last flush */
+    unsigned long long nref;      /* reference-equivalent tests, thread 0 only */
+    int rbeg[8], rcum[9];         /* the 8 candidate owner-cell ranges of this visit */
+    uint16_t sub_of[AMC_MAX_MEMBERS], pos_of[AMC_MAX_MEMBERS], order[AMC_MAX_MEMBERS];
+    int sub_off[AMC_SUBGRID * AMC_SUBGRID * AMC_SUBGRID + 1];
+    int sub_cnt[AMC_SUBGRID * AMC_SUBGRID * AMC_SUBGRID];
 };
 
 __device__ __forceinline__ unsigned long long pair_key(int32_t ia, int32_t ib)
@@ -309,6 +318,8 @@ __device__ __noinline__ void resolve_pair(const P &p, CellShared &S, int m1, int
                 int cz = member_axis(p.edge[2], p.lo[2], p.nc[2], o[2], g2 & 1, z);
                 int32_t cc = (cx < 0 || cy < 0 || cz < 0) ? -1 : ((cx >> 1) * (p.nc[1] >> 1) + (cy >> 1)) * (p.nc[2] >> 1) + (cz >> 1);
                 p.esc_cell[e * 8 + g2] = cc;
+                if (cc >= 0 && atomicExch(&p.cell_active[(size_t)g2 * p.wl_stride + cc], 1) == 0)
+                    p.wl[(size_t)g2 * p.wl_stride + atomicAdd(&p.wl_count[g2], 1)] = cc; /* group g2 has not started yet */
             }
         }
     }
@@ -320,15 +331,68 @@ __device__ void cell_process(const P &p, CellShared &S, int group, int cell)
 {
     const int n = S.n, tid = threadIdx.x, nthreads = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
-    if (tid == 0) {
-        unsigned long long c = (unsigned long long)n * (n - 1) / 2;
-        atomicAdd(&p.stats->checks_ref, c);
-        atomicAdd(&p.stats->checks_exec, c);
-    }
-    for (int a = warp; a < n - 1; a += nwarps) {
-        double xa = S.x[a], ya = S.y[a], za = S.z[a];
-        for (int b = a + 1 + lane; b < n; b += 32)
-            if (overlap(p, xa, ya, za, S.x[b], S.y[b], S.z[b])) push_cand(S, p, a, b);
+    if (tid == 0) S.nref += (unsigned long long)n * (n - 1) / 2;
+    if (n < AMC_SUB_MIN_N || !S.sub_ok) {
+        // small cell: all unordered pairs, one warp per row
+        for (int a = warp; a < n - 1; a += nwarps) {
+            double xa = S.x[a], ya = S.y[a], za = S.z[a];
+            for (int b = a + 1 + lane; b < n; b += 32)
+                if (overlap(p, xa, ya, za, S.x[b], S.y[b], S.z[b])) push_cand(S, p, a, b);
+        }
+        if (tid == 0) atomicAdd(&S.nexec, (unsigned int)(n * (n - 1) / 2));
+    } else {
+        // Bin the members into AMC_SUBGRID^3 sub-cells (edge >= 1.05 collision ranges, checked on the
+        // host), z fastest, and test each member only against members of the 27 surrounding sub-cells
+        // that come later in sub-cell order: two spheres closer than the collision range differ by at
+        // most one sub-cell per axis, so the candidate set equals the all-pairs scan's.
+        constexpr int G = AMC_SUBGRID, G3 = G * G * G;
+        for (int c = tid; c < G3; c += nthreads) S.sub_cnt[c] = 0;
+        __syncthreads();
+        for (int k = tid; k < n; k += nthreads) {
+            int ix = min(G - 1, max(0, (int)((S.x[k] - S.lo[0]) * S.inv_s[0])));
+            int iy = min(G - 1, max(0, (int)((S.y[k] - S.lo[1]) * S.inv_s[1])));
+            int iz = min(G - 1, max(0, (int)((S.z[k] - S.lo[2]) * S.inv_s[2])));
+            int c = (ix * G + iy) * G + iz;
+            S.sub_of[k] = (uint16_t)c;
+            S.pos_of[k] = (uint16_t)atomicAdd(&S.sub_cnt[c], 1);
+        }
+        __syncthreads();
+        { // exclusive scan of the G3 counters: each warp scans a contiguous chunk, then chunk offsets
+            const int per = (G3 + nthreads - 1) / nthreads;
+            int base = tid * per, sum = 0;
+            for (int k = 0; k < per; k++) if (base + k < G3) sum += S.sub_cnt[base + k];
+            __shared__ int sub_total;
+            int ex = block_exclusive_scan(sum, &sub_total);
+            for (int k = 0; k < per; k++) if (base + k < G3) { S.sub_off[base + k] = ex; ex += S.sub_cnt[base + k]; }
+            if (tid == 0) S.sub_off[G3] = n;
+        }
+        __syncthreads();
+        for (int k = tid; k < n; k += nthreads) {
+            int pos = S.sub_off[S.sub_of[k]] + S.pos_of[k];
+            S.pos_of[k] = (uint16_t)pos;
+            S.order[pos] = (uint16_t)k;
+        }
+        __syncthreads();
+        unsigned int mine = 0;
+        for (int a = tid; a < n; a += nthreads) {
+            double xa = S.x[a], ya = S.y[a], za = S.z[a];
+            int c = S.sub_of[a], pa = S.pos_of[a];
+            int ix = c / (G * G), iy = (c / G) % G, iz = c % G;
+            int z0 = max(iz - 1, 0), z1 = min(iz + 1, G - 1);
+            for (int jx = max(ix - 1, 0); jx <= min(ix + 1, G - 1); jx++)
+                for (int jy = max(iy - 1, 0); jy <= min(iy + 1, G - 1); jy++) {
+                    int row = (jx * G + jy) * G;
+                    int beg = S.sub_off[row + z0], end = S.sub_off[row + z1 + 1];
+                    if (beg <= pa) beg = pa + 1; /* only partners later in sub-cell order: each pair once */
+                    for (int q = beg; q < end; q++) {
+                        int b = S.order[q];
+                        mine++;
+                        if (overlap(p, xa, ya, za, S.x[b], S.y[b], S.z[b])) push_cand(S, p, a, b);
+                    }
+                }
+        }
+        mine = __reduce_add_sync(0xffffffffu, mine);
+        if (lane == 0 && mine) atomicAdd(&S.nexec, mine);
     }
     __syncthreads();
     if (S.ncand == 0) return;
@@ -367,7 +431,7 @@ __device__ void cell_process(const P &p, CellShared &S, int group, int cell)
                 if (pair_key(S.id[a], S.id[k]) > cur && overlap(p, xa, ya, za, xk, yk, zk)) push_cand(S, p, a, k);
                 if (pair_key(S.id[b], S.id[k]) > cur && overlap(p, xb, yb, zb, xk, yk, zk)) push_cand(S, p, b, k);
             }
-            if (tid == 0) atomicAdd(&p.stats->checks_exec, (unsigned long long)(2 * (n - 2)));
+            if (tid == 0) atomicAdd(&S.nexec, (unsigned int)(2 * (n - 2)));
         }
         __syncthreads();
         if (tid == 0 && S.ncand > AMC_MAX_CAND) S.ncand = AMC_MAX_CAND;
@@ -375,56 +439,108 @@ __device__ void cell_process(const P &p, CellShared &S, int group, int cell)
     }
 }
 
-// one colour group (Pore:522-549): grid = all reference cells of the group, x-major / z-minor
-__global__ void __launch_bounds__(PAIR_THREADS) k_pairs_group(const __grid_constant__ P p, const int group)
+// worklist of one pair pass: every reference cell whose 8 candidate owner cells hold at least two
+// particles, per colour group.  Cells that later receive an escaped particle are appended by
+// resolve_pair.  One thread per reference cell.
+__global__ void __launch_bounds__(ADVECT_THREADS) k_build_worklist(const __grid_constant__ P p)
+{
+    int cid = blockIdx.x * blockDim.x + threadIdx.x; /* linear over (kx, ky, kz), z fastest */
+    if (threadIdx.x < 8 && blockIdx.x == 0) { /* wl_count is zeroed by the host before this launch */ }
+    int ncell = p.nc[0] * p.nc[1] * p.nc[2];
+    if (cid >= ncell) return;
+    int kz = cid % p.nc[2], ky = (cid / p.nc[2]) % p.nc[1], kx = cid / (p.nc[2] * p.nc[1]);
+    int total = 0;
+#pragma unroll
+    for (int nb = 0; nb < 8; nb++) {
+        int oc = ((kx + 1 - (nb >> 2)) * p.pnc[1] + (ky + 1 - ((nb >> 1) & 1))) * p.pnc[2] + (kz + 1 - (nb & 1));
+        total += p.cell_start[oc + 1] - p.cell_start[oc];
+    }
+    int group = ((kx & 1) << 2) | ((ky & 1) << 1) | (kz & 1);
+    int cell = ((kx >> 1) * (p.nc[1] >> 1) + (ky >> 1)) * (p.nc[2] >> 1) + (kz >> 1);
+    int active = total >= 2;
+    p.cell_active[(size_t)group * p.wl_stride + cell] = active;
+    if (active) p.wl[(size_t)group * p.wl_stride + atomicAdd(&p.wl_count[group], 1)] = cell;
+}
+
+// one colour group (Pore:522-549): persistent CTAs walk the group's worklist
+__global__ void __launch_bounds__(PAIR_THREADS, 4) k_pairs_group(const __grid_constant__ P p, const int group)
 {
     __shared__ CellShared S;
     const int tid = threadIdx.x;
     const int nhy = p.nc[1] >> 1, nhz = p.nc[2] >> 1;
-    const int cell = blockIdx.x;
-    const int hz = cell % nhz, hy = (cell / nhz) % nhy, hx = cell / (nhz * nhy);
-    const int kx = 2 * hx + ((group >> 2) & 1), ky = 2 * hy + ((group >> 1) & 1), kz = 2 * hz + (group & 1);
-    if (tid == 0) { S.n = 0; S.ncand = 0; S.kx = kx; S.ky = ky; S.kz = kz; }
-    __syncthreads();
-    const double lox = p.lo[0][kx], hix = p.edge[0][kx + 1];
-    const double loy = p.lo[1][ky], hiy = p.edge[1][ky + 1];
-    const double loz = p.lo[2][kz], hiz = p.edge[2][kz + 1];
     const Arrays &A = p.a;
-    // members: the owner cell itself plus the low-side band of its 7 lower neighbours (padded owner
-    // index = cell index + 1), membership decided on the live position (Pore:527-530)
-#pragma unroll 1
-    for (int nb = 0; nb < 8; nb++) {
-        int ox = kx + 1 - (nb >> 2), oy = ky + 1 - ((nb >> 1) & 1), oz = kz + 1 - (nb & 1);
-        int oc = (ox * p.pnc[1] + oy) * p.pnc[2] + oz;
-        int beg = p.cell_start[oc], end = p.cell_start[oc + 1];
-        for (int s = beg + tid; s < end; s += PAIR_THREADS) {
-            if (A.flag[s] & AMC_FLAG_ESC) continue;
-            double x = A.x[s], y = A.y[s], z = A.z[s];
-            if (lox < x && x < hix && loy < y && y < hiy && loz < z && z < hiz) {
-                int k = atomicAdd(&S.n, 1);
-                if (k < AMC_MAX_MEMBERS) { S.x[k] = x; S.y[k] = y; S.z[k] = z; S.id[k] = A.id[s]; S.slot[k] = s; S.src[k] = -1 - nb; }
+    const int nwork = p.wl_count[group];
+    const int32_t *wl = p.wl + (size_t)group * p.wl_stride;
+    if (tid == 0) { S.nexec = 0; S.nref = 0; }
+    for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
+        const int cell = wl[w];
+        const int hz = cell % nhz, hy = (cell / nhz) % nhy, hx = cell / (nhz * nhy);
+        const int kx = 2 * hx + ((group >> 2) & 1), ky = 2 * hy + ((group >> 1) & 1), kz = 2 * hz + (group & 1);
+        __syncthreads(); /* previous cell fully processed before S is reused */
+        const double lox = p.lo[0][kx], hix = p.edge[0][kx + 1];
+        const double loy = p.lo[1][ky], hiy = p.edge[1][ky + 1];
+        const double loz = p.lo[2][kz], hiz = p.edge[2][kz + 1];
+        if (tid == 0) {
+            S.n = 0; S.ncand = 0; S.kx = kx; S.ky = ky; S.kz = kz;
+            S.lo[0] = lox; S.lo[1] = loy; S.lo[2] = loz;
+            S.inv_s[0] = (double)AMC_SUBGRID / (hix - lox); S.inv_s[1] = (double)AMC_SUBGRID / (hiy - loy);
+            S.inv_s[2] = (double)AMC_SUBGRID / (hiz - loz);
+            double smin = fmin(fmin(hix - lox, hiy - loy), hiz - loz) / AMC_SUBGRID;
+            S.sub_ok = smin >= 1.05 * p.cr;
+        }
+        // candidates: the owner cell itself plus its 7 low-side neighbours (padded owner index = cell
+        // index + 1); the 8 ranges are walked as one flat index space so every thread has independent
+        // loads in flight.  Membership is decided on the live position (Pore:527-530).
+        if (tid < 8) {
+            int ox = kx + 1 - (tid >> 2), oy = ky + 1 - ((tid >> 1) & 1), oz = kz + 1 - (tid & 1);
+            int oc = (ox * p.pnc[1] + oy) * p.pnc[2] + oz;
+            int beg = p.cell_start[oc], len = p.cell_start[oc + 1] - beg;
+            S.rbeg[tid] = beg;
+            int inc = len;
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) { int t = __shfl_up_sync(0xffu, inc, o); if (tid >= o) inc += t; }
+            S.rcum[tid + 1] = inc;
+            if (tid == 0) S.rcum[0] = 0;
+        }
+        __syncthreads();
+        {
+            const int total = S.rcum[8];
+            for (int t = tid; t < total; t += PAIR_THREADS) {
+                int nb = 0;
+#pragma unroll
+                for (int r = 1; r < 8; r++) nb += t >= S.rcum[r];
+                int s = S.rbeg[nb] + (t - S.rcum[nb]);
+                unsigned fl = A.flag[s];
+                double x = A.x[s], y = A.y[s], z = A.z[s];
+                if (!(fl & AMC_FLAG_ESC) && lox < x && x < hix && loy < y && y < hiy && loz < z && z < hiz) {
+                    int k = atomicAdd(&S.n, 1);
+                    if (k < AMC_MAX_MEMBERS) { S.x[k] = x; S.y[k] = y; S.z[k] = z; S.id[k] = A.id[s]; S.slot[k] = s; S.src[k] = -1 - nb; }
+                }
             }
         }
-    }
-    {
-        int ne = *p.esc_count;
-        if (ne > p.esc_cap) ne = p.esc_cap;
-        for (int e = tid; e < ne; e += PAIR_THREADS) {
-            if (p.esc_cell[e * 8 + group] != cell) continue;
-            int s = p.esc_slot[e];
-            int k = atomicAdd(&S.n, 1);
-            if (k < AMC_MAX_MEMBERS) { S.x[k] = A.x[s]; S.y[k] = A.y[s]; S.z[k] = A.z[s]; S.id[k] = A.id[s]; S.slot[k] = s; S.src[k] = e; }
+        {
+            int ne = *p.esc_count;
+            if (ne > p.esc_cap) ne = p.esc_cap;
+            for (int e = tid; e < ne; e += PAIR_THREADS) {
+                if (p.esc_cell[e * 8 + group] != cell) continue;
+                int s = p.esc_slot[e];
+                int k = atomicAdd(&S.n, 1);
+                if (k < AMC_MAX_MEMBERS) { S.x[k] = A.x[s]; S.y[k] = A.y[s]; S.z[k] = A.z[s]; S.id[k] = A.id[s]; S.slot[k] = s; S.src[k] = e; }
+            }
         }
+        __syncthreads();
+        if (S.n > AMC_MAX_MEMBERS) {
+            __syncthreads();
+            if (tid == 0) { atomicAdd(&p.stats->cell_overflow, 1ull); S.n = AMC_MAX_MEMBERS; }
+            __syncthreads();
+        }
+        if (S.n >= 2) cell_process(p, S, group, cell);
     }
     __syncthreads();
-    if (S.n > AMC_MAX_MEMBERS) {
-        if (tid == 0) { atomicAdd(&p.stats->cell_overflow, 1ull); }
-        __syncthreads();
-        if (tid == 0) S.n = AMC_MAX_MEMBERS;
-        __syncthreads();
+    if (tid == 0) { /* one pair of global atomics per CTA instead of per cell */
+        if (S.nref) atomicAdd(&p.stats->checks_ref, S.nref);
+        if (S.nexec) atomicAdd(&p.stats->checks_exec, (unsigned long long)S.nexec);
     }
-    if (S.n < 2) return;
-    cell_process(p, S, group, cell);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -439,6 +555,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_cube_sweep(const __grid_const
     const int tid = threadIdx.x;
     const Arrays &A = p.a;
     int32_t *lx = p.key, *lxy = p.rank;
+    if (tid == 0) { S.nexec = 0; S.nref = 0; }
     for (int xl = 0; xl < p.nc[0]; xl++) {
         if (tid == 0) nx = 0;
         __syncthreads();
@@ -463,7 +580,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_cube_sweep(const __grid_const
             }
             __syncthreads();
             for (int zl = 0; zl < p.nc[2]; zl++) {
-                if (tid == 0) { S.n = 0; S.ncand = 0; }
+                if (tid == 0) { S.n = 0; S.ncand = 0; S.sub_ok = 0; }
                 __syncthreads();
                 {
                     double lo = p.lo[2][zl], hi = p.edge[2][zl + 1];
@@ -485,6 +602,10 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_cube_sweep(const __grid_const
                 __syncthreads();
             }
         }
+    }
+    if (tid == 0) {
+        if (S.nref) atomicAdd(&p.stats->checks_ref, S.nref);
+        if (S.nexec) atomicAdd(&p.stats->checks_exec, (unsigned long long)S.nexec);
     }
 }
 

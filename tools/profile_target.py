@@ -1,0 +1,20 @@
+"""Small fixed workload for ncu captures: python tools/profile_target.py {pore_ref|temp_scaled} STEPS [PARTICLES]"""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from argon_monte_carlo_b200 import amc, config, init_state
+
+kind, steps = sys.argv[1], int(sys.argv[2])
+if kind == "pore_ref":
+    cfg = config.pore_config(False)
+    state = init_state.pore_initial_state(cfg)
+else:
+    n = int(sys.argv[3]) if len(sys.argv) > 3 else 12_500_000
+    cfg = config.pore_config(True, scale=(n / 557649) ** (1 / 3))
+    state = init_state.synthetic_pore_state(cfg, seed=17)
+sim = amc.Simulation(cfg, max_particles=len(state[0]))
+sim.set_state(*state)
+for k in range(steps):
+    st = sim.step(1)[0]
+ms, launches = sim.last_timing()
+print(kind, len(state[0]), "last step ms", ms, "collisions", st["collisions"], "checks exec/ref", st["pair_checks_exec"], st["pair_checks_ref"])
+sim.close()
