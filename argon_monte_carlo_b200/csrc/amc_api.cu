@@ -172,7 +172,7 @@ static int create_impl(amc_handle *h, const amc_config *cfg, int device)
     if (ncell + 2 > 0x7fffffffLL) return h->fail(AMC_E_INVALID, "too many cells");
     p.ncell_pad = (int32_t)ncell;
     h->n_buckets = (int)ncell + 1;
-    ALLOC(p.cell_count, h->n_buckets + 1); ALLOC(p.cell_start, h->n_buckets + 1);
+    ALLOC(p.band_count, h->n_buckets + 1); ALLOC(p.rest_count, h->n_buckets + 1); ALLOC(p.cell_start, h->n_buckets + 1);
     ALLOC(h->d_tile_sums, (h->n_buckets + SCAN_TILE - 1) / SCAN_TILE + 1);
     p.key0 = (uint32_t)cfg->seed; p.key1 = (uint32_t)(cfg->seed >> 32);
     if (cfg->cheb_coef && cfg->cheb_n > 0) {
@@ -321,7 +321,7 @@ static int sort_scatter(amc_handle *h, int64_t *launches)
     P &p = h->p;
     int m = h->n_buckets;
     int ntiles = (m + SCAN_TILE - 1) / SCAN_TILE;
-    k_scan_tiles<<<ntiles, SCAN_THREADS, 0, h->stream>>>(p.cell_count, p.cell_start, h->d_tile_sums, m);
+    k_scan_tiles<<<ntiles, SCAN_THREADS, 0, h->stream>>>(p.band_count, p.rest_count, p.cell_start, h->d_tile_sums, m);
     k_scan_sums<<<1, SCAN_THREADS, 0, h->stream>>>(h->d_tile_sums, ntiles);
     k_scan_add<<<ntiles, SCAN_THREADS, 0, h->stream>>>(p.cell_start, h->d_tile_sums, m, (int32_t)h->n);
     k_scatter<<<grid_for(h->n, ADVECT_THREADS), ADVECT_THREADS, 0, h->stream>>>(p);
@@ -388,7 +388,10 @@ extern "C" int amc_step(amc_handle *h, int32_t n_steps, amc_step_stats *stats)
             p.step = h->step_index++;
             if (h->n > 0) {
                 int phase = PH_DRIFT | PH_WALLS | (has_recap ? PH_RECAP : 0) | (sweep ? 0 : PH_KEYS);
-                if (!sweep) CK(cudaMemsetAsync(p.cell_count, 0, (h->n_buckets + 1) * sizeof(int32_t), h->stream));
+                if (!sweep) {
+                    CK(cudaMemsetAsync(p.band_count, 0, (h->n_buckets + 1) * sizeof(int32_t), h->stream));
+                    CK(cudaMemsetAsync(p.rest_count, 0, (h->n_buckets + 1) * sizeof(int32_t), h->stream));
+                }
                 k_advect<<<grid_for(h->n, ADVECT_THREADS), ADVECT_THREADS, 0, h->stream>>>(p, phase);
                 h->last_launches += 1;
                 CK(cudaEventRecord(h->events[4 * s + 1], h->stream));
@@ -493,7 +496,8 @@ extern "C" int amc_pairs(amc_handle *h, amc_step_stats *stats)
         if (p.pp_mode == AMC_PP_SWEEP) {
             if ((rc = unsort(h)) != AMC_OK) return rc;
         } else {
-            CK(cudaMemsetAsync(p.cell_count, 0, (h->n_buckets + 1) * sizeof(int32_t), h->stream));
+            CK(cudaMemsetAsync(p.band_count, 0, (h->n_buckets + 1) * sizeof(int32_t), h->stream));
+            CK(cudaMemsetAsync(p.rest_count, 0, (h->n_buckets + 1) * sizeof(int32_t), h->stream));
             k_advect<<<grid_for(h->n, ADVECT_THREADS), ADVECT_THREADS, 0, h->stream>>>(p, PH_KEYS);
             if ((rc = sort_scatter(h, nullptr)) != AMC_OK) return rc;
         }

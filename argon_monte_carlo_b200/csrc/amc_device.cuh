@@ -12,8 +12,8 @@
 #define AMC_FLAG_PATH 1u /* full_path_traveled (Pore:392) */
 #define AMC_FLAG_ESC 2u  /* transient: particle left its sorted owner cell during the pair pass */
 
-#define AMC_MAX_MEMBERS 768  /* particles per reference cell incl. overlap band (reference: <= 308) */
-#define AMC_MAX_CAND 256     /* simultaneously overlapping pairs per cell visit */
+#define AMC_MAX_MEMBERS 512  /* particles per reference cell incl. overlap band (reference: <= 308) */
+#define AMC_MAX_CAND 128     /* simultaneously overlapping pairs per cell visit */
 #define AMC_SUBGRID 8        /* sub-cells per axis of the in-CTA neighbour search */
 #define AMC_SUB_MIN_N 48     /* below this many members the plain all-pairs scan is cheaper */
 
@@ -37,7 +37,8 @@ struct P {
     Arrays a, b;
     double *px, *py, *pz;
     int32_t *key, *rank;
-    int32_t *cell_count, *cell_start;
+    int32_t *band_count, *rest_count; /* per owner cell: particles inside / outside a low-side band of a next cell */
+    int32_t *cell_start;
     int32_t ncell_pad;
     int32_t pnc[3];
     int32_t kind, pp_mode;
@@ -454,6 +455,16 @@ __device__ __forceinline__ int32_t owner_key(const P &p, double x, double y, dou
     o[2] = owner_axis(p.edge[2], p.nc[2], p.e0[2], p.inv_d[2], z);
     if (o[0] == p.nc[0] || o[1] == p.nc[1] || o[2] == p.nc[2]) return p.ncell_pad;
     return ((o[0] + 1) * p.pnc[1] + (o[1] + 1)) * p.pnc[2] + (o[2] + 1);
+}
+// true when the coordinate lies inside the low-side band of the next cell up on this axis, i.e. the
+// particle can be a member of a reference cell other than its owner cell (Pore:527-529)
+__device__ __forceinline__ bool in_next_band(const double *lo, int nc, int owner, double v)
+{
+    return owner + 1 < nc && v > lo[owner + 1];
+}
+__device__ __forceinline__ bool any_band(const P &p, double x, double y, double z, const int o[3])
+{
+    return in_next_band(p.lo[0], p.nc[0], o[0], x) || in_next_band(p.lo[1], p.nc[1], o[1], y) || in_next_band(p.lo[2], p.nc[2], o[2], z);
 }
 // member cell (0-based) of coordinate v on one axis for parity `par`, or -1 (strict inequalities
 // lo[k] < v < edge[k+1], Pore:527-529)

@@ -9,7 +9,7 @@
 #include "amc_device.cuh"
 
 #define ADVECT_THREADS 256
-#define PAIR_THREADS 256
+#define PAIR_THREADS 128
 #define SWEEP_THREADS 512
 
 __device__ __forceinline__ void load_part(const Arrays &a, int64_t s, Part &q)
@@ -76,7 +76,10 @@ __global__ void __launch_bounds__(ADVECT_THREADS) k_advect(const __grid_constant
         int o[3];
         int32_t k = owner_key(p, q.x, q.y, q.z, o);
         p.key[s] = k;
-        p.rank[s] = atomicAdd(&p.cell_count[k], 1);
+        // band particles go to the front of their owner cell's segment so that neighbouring reference
+        // cells only have to read that prefix; rank >= 0: band, rank < 0: ~rank among the others
+        if (k != p.ncell_pad && any_band(p, q.x, q.y, q.z, o)) p.rank[s] = atomicAdd(&p.band_count[k], 1);
+        else p.rank[s] = ~atomicAdd(&p.rest_count[k], 1);
     }
 }
 
@@ -108,13 +111,13 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int *total)
     return r;
 }
 
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_tiles(const int32_t *in, int32_t *out, int32_t *tile_sums, int m)
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_tiles(const int32_t *in, const int32_t *in2, int32_t *out, int32_t *tile_sums, int m)
 {
     __shared__ int total;
     int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
     int v[SCAN_ITEMS], sum = 0;
 #pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; k++) { v[k] = base + k < m ? in[base + k] : 0; sum += v[k]; }
+    for (int k = 0; k < SCAN_ITEMS; k++) { v[k] = base + k < m ? in[base + k] + in2[base + k] : 0; sum += v[k]; }
     int ex = block_exclusive_scan(sum, &total);
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; k++) { if (base + k < m) out[base + k] = ex; ex += v[k]; }
@@ -150,7 +153,8 @@ __global__ void __launch_bounds__(ADVECT_THREADS) k_scatter(const __grid_constan
 {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= p.n) return;
-    int64_t t = (int64_t)p.cell_start[p.key[s]] + p.rank[s];
+    int32_t k = p.key[s], r = p.rank[s];
+    int64_t t = (int64_t)p.cell_start[k] + (r >= 0 ? r : p.band_count[k] + ~r);
     p.b.x[t] = p.a.x[s]; p.b.y[t] = p.a.y[s]; p.b.z[t] = p.a.z[s];
     p.b.vx[t] = p.a.vx[s]; p.b.vy[t] = p.a.vy[s]; p.b.vz[t] = p.a.vz[s];
     p.b.d[t] = p.a.d[s]; p.b.dx[t] = p.a.dx[s]; p.b.dy[t] = p.a.dy[s]; p.b.dz[t] = p.a.dz[s];
@@ -303,7 +307,9 @@ __device__ __noinline__ void resolve_pair(const P &p, CellShared &S, int m1, int
             if (e < 0) { /* found through the sorted layout: src = -1 - (low-side neighbour code) */
                 int nb = -1 - e;
                 int oc = ((S.kx + 1 - (nb >> 2)) * p.pnc[1] + (S.ky + 1 - ((nb >> 1) & 1))) * p.pnc[2] + (S.kz + 1 - (nb & 1));
-                if (k == oc) continue; /* still in its sorted owner cell */
+                /* still findable through the sorted layout: same owner cell, and either it sits in the
+                   band prefix of that cell or it is (still) outside every band */
+                if (k == oc && (s < p.cell_start[oc] + p.band_count[oc] || !any_band(p, x, y, z, o))) continue;
             }
             if (e < 0) {
                 e = atomicAdd(p.esc_count, 1);
@@ -341,13 +347,13 @@ __device__ void cell_process(const P &p, CellShared &S, int group, int cell)
         }
         if (tid == 0) atomicAdd(&S.nexec, (unsigned int)(n * (n - 1) / 2));
     } else {
-        // Bin the members into AMC_SUBGRID^3 sub-cells (edge >= 1.05 collision ranges, checked on the
-        // host), z fastest, and test each member only against members of the 27 surrounding sub-cells
-        // that come later in sub-cell order: two spheres closer than the collision range differ by at
-        // most one sub-cell per axis, so the candidate set equals the all-pairs scan's.
+        // Bin the members into AMC_SUBGRID^3 sub-cells (edge >= 1.05 collision ranges, checked per
+        // cell), z fastest.  Two spheres closer than the collision range differ by at most one
+        // sub-cell per axis, so testing each member against the members of its own (x,y) row of
+        // sub-cells that come later in sub-cell order, and of the four "forward" neighbour rows,
+        // each restricted to iz-1..iz+1, visits every candidate pair exactly once.
+        // (S.sub_cnt was zeroed while the members were gathered.)
         constexpr int G = AMC_SUBGRID, G3 = G * G * G;
-        for (int c = tid; c < G3; c += nthreads) S.sub_cnt[c] = 0;
-        __syncthreads();
         for (int k = tid; k < n; k += nthreads) {
             int ix = min(G - 1, max(0, (int)((S.x[k] - S.lo[0]) * S.inv_s[0])));
             int iy = min(G - 1, max(0, (int)((S.y[k] - S.lo[1]) * S.inv_s[1])));
@@ -357,14 +363,18 @@ __device__ void cell_process(const P &p, CellShared &S, int group, int cell)
             S.pos_of[k] = (uint16_t)atomicAdd(&S.sub_cnt[c], 1);
         }
         __syncthreads();
-        { // exclusive scan of the G3 counters: each warp scans a contiguous chunk, then chunk offsets
-            const int per = (G3 + nthreads - 1) / nthreads;
-            int base = tid * per, sum = 0;
-            for (int k = 0; k < per; k++) if (base + k < G3) sum += S.sub_cnt[base + k];
-            __shared__ int sub_total;
-            int ex = block_exclusive_scan(sum, &sub_total);
-            for (int k = 0; k < per; k++) if (base + k < G3) { S.sub_off[base + k] = ex; ex += S.sub_cnt[base + k]; }
-            if (tid == 0) S.sub_off[G3] = n;
+        if (warp == 0) { // exclusive scan of the G3 counters by one warp: G3/32 consecutive counters per lane
+            constexpr int PER = G3 / 32;
+            int v[PER], sum = 0;
+#pragma unroll
+            for (int k = 0; k < PER; k++) { v[k] = S.sub_cnt[lane * PER + k]; sum += v[k]; }
+            int inc = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+            int ex = inc - sum;
+#pragma unroll
+            for (int k = 0; k < PER; k++) { S.sub_off[lane * PER + k] = ex; ex += v[k]; S.sub_cnt[lane * PER + k] = 0; }
+            if (lane == 31) S.sub_off[G3] = ex;
         }
         __syncthreads();
         for (int k = tid; k < n; k += nthreads) {
@@ -374,22 +384,23 @@ __device__ void cell_process(const P &p, CellShared &S, int group, int cell)
         }
         __syncthreads();
         unsigned int mine = 0;
-        for (int a = tid; a < n; a += nthreads) {
-            double xa = S.x[a], ya = S.y[a], za = S.z[a];
-            int c = S.sub_of[a], pa = S.pos_of[a];
+        for (int item = tid; item < 5 * n; item += nthreads) { // (member, row) work items: balanced over the CTA
+            int a = item / 5, r = item - 5 * a;
+            int c = S.sub_of[a];
             int ix = c / (G * G), iy = (c / G) % G, iz = c % G;
-            int z0 = max(iz - 1, 0), z1 = min(iz + 1, G - 1);
-            for (int jx = max(ix - 1, 0); jx <= min(ix + 1, G - 1); jx++)
-                for (int jy = max(iy - 1, 0); jy <= min(iy + 1, G - 1); jy++) {
-                    int row = (jx * G + jy) * G;
-                    int beg = S.sub_off[row + z0], end = S.sub_off[row + z1 + 1];
-                    if (beg <= pa) beg = pa + 1; /* only partners later in sub-cell order: each pair once */
-                    for (int q = beg; q < end; q++) {
-                        int b = S.order[q];
-                        mine++;
-                        if (overlap(p, xa, ya, za, S.x[b], S.y[b], S.z[b])) push_cand(S, p, a, b);
-                    }
-                }
+            // rows: 0 = own row (later partners only), 1 = (ix, iy+1), 2..4 = (ix+1, iy-1..iy+1)
+            int jx = ix + (r >= 2), jy = r == 0 ? iy : (r == 1 ? iy + 1 : iy + r - 3);
+            if (jx >= G || jy < 0 || jy >= G) continue;
+            int row = (jx * G + jy) * G;
+            int beg = S.sub_off[row + max(iz - 1, 0)], end = S.sub_off[row + min(iz + 1, G - 1) + 1];
+            if (r == 0) beg = S.pos_of[a] + 1;
+            if (beg >= end) continue;
+            double xa = S.x[a], ya = S.y[a], za = S.z[a];
+            for (int q = beg; q < end; q++) {
+                int b2 = S.order[q];
+                mine++;
+                if (overlap(p, xa, ya, za, S.x[b2], S.y[b2], S.z[b2])) push_cand(S, p, a, b2);
+            }
         }
         mine = __reduce_add_sync(0xffffffffu, mine);
         if (lane == 0 && mine) atomicAdd(&S.nexec, mine);
@@ -449,11 +460,11 @@ __global__ void __launch_bounds__(ADVECT_THREADS) k_build_worklist(const __grid_
     int ncell = p.nc[0] * p.nc[1] * p.nc[2];
     if (cid >= ncell) return;
     int kz = cid % p.nc[2], ky = (cid / p.nc[2]) % p.nc[1], kx = cid / (p.nc[2] * p.nc[1]);
-    int total = 0;
+    int total = 0; /* upper bound of the member count: own owner cell + band prefixes of the 7 lower neighbours */
 #pragma unroll
     for (int nb = 0; nb < 8; nb++) {
         int oc = ((kx + 1 - (nb >> 2)) * p.pnc[1] + (ky + 1 - ((nb >> 1) & 1))) * p.pnc[2] + (kz + 1 - (nb & 1));
-        total += p.cell_start[oc + 1] - p.cell_start[oc];
+        total += nb == 0 ? p.cell_start[oc + 1] - p.cell_start[oc] : p.band_count[oc];
     }
     int group = ((kx & 1) << 2) | ((ky & 1) << 1) | (kz & 1);
     int cell = ((kx >> 1) * (p.nc[1] >> 1) + (ky >> 1)) * (p.nc[2] >> 1) + (kz >> 1);
@@ -463,47 +474,56 @@ __global__ void __launch_bounds__(ADVECT_THREADS) k_build_worklist(const __grid_
 }
 
 // one colour group (Pore:522-549): persistent CTAs walk the group's worklist
-__global__ void __launch_bounds__(PAIR_THREADS, 4) k_pairs_group(const __grid_constant__ P p, const int group)
+__global__ void __launch_bounds__(PAIR_THREADS, 8) k_pairs_group(const __grid_constant__ P p, const int group)
 {
     __shared__ CellShared S;
+    __shared__ double s_lo[3], s_hi[3];
+    __shared__ int s_ne;
     const int tid = threadIdx.x;
     const int nhy = p.nc[1] >> 1, nhz = p.nc[2] >> 1;
     const Arrays &A = p.a;
     const int nwork = p.wl_count[group];
     const int32_t *wl = p.wl + (size_t)group * p.wl_stride;
     if (tid == 0) { S.nexec = 0; S.nref = 0; }
+    for (int c = tid; c < AMC_SUBGRID * AMC_SUBGRID * AMC_SUBGRID; c += PAIR_THREADS) S.sub_cnt[c] = 0; /* kept zero by the scan */
     for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
         const int cell = wl[w];
-        const int hz = cell % nhz, hy = (cell / nhz) % nhy, hx = cell / (nhz * nhy);
-        const int kx = 2 * hx + ((group >> 2) & 1), ky = 2 * hy + ((group >> 1) & 1), kz = 2 * hz + (group & 1);
         __syncthreads(); /* previous cell fully processed before S is reused */
-        const double lox = p.lo[0][kx], hix = p.edge[0][kx + 1];
-        const double loy = p.lo[1][ky], hiy = p.edge[1][ky + 1];
-        const double loz = p.lo[2][kz], hiz = p.edge[2][kz + 1];
-        if (tid == 0) {
-            S.n = 0; S.ncand = 0; S.kx = kx; S.ky = ky; S.kz = kz;
-            S.lo[0] = lox; S.lo[1] = loy; S.lo[2] = loz;
-            S.inv_s[0] = (double)AMC_SUBGRID / (hix - lox); S.inv_s[1] = (double)AMC_SUBGRID / (hiy - loy);
-            S.inv_s[2] = (double)AMC_SUBGRID / (hiz - loz);
-            double smin = fmin(fmin(hix - lox, hiy - loy), hiz - loz) / AMC_SUBGRID;
-            S.sub_ok = smin >= 1.05 * p.cr;
-        }
-        // candidates: the owner cell itself plus its 7 low-side neighbours (padded owner index = cell
-        // index + 1); the 8 ranges are walked as one flat index space so every thread has independent
-        // loads in flight.  Membership is decided on the live position (Pore:527-530).
         if (tid < 8) {
+            // lanes 0..7: the 8 candidate owner-cell ranges (own cell: all of it; the 7 low-side
+            // neighbours: their band prefix); lanes 0..2 also fetch the bounds of one axis
+            const int hz = cell % nhz, hy = (cell / nhz) % nhy, hx = cell / (nhz * nhy);
+            const int kx = 2 * hx + ((group >> 2) & 1), ky = 2 * hy + ((group >> 1) & 1), kz = 2 * hz + (group & 1);
             int ox = kx + 1 - (tid >> 2), oy = ky + 1 - ((tid >> 1) & 1), oz = kz + 1 - (tid & 1);
             int oc = (ox * p.pnc[1] + oy) * p.pnc[2] + oz;
-            int beg = p.cell_start[oc], len = p.cell_start[oc + 1] - beg;
+            int beg = p.cell_start[oc], len = tid == 0 ? p.cell_start[oc + 1] - beg : p.band_count[oc];
             S.rbeg[tid] = beg;
             int inc = len;
 #pragma unroll
             for (int o = 1; o < 8; o <<= 1) { int t = __shfl_up_sync(0xffu, inc, o); if (tid >= o) inc += t; }
             S.rcum[tid + 1] = inc;
-            if (tid == 0) S.rcum[0] = 0;
+            bool wide = true; /* sub-cells of this axis are wider than 1.05 collision ranges */
+            if (tid < 3) {
+                int k = tid == 0 ? kx : (tid == 1 ? ky : kz);
+                double lo = p.lo[tid][k], hi = p.edge[tid][k + 1];
+                s_lo[tid] = lo; s_hi[tid] = hi;
+                S.lo[tid] = lo;
+                S.inv_s[tid] = (double)AMC_SUBGRID / (hi - lo);
+                wide = (hi - lo) / AMC_SUBGRID >= 1.05 * p.cr;
+            }
+            unsigned widem = __ballot_sync(0xffu, wide);
+            if (tid == 0) {
+                S.sub_ok = widem == 0xffu;
+                S.rcum[0] = 0; S.n = 0; S.ncand = 0; S.kx = kx; S.ky = ky; S.kz = kz;
+                int ne = *p.esc_count;
+                s_ne = ne > p.esc_cap ? p.esc_cap : ne;
+            }
         }
         __syncthreads();
+        const double lox = s_lo[0], hix = s_hi[0], loy = s_lo[1], hiy = s_hi[1], loz = s_lo[2], hiz = s_hi[2];
         {
+            // membership is decided on the live position (Pore:527-530); the 8 ranges are walked as one
+            // flat index space so every thread has independent loads in flight
             const int total = S.rcum[8];
             for (int t = tid; t < total; t += PAIR_THREADS) {
                 int nb = 0;
@@ -517,11 +537,7 @@ __global__ void __launch_bounds__(PAIR_THREADS, 4) k_pairs_group(const __grid_co
                     if (k < AMC_MAX_MEMBERS) { S.x[k] = x; S.y[k] = y; S.z[k] = z; S.id[k] = A.id[s]; S.slot[k] = s; S.src[k] = -1 - nb; }
                 }
             }
-        }
-        {
-            int ne = *p.esc_count;
-            if (ne > p.esc_cap) ne = p.esc_cap;
-            for (int e = tid; e < ne; e += PAIR_THREADS) {
+            for (int e = tid; e < s_ne; e += PAIR_THREADS) { /* particles that left their sorted owner cell earlier in this pass */
                 if (p.esc_cell[e * 8 + group] != cell) continue;
                 int s = p.esc_slot[e];
                 int k = atomicAdd(&S.n, 1);
