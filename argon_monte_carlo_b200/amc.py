@@ -52,7 +52,8 @@ class AmcConfig(C.Structure):
 class AmcStepStats(C.Structure):
     _fields_ = [("wall_hits", C.c_int64 * NUM_CASES), ("wall_collisions", C.c_int64), ("pp_collisions", C.c_int64),
                 ("pair_checks_ref", C.c_int64), ("pair_checks_exec", C.c_int64), ("oob_after_walls", C.c_int64),
-                ("oob_after_pp", C.c_int64), ("errors", C.c_int64), ("completed_paths", C.c_int64),
+                ("oob_after_pp", C.c_int64), ("oob_after_walls_recapture", C.c_int64),
+                ("oob_after_pp_recapture", C.c_int64), ("errors", C.c_int64), ("completed_paths", C.c_int64),
                 ("dpz", C.c_double), ("e_cold", C.c_double), ("e_hot", C.c_double)]
 
     def as_dict(self):
@@ -231,10 +232,10 @@ class Simulation:
         self._check(self.lib.amc_walls(self.h, C.byref(st)), "amc_walls")
         return st.as_dict()
 
-    def recapture(self):
-        cnt = C.c_int64(0)
-        self._check(self.lib.amc_recapture(self.h, C.byref(cnt)), "amc_recapture")
-        return int(cnt.value)
+    def recapture(self, with_after=False):
+        cnt, after = C.c_int64(0), C.c_int64(0)
+        self._check(self.lib.amc_recapture(self.h, C.byref(cnt), C.byref(after)), "amc_recapture")
+        return (int(cnt.value), int(after.value)) if with_after else int(cnt.value)
 
     def pairs(self):
         st = AmcStepStats()
@@ -312,11 +313,12 @@ class Simulation:
                 e_cold = e_cold + se
             elif case in (4, 6, 8):
                 e_hot = e_hot + se
-        oob_walls = self.recapture()
+        oob_walls, oob_walls_after = self.recapture(True)
         st = self.pairs()
-        oob_pp = self.recapture()
+        oob_pp, oob_pp_after = self.recapture(True)
         wall_hits = int(counts[3:].sum())
         st.update(wall_hits=counts, wall_collisions=wall_hits, oob_after_walls=oob_walls, oob_after_pp=oob_pp,
+                  oob_after_walls_recapture=oob_walls_after, oob_after_pp_recapture=oob_pp_after,
                   dpz=dpz, e_cold=e_cold, e_hot=e_hot, collisions=wall_hits + st["pp_collisions"],
                   errors=st["errors"] + errors)
         return st

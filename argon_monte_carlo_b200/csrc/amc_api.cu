@@ -92,6 +92,8 @@ static void stats_to_host(const amc_handle *h, const StatsDev &s, amc_step_stats
     o->pair_checks_exec = (int64_t)s.checks_exec;
     o->oob_after_walls = (int64_t)s.oob_walls;
     o->oob_after_pp = (int64_t)s.oob_pp;
+    o->oob_after_walls_recapture = (int64_t)s.oob_walls_after;
+    o->oob_after_pp_recapture = (int64_t)s.oob_pp_after;
     o->errors = (int64_t)s.errors;
     o->completed_paths = (int64_t)s.paths;
     o->dpz = ldexp((double)(long long)s.dpz[0], -116) + ldexp((double)(long long)s.dpz[1], -156);
@@ -473,7 +475,7 @@ extern "C" int amc_walls(amc_handle *h, amc_step_stats *stats)
     return phase_end(h, stats);
 }
 
-extern "C" int amc_recapture(amc_handle *h, int64_t *count)
+extern "C" int amc_recapture(amc_handle *h, int64_t *count, int64_t *count_after)
 {
     if (!h) return AMC_E_INVALID;
     int rc = phase_begin(h);
@@ -483,6 +485,7 @@ extern "C" int amc_recapture(amc_handle *h, int64_t *count)
     amc_step_stats st;
     rc = phase_end(h, &st);
     if (count) *count = st.oob_after_pp;
+    if (count_after) *count_after = st.oob_after_pp_recapture;
     return rc;
 }
 

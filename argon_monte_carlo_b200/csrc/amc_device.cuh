@@ -27,7 +27,7 @@ struct Arrays {
 
 struct StatsDev {
     unsigned long long wall_hits[AMC_NUM_CASES];
-    unsigned long long pp, checks_ref, checks_exec, oob_walls, oob_pp, errors, paths;
+    unsigned long long pp, checks_ref, checks_exec, oob_walls, oob_pp, oob_walls_after, oob_pp_after, errors, paths;
     unsigned long long cell_overflow, cand_overflow, esc_overflow;
     unsigned long long dpz[2], ecold[2], ehot[2]; /* two-limb fixed point, see acc_add */
 };

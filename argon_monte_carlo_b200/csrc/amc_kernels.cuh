@@ -68,7 +68,10 @@ __global__ void __launch_bounds__(ADVECT_THREADS) k_advect(const __grid_constant
         } else if (p.kind == AMC_KIND_TEMP) {
             int cnt = temp_oob(p.g, q);
             if (cnt) atomicAdd(&p.stats->oob_walls, (unsigned long long)cnt);
-            temp_recapture(p.g, q);
+            if (temp_recapture(p.g, q)) {
+                int after = temp_oob(p.g, q);
+                if (after) atomicAdd(&p.stats->oob_walls_after, (unsigned long long)after);
+            }
         }
     }
     if (phase & (PH_DRIFT | PH_WALLS | PH_RECAP | PH_RECAP_POST)) store_part(p.a, s, q);
@@ -198,6 +201,10 @@ __global__ void __launch_bounds__(ADVECT_THREADS) k_recapture_post(const __grid_
     int moved = p.kind == AMC_KIND_TEMP ? temp_recapture(p.g, q) : pore_recapture(p.g, q);
     if (p.kind != AMC_KIND_TEMP) cnt = moved;
     if (cnt) atomicAdd(&p.stats->oob_pp, (unsigned long long)cnt);
+    if (p.kind == AMC_KIND_TEMP && moved) {
+        int after = temp_oob(p.g, q);
+        if (after) atomicAdd(&p.stats->oob_pp_after, (unsigned long long)after);
+    }
     if (q.x != x0) p.a.x[s] = q.x;
     if (q.y != y0) p.a.y[s] = q.y;
     if (q.z != z0) p.a.z[s] = q.z;

@@ -104,6 +104,8 @@ typedef struct amc_step_stats {
     int64_t pair_checks_exec; /* distance tests actually executed on the device */
     int64_t oob_after_walls;  /* "particles out of bounds after handling wall collisions" */
     int64_t oob_after_pp;     /* "... after particle-particle collisions" */
+    int64_t oob_after_walls_recapture; /* Temp: "... after post wall collision recapture"        Temp:805 */
+    int64_t oob_after_pp_recapture;    /* Temp: "... after post particle-particle recapture"     Temp:845 */
     int64_t errors;           /* floating-point anomalies (negative discriminant, zero relative speed) */
     int64_t completed_paths;  /* free paths completed during this step */
     double dpz, e_cold, e_hot; /* momentum_z_change / energy_transfer_{cold,hot} of this step  Temp:756-758 */
@@ -135,12 +137,13 @@ int amc_step(amc_handle *h, int32_t n_steps, amc_step_stats *stats);
  *   amc_drift      Pore:427-437 / Temp:673-683 / Cube:180-187
  *   amc_walls      all wall cases in order: Pore:442-485 / Temp:693-753 (device RNG) / Cube:192-226
  *   amc_recapture  Pore num_out_of_bounds() 354-375 / Temp num_out_of_bounds()+recapture 560-616;
- *                  *count = Pore: particles teleported; Temp: the report count taken before recapture
+ *                  *count = Pore: particles teleported; Temp: the report count taken before recapture;
+ *                  *count_after (nullable) = Temp: the report count taken again after recapture
  *   amc_pairs      the whole particle-particle pass Pore:522-549 / Temp:815-842 / Cube:232-336
  * stats (nullable) receives the counters the phase produces; other fields are zero. */
 int amc_drift(amc_handle *h);
 int amc_walls(amc_handle *h, amc_step_stats *stats);
-int amc_recapture(amc_handle *h, int64_t *count);
+int amc_recapture(amc_handle *h, int64_t *count, int64_t *count_after);
 int amc_pairs(amc_handle *h, amc_step_stats *stats);
 
 /* parity hooks for the energized walls (AMC_KIND_TEMP): one wall case at a time, in AMC_CASE_*

@@ -205,5 +205,24 @@ def cells():
         json.dump(out, f)
 
 
+def init():
+    """SHA-256 of the initial positions / velocities produced by the reference's own
+    init_positions() / init_velocities() under its seeds."""
+    sys.path.insert(0, ROOT)
+    import random
+    from oracle import ref_import
+    out = {}
+    for name, kind in (("Open_Air_Pore_MC", "pore"), ("Temperature_Pore_MC", "temp")):
+        M = ref_import.load(name)          # seeds both generators at import (Pore:89-90)
+        x, y, z = M.init_positions()
+        vx, vy, vz = M.init_velocities()
+        out[kind] = {k: digest(v) for k, v in zip(("x", "y", "z", "vx", "vy", "vz"), (x, y, z, vx, vy, vz))}
+        out[kind]["n"] = int(len(x))
+        out[kind]["next_np_uniform"] = float(np.random.uniform()).hex()
+        out[kind]["next_py_random"] = float(random.random()).hex()
+    with open(os.path.join(GOLD, "ref_init.json"), "w") as f:
+        json.dump(out, f, indent=1)
+
+
 if __name__ == "__main__":
-    {"run": run, "pack": pack, "cells": cells}[sys.argv[1]]()
+    {"run": run, "pack": pack, "cells": cells, "init": init}[sys.argv[1]]()
