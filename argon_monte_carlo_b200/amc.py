@@ -73,7 +73,9 @@ _lib = None
 EXPORTS = ("amc_create", "amc_destroy", "amc_last_error", "amc_abi_version", "amc_set_state", "amc_get_state",
            "amc_num_particles", "amc_step", "amc_drift", "amc_walls", "amc_recapture", "amc_pairs", "amc_wall_case",
            "amc_wall_hits_pending", "amc_wall_apply_directions", "amc_get_histograms", "amc_get_pair_list",
-           "amc_get_wall_bits", "amc_get_completed_paths", "amc_clear_taps", "amc_set_step_index", "amc_last_timing")
+           "amc_get_wall_bits", "amc_get_completed_paths", "amc_clear_taps", "amc_set_step_index", "amc_last_timing",
+           "amc_slab_enable", "amc_set_stream", "amc_set_ids", "amc_slab_advect", "amc_slab_sort", "amc_slab_pairs_begin",
+           "amc_slab_group", "amc_slab_apply", "amc_slab_finish", "amc_slab_get_owned")
 
 
 def load_library():

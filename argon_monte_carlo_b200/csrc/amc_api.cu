@@ -15,6 +15,10 @@ struct amc_handle {
     amc_config cfg;
     int device = 0;
     cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    bool slab = false;
+    int32_t *d_counters = nullptr; // slab mode: xf_count[nranks], n_in, bnd_n[2], rel_count, n_foreign, compact count
+    unsigned long long *d_slab_overflow = nullptr;
     P p;                        // kernel parameter block (device pointers)
     int64_t cap = 0, n = 0;
     std::vector<void *> allocs; // every cudaMalloc, freed in amc_destroy
@@ -123,7 +127,7 @@ extern "C" int amc_destroy(amc_handle *h)
     for (void *q : h->allocs) cudaFree(q);
     for (cudaEvent_t e : h->events) cudaEventDestroy(e);
     if (h->h_stats) cudaFreeHost(h->h_stats);
-    if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
     return AMC_OK;
 }
@@ -136,7 +140,7 @@ static int create_impl(amc_handle *h, const amc_config *cfg, int device)
     if (cfg->max_particles <= 0 || cfg->max_particles > 0x7fffffffLL) return h->fail(AMC_E_INVALID, "max_particles out of range");
     for (int a = 0; a < 3; a++) {
         if (cfg->nc[a] < 1 || !cfg->edge[a] || !cfg->lo[a]) return h->fail(AMC_E_INVALID, "grid tables missing");
-        if (cfg->pp_mode == AMC_PP_GROUPS && (cfg->nc[a] & 1)) return h->fail(AMC_E_INVALID, "colour groups need an even cell count per axis");
+        if (cfg->pp_mode == AMC_PP_GROUPS && a < 2 && (cfg->nc[a] & 1)) return h->fail(AMC_E_INVALID, "colour groups need an even cell count in x and y");
     }
     if (!cfg->hist_edges) return h->fail(AMC_E_INVALID, "hist_edges missing");
     if (cfg->kind == AMC_KIND_TEMP && cfg->rng_mode == AMC_RNG_DEVICE && (!cfg->cheb_coef || cfg->cheb_n < 1))
@@ -173,7 +177,8 @@ static int create_impl(amc_handle *h, const amc_config *cfg, int device)
     }
     if (ncell + 2 > 0x7fffffffLL) return h->fail(AMC_E_INVALID, "too many cells");
     p.ncell_pad = (int32_t)ncell;
-    h->n_buckets = (int)ncell + 1;
+    for (int a = 0; a < 3; a++) p.nh[a] = (cfg->nc[a] + 1) / 2;
+    h->n_buckets = (int)ncell + 2; /* padded owner cells + OUT + GONE (slab mode: emigrants and dropped ghosts) */
     ALLOC(p.band_count, h->n_buckets + 1); ALLOC(p.rest_count, h->n_buckets + 1); ALLOC(p.cell_start, h->n_buckets + 1);
     ALLOC(h->d_tile_sums, (h->n_buckets + SCAN_TILE - 1) / SCAN_TILE + 1);
     p.key0 = (uint32_t)cfg->seed; p.key1 = (uint32_t)(cfg->seed >> 32);
@@ -683,5 +688,218 @@ extern "C" int amc_last_timing(amc_handle *h, double ms[5], int64_t *launches)
     if (!h) return AMC_E_INVALID;
     if (ms) memcpy(ms, h->last_ms, sizeof(h->last_ms));
     if (launches) *launches = h->last_launches;
+    return AMC_OK;
+}
+
+// ---- slab decomposition (multi-GPU) ---------------------------------------------------------------
+extern "C" int amc_set_stream(amc_handle *h, void *cuda_stream)
+{
+    if (!h) return AMC_E_INVALID;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->own_stream) CK(cudaStreamDestroy(h->stream));
+    h->stream = (cudaStream_t)cuda_stream;
+    h->own_stream = false;
+    return AMC_OK;
+}
+
+extern "C" int amc_set_ids(amc_handle *h, const int64_t *ids)
+{
+    if (!h || !ids) return AMC_E_INVALID;
+    CK(cudaSetDevice(h->device));
+    std::vector<int32_t> v((size_t)h->n);
+    for (int64_t i = 0; i < h->n; i++) {
+        if (ids[i] < 0 || ids[i] > 0x7fffffffLL) return h->fail(AMC_E_INVALID, "particle id out of range");
+        v[(size_t)i] = (int32_t)ids[i];
+    }
+    CK(cudaMemcpyAsync(h->p.a.id, v.data(), h->n * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return AMC_OK;
+}
+
+extern "C" int amc_slab_enable(amc_handle *h, const amc_slab_config *c)
+{
+    if (!h || !c) return AMC_E_INVALID;
+    if (h->cfg.pp_mode != AMC_PP_GROUPS) return h->fail(AMC_E_INVALID, "slabs need the colour-group schedule");
+    if (c->nranks < 1 || c->rank < 0 || c->rank >= c->nranks || !c->cuts || !c->gz_edge || !c->gz_lo) return h->fail(AMC_E_INVALID, "bad slab config");
+    if (c->cuts[c->rank + 1] - c->cuts[c->rank] != h->cfg.nc[2]) return h->fail(AMC_E_INVALID, "handle z grid does not match its slab");
+    CK(cudaSetDevice(h->device));
+    P &p = h->p;
+    p.slab = 1; p.srank = c->rank; p.nranks = c->nranks; p.zoff = c->cuts[c->rank]; p.gncz = c->gncz;
+    int32_t *dc = nullptr; double *de = nullptr;
+    ALLOC(dc, c->nranks + 1); ALLOC(de, c->gncz + 1);
+    CK(cudaMemcpy(dc, c->cuts, (c->nranks + 1) * sizeof(int32_t), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(de, c->gz_edge, (c->gncz + 1) * sizeof(double), cudaMemcpyHostToDevice));
+    p.cuts = dc; p.gz_edge = de;
+    p.g_e0z = c->gz_edge[0];
+    p.g_inv_dz = (double)c->gncz / (c->gz_edge[c->gncz] - c->gz_edge[0]);
+    p.up_thr = c->rank + 1 < c->nranks ? c->gz_lo[c->cuts[c->rank + 1]] : INFINITY;
+    p.down_thr = c->rank > 0 ? c->gz_edge[c->cuts[c->rank]] : -INFINITY;
+    p.xf_cap = c->xfer_capacity; p.bnd_cap = c->bnd_capacity;
+    p.xf_send = (double *)c->xfer_send; p.xf_recv = (const double *)c->xfer_recv;
+    p.bnd_send[0] = (double *)c->bnd_send_up; p.bnd_send[1] = (double *)c->bnd_send_down;
+    p.bnd_recv[0] = (const double *)c->bnd_recv_up; p.bnd_recv[1] = (const double *)c->bnd_recv_down;
+    p.rel_cap = (int32_t)std::min<int64_t>(std::max<int64_t>(h->cap / 8, 1 << 16), 1 << 24);
+    p.foreign_cap = std::max(c->bnd_capacity * 16, 4096);
+    ALLOC(h->d_counters, c->nranks + 8);
+    CK(cudaMemset(h->d_counters, 0, (c->nranks + 8) * sizeof(int32_t)));
+    p.xf_count = h->d_counters; p.n_in = h->d_counters + c->nranks; p.bnd_n = h->d_counters + c->nranks + 1;
+    p.rel_count = h->d_counters + c->nranks + 3; p.n_foreign = h->d_counters + c->nranks + 4;
+    ALLOC(p.bnd_dirty[0], p.bnd_cap); ALLOC(p.bnd_dirty[1], p.bnd_cap);
+    ALLOC(p.rel_id, p.rel_cap); ALLOC(p.rel_slot, p.rel_cap); ALLOC(p.skey, h->cap);
+    ALLOC(h->d_slab_overflow, 1);
+    CK(cudaMemset(h->d_slab_overflow, 0, sizeof(unsigned long long)));
+    p.slab_overflow = h->d_slab_overflow;
+    p.group_done = -1;
+    h->slab = true;
+    CK(cudaDeviceSynchronize());
+    return AMC_OK;
+}
+
+static int slab_check(amc_handle *h)
+{
+    if (!h) return AMC_E_INVALID;
+    if (!h->slab) return h->fail(AMC_E_STATE, "amc_slab_enable has not been called");
+    CK(cudaSetDevice(h->device));
+    return AMC_OK;
+}
+
+extern "C" int amc_slab_advect(amc_handle *h)
+{
+    int rc = slab_check(h);
+    if (rc != AMC_OK) return rc;
+    P &p = h->p;
+    p.stats = h->d_stats;
+    p.step = h->step_index++;
+    CK(cudaMemsetAsync(h->d_stats, 0, sizeof(StatsDev), h->stream));
+    CK(cudaMemsetAsync(h->d_counters, 0, (p.nranks + 8) * sizeof(int32_t), h->stream));
+    CK(cudaMemsetAsync(p.band_count, 0, (h->n_buckets + 1) * sizeof(int32_t), h->stream));
+    CK(cudaMemsetAsync(p.rest_count, 0, (h->n_buckets + 1) * sizeof(int32_t), h->stream));
+    int phase = PH_DRIFT | PH_WALLS | (p.kind != AMC_KIND_CUBE ? PH_RECAP : 0) | PH_KEYS;
+    if (h->n) k_advect<<<grid_for(h->n, ADVECT_THREADS), ADVECT_THREADS, 0, h->stream>>>(p, phase);
+    k_xfer_headers<<<1, 32, 0, h->stream>>>(p);
+    CK(cudaGetLastError());
+    return AMC_OK;
+}
+
+extern "C" int amc_slab_sort(amc_handle *h, int64_t *n_resident)
+{
+    int rc = slab_check(h);
+    if (rc != AMC_OK) return rc;
+    P &p = h->p;
+    int64_t bound = h->n + (int64_t)p.nranks * p.xf_cap;
+    if (bound > h->cap) bound = h->cap;
+    dim3 ug(grid_for(p.xf_cap, ADVECT_THREADS), p.nranks);
+    k_xfer_unpack<<<ug, ADVECT_THREADS, 0, h->stream>>>(p);
+    int m = h->n_buckets;
+    int ntiles = (m + SCAN_TILE - 1) / SCAN_TILE;
+    k_scan_tiles<<<ntiles, SCAN_THREADS, 0, h->stream>>>(p.band_count, p.rest_count, p.cell_start, h->d_tile_sums, m);
+    k_scan_sums<<<1, SCAN_THREADS, 0, h->stream>>>(h->d_tile_sums, ntiles);
+    k_scan_add<<<ntiles, SCAN_THREADS, 0, h->stream>>>(p.cell_start, h->d_tile_sums, m, 0);
+    if (bound) k_scatter<<<grid_for(bound, ADVECT_THREADS), ADVECT_THREADS, 0, h->stream>>>(p);
+    CK(cudaGetLastError());
+    std::swap(p.a, p.b);
+    int32_t counts[2] = {0, 0}; // resident = start of the GONE bucket; n_in for the capacity check
+    CK(cudaMemcpyAsync(&counts[0], p.cell_start + (p.ncell_pad + 1), sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(&counts[1], p.n_in, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    unsigned long long ovf = 0;
+    CK(cudaMemcpyAsync(&ovf, h->d_slab_overflow, sizeof(ovf), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (ovf) return h->fail(AMC_E_CAPACITY, "slab exchange buffer overflow (raise xfer_capacity / bnd_capacity)");
+    if (h->n + counts[1] > h->cap) return h->fail(AMC_E_CAPACITY, "max_particles too small for the immigrants of this step");
+    h->n = counts[0];
+    p.n = h->n;
+    if (n_resident) *n_resident = h->n;
+    return AMC_OK;
+}
+
+extern "C" int amc_slab_pairs_begin(amc_handle *h)
+{
+    int rc = slab_check(h);
+    if (rc != AMC_OK) return rc;
+    P &p = h->p;
+    p.group_done = -1;
+    k_pp_begin<<<1, 256, 0, h->stream>>>(p);
+    CK(cudaMemsetAsync(p.wl_count, 0, 8 * sizeof(int32_t), h->stream));
+    int ncell = p.nc[0] * p.nc[1] * p.nc[2];
+    k_build_worklist<<<grid_for(ncell, ADVECT_THREADS), ADVECT_THREADS, 0, h->stream>>>(p);
+    dim3 pg(grid_for(p.bnd_cap, ADVECT_THREADS), 2);
+    k_bnd_pack<<<pg, ADVECT_THREADS, 0, h->stream>>>(p); // immigrants that landed in the top band
+    k_bnd_reset<<<1, 32, 0, h->stream>>>(p);
+    CK(cudaGetLastError());
+    return AMC_OK;
+}
+
+extern "C" int amc_slab_group(amc_handle *h, int32_t g)
+{
+    int rc = slab_check(h);
+    if (rc != AMC_OK) return rc;
+    if (g < 0 || g > 7) return h->fail(AMC_E_INVALID, "group out of range");
+    P &p = h->p;
+    int ncell = p.nc[0] * p.nc[1] * p.nc[2];
+    unsigned grid = (unsigned)std::min<int64_t>((int64_t)h->pair_grid, std::max<int64_t>(ncell / 8, 1));
+    if (h->n) k_pairs_group<<<grid, PAIR_THREADS, 0, h->stream>>>(p, g);
+    dim3 pg(grid_for(p.bnd_cap, ADVECT_THREADS), 2);
+    k_bnd_pack<<<pg, ADVECT_THREADS, 0, h->stream>>>(p);
+    k_bnd_reset<<<1, 32, 0, h->stream>>>(p);
+    CK(cudaGetLastError());
+    return AMC_OK;
+}
+
+extern "C" int amc_slab_apply(amc_handle *h, int32_t group_done)
+{
+    int rc = slab_check(h);
+    if (rc != AMC_OK) return rc;
+    P &p = h->p;
+    p.group_done = group_done;
+    if (p.srank + 1 < p.nranks) k_bnd_apply<<<p.bnd_cap, 128, 0, h->stream>>>(p, 0);
+    if (p.srank > 0) k_bnd_apply<<<p.bnd_cap, 128, 0, h->stream>>>(p, 1);
+    CK(cudaGetLastError());
+    return AMC_OK;
+}
+
+extern "C" int amc_slab_finish(amc_handle *h, amc_step_stats *stats)
+{
+    int rc = slab_check(h);
+    if (rc != AMC_OK) return rc;
+    P &p = h->p;
+    int32_t nf = 0;
+    CK(cudaMemcpyAsync(&nf, p.n_foreign, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    if (h->n && p.kind != AMC_KIND_CUBE) k_recapture_post<<<grid_for(h->n, ADVECT_THREADS), ADVECT_THREADS, 0, h->stream>>>(p);
+    unsigned long long ovf = 0;
+    CK(cudaMemcpyAsync(&ovf, h->d_slab_overflow, sizeof(ovf), cudaMemcpyDeviceToHost, h->stream));
+    rc = phase_end(h, stats);
+    if (rc != AMC_OK) return rc;
+    if (ovf) return h->fail(AMC_E_CAPACITY, "slab exchange buffer overflow (raise xfer_capacity / bnd_capacity)");
+    h->n += nf; // foreign copies appended behind the sorted particles; dropped by the next amc_slab_advect
+    p.n = h->n;
+    return AMC_OK;
+}
+
+extern "C" int amc_slab_get_owned(amc_handle *h, int64_t cap, int64_t *n, int64_t *ids, double *x, double *y, double *z,
+                                  double *vx, double *vy, double *vz, double *dist, double *dist_x, double *dist_y,
+                                  double *dist_z, uint8_t *flag)
+{
+    int rc = slab_check(h);
+    if (rc != AMC_OK) return rc;
+    P &p = h->p;
+    int32_t *cnt = h->d_counters + p.nranks + 5;
+    CK(cudaMemsetAsync(cnt, 0, sizeof(int32_t), h->stream));
+    if (h->n) k_compact_owned<<<grid_for(h->n, ADVECT_THREADS), ADVECT_THREADS, 0, h->stream>>>(p, cnt);
+    int32_t c = 0;
+    CK(cudaMemcpyAsync(&c, cnt, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (n) *n = c;
+    if (c > cap) return h->fail(AMC_E_CAPACITY, "caller buffers too small for the owned particles");
+    Arrays &b = p.b;
+    double *dst[10] = {x, y, z, vx, vy, vz, dist, dist_x, dist_y, dist_z};
+    const double *src[10] = {b.x, b.y, b.z, b.vx, b.vy, b.vz, b.d, b.dx, b.dy, b.dz};
+    for (int k = 0; k < 10; k++)
+        if (dst[k] && c) CK(cudaMemcpyAsync(dst[k], src[k], c * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (flag && c) CK(cudaMemcpyAsync(flag, b.flag, c, cudaMemcpyDeviceToHost, h->stream));
+    std::vector<int32_t> tmp((size_t)c);
+    if (ids && c) CK(cudaMemcpyAsync(tmp.data(), b.id, c * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (ids) for (int32_t k = 0; k < c; k++) ids[k] = tmp[(size_t)k];
     return AMC_OK;
 }

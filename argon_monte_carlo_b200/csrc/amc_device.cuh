@@ -11,6 +11,15 @@
 
 #define AMC_FLAG_PATH 1u /* full_path_traveled (Pore:392) */
 #define AMC_FLAG_ESC 2u  /* transient: particle left its sorted owner cell during the pair pass */
+/* slab decomposition (multi-GPU), all transient within one timestep */
+#define AMC_FLAG_GHOST 4u     /* copy of a particle owned by a neighbouring rank */
+#define AMC_FLAG_REL_UP 8u    /* the rank above holds a copy of / owns this particle */
+#define AMC_FLAG_REL_DOWN 16u /* the rank below holds a copy of / owns this particle */
+#define AMC_FLAG_LATE_UP 32u  /* immigrant that landed in the top band: export it before the first group */
+#define AMC_FLAG_DIRTY_UP 64u  /* already queued for the boundary exchange of the current group */
+#define AMC_FLAG_DIRTY_DOWN 128u
+#define AMC_FLAG_KEEP (AMC_FLAG_PATH | AMC_FLAG_GHOST | AMC_FLAG_REL_UP | AMC_FLAG_REL_DOWN)
+#define AMC_REC 12            /* doubles per exchanged particle record: 10 state, id, flags */
 
 #define AMC_MAX_MEMBERS 512  /* particles per reference cell incl. overlap band (reference: <= 308) */
 #define AMC_MAX_CAND 128     /* simultaneously overlapping pairs per cell visit */
@@ -72,6 +81,32 @@ struct P {
     int32_t *wl_count;    /* [8] */
     int32_t *cell_active; /* [8][wl_stride] 1 = cell is in its group's worklist */
     int32_t wl_stride;    /* reference cells per colour group */
+    int32_t nh[3];        /* reference cells per axis and parity class: (nc+1)/2 */
+    /* ---- slab decomposition along z (multi-GPU); slab == 0: single domain */
+    int32_t slab, srank, nranks; /* srank: this handle's rank in the slab decomposition */
+    int32_t zoff;             /* global z index of local cell layer 0 */
+    const int32_t *cuts;      /* [nranks+1] global layer cuts */
+    const double *gz_edge;    /* global z edges [gncz+1] */
+    int32_t gncz;
+    double g_e0z, g_inv_dz;
+    double up_thr, down_thr;  /* lo_global[Z_{r+1}] (+inf on the last rank), edge_global[Z_r] (-inf on rank 0) */
+    double *xf_send;          /* [nranks][xf_cap+1] records, record 0 = header (count) */
+    const double *xf_recv;
+    int32_t *xf_count;        /* [nranks] */
+    int32_t xf_cap;
+    int32_t *n_in;            /* particles unpacked from xf_recv in this step */
+    int32_t *bnd_dirty[2];    /* [0] = up, [1] = down: slots moved in the current group that the neighbour must see */
+    int32_t *bnd_n;           /* [2] */
+    int32_t bnd_cap;
+    double *bnd_send[2];
+    const double *bnd_recv[2];
+    int32_t *rel_id, *rel_slot, *rel_count; /* particles a neighbour may send updates for: id -> slot */
+    int32_t rel_cap;
+    int32_t *skey;            /* owner key each slot was sorted into (-1: appended foreign copy) */
+    int32_t *n_foreign;       /* foreign copies appended after the sort */
+    int32_t foreign_cap;
+    int32_t group_done;       /* last finished colour group (-1 before the first) */
+    unsigned long long *slab_overflow;
     int32_t esc_cap;
     int32_t *esc_count;
     int32_t *esc_slot;

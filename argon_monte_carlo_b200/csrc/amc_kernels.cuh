@@ -36,6 +36,10 @@ __global__ void __launch_bounds__(ADVECT_THREADS) k_advect(const __grid_constant
     if (s >= p.n) return;
     Part q;
     load_part(p.a, s, q);
+    if (p.slab && (q.flag & AMC_FLAG_GHOST)) { // last step's copy of a neighbour's particle: drop it
+        if (phase & PH_KEYS) { p.key[s] = p.ncell_pad + 1; p.rank[s] = ~atomicAdd(&p.rest_count[p.ncell_pad + 1], 1); }
+        return;
+    }
     q.flag &= AMC_FLAG_PATH;
     int32_t id = p.a.id[s];
     if (phase & PH_RECAP_POST) { // recapture that closes the previous step's pair pass (Pore:550 / Temp:843-845)
@@ -72,6 +76,33 @@ __global__ void __launch_bounds__(ADVECT_THREADS) k_advect(const __grid_constant
                 int after = temp_oob(p.g, q);
                 if (after) atomicAdd(&p.stats->oob_walls_after, (unsigned long long)after);
             }
+        }
+    }
+    if ((phase & PH_KEYS) && p.slab) {
+        // slab decomposition: the rank that owns the particle's global z layer keeps it; everything
+        // else is packed for that rank.  A kept particle inside the overlap band below the upper cut is
+        // also sent up as a ghost copy (the cells of the rank above read it as a band member).
+        int gz = owner_axis(p.gz_edge, p.gncz, p.g_e0z, p.g_inv_dz, q.z);
+        int layer = gz < 0 ? 0 : (gz >= p.gncz ? p.gncz - 1 : gz);
+        int dest = 0;
+        while (dest + 1 < p.nranks && layer >= p.cuts[dest + 1]) dest++;
+        bool ghost_up = dest == p.srank && p.srank + 1 < p.nranks && q.z > p.up_thr;
+        if (ghost_up) q.flag |= AMC_FLAG_REL_UP;
+        if (dest != p.srank || ghost_up) {
+            int to = dest != p.srank ? dest : p.srank + 1;
+            int j = atomicAdd(&p.xf_count[to], 1);
+            if (j < p.xf_cap) {
+                double *r = p.xf_send + ((size_t)to * (p.xf_cap + 1) + 1 + j) * AMC_REC;
+                r[0] = q.x; r[1] = q.y; r[2] = q.z; r[3] = q.vx; r[4] = q.vy; r[5] = q.vz;
+                r[6] = q.d; r[7] = q.dx; r[8] = q.dy; r[9] = q.dz; r[10] = (double)id;
+                r[11] = (double)((q.flag & AMC_FLAG_PATH) | (dest != p.srank ? 0u : (AMC_FLAG_GHOST | AMC_FLAG_REL_DOWN)));
+            } else atomicAdd(p.slab_overflow, 1ull);
+        }
+        if (dest != p.srank) { // emigrant: leaves this rank's arrays at the coming sort
+            store_part(p.a, s, q);
+            p.key[s] = p.ncell_pad + 1;
+            p.rank[s] = ~atomicAdd(&p.rest_count[p.ncell_pad + 1], 1);
+            return;
         }
     }
     if (phase & (PH_DRIFT | PH_WALLS | PH_RECAP | PH_RECAP_POST)) store_part(p.a, s, q);
@@ -155,14 +186,27 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_add(int32_t *out, const i
 __global__ void __launch_bounds__(ADVECT_THREADS) k_scatter(const __grid_constant__ P p)
 {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= p.n) return;
+    if (s >= p.n + (p.slab ? *p.n_in : 0)) return;
     int32_t k = p.key[s], r = p.rank[s];
     int64_t t = (int64_t)p.cell_start[k] + (r >= 0 ? r : p.band_count[k] + ~r);
     p.b.x[t] = p.a.x[s]; p.b.y[t] = p.a.y[s]; p.b.z[t] = p.a.z[s];
     p.b.vx[t] = p.a.vx[s]; p.b.vy[t] = p.a.vy[s]; p.b.vz[t] = p.a.vz[s];
     p.b.d[t] = p.a.d[s]; p.b.dx[t] = p.a.dx[s]; p.b.dy[t] = p.a.dy[s]; p.b.dz[t] = p.a.dz[s];
-    p.b.flag[t] = p.a.flag[s] & AMC_FLAG_PATH;
-    p.b.id[t] = p.a.id[s];
+    unsigned fl = p.a.flag[s];
+    int32_t id = p.a.id[s];
+    p.b.flag[t] = (uint8_t)(fl & (p.slab ? AMC_FLAG_KEEP : AMC_FLAG_PATH));
+    p.b.id[t] = id;
+    if (p.slab) {
+        p.skey[t] = k;
+        if (k <= p.ncell_pad && (fl & (AMC_FLAG_GHOST | AMC_FLAG_REL_UP | AMC_FLAG_REL_DOWN))) {
+            int j = atomicAdd(p.rel_count, 1);
+            if (j < p.rel_cap) { p.rel_id[j] = id; p.rel_slot[j] = (int32_t)t; } else atomicAdd(p.slab_overflow, 1ull);
+        }
+        if (k <= p.ncell_pad && (fl & AMC_FLAG_LATE_UP)) {
+            int j = atomicAdd(&p.bnd_n[0], 1);
+            if (j < p.bnd_cap) p.bnd_dirty[0][j] = (int32_t)t; else atomicAdd(p.slab_overflow, 1ull);
+        }
+    }
 }
 
 // gather back to original index order (amc_get_state)
@@ -194,6 +238,7 @@ __global__ void __launch_bounds__(ADVECT_THREADS) k_recapture_post(const __grid_
 {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= p.n) return;
+    if (p.slab && (p.a.flag[s] & AMC_FLAG_GHOST)) return; /* the owning rank recaptures it */
     Part q;
     q.x = p.a.x[s]; q.y = p.a.y[s]; q.z = p.a.z[s];
     double x0 = q.x, y0 = q.y, z0 = q.z;
@@ -301,6 +346,32 @@ __device__ __noinline__ void resolve_pair(const P &p, CellShared &S, int m1, int
         unsigned long long k = atomicAdd(p.pair_count, 1ull);
         if ((int64_t)k < p.pair_cap) { p.pair_hi[k] = S.id[m2]; p.pair_lo[k] = S.id[m1]; p.pair_group[k] = group; p.pair_cell[k] = cell; }
     }
+    if (p.slab) {
+        // slab decomposition: a moved particle that a neighbouring rank holds a copy of (or now
+        // needs, because it entered the band at a cut / crossed it) is queued for the boundary
+        // exchange that follows this colour group
+        for (int w = 0; w < 2; w++) {
+            int s = w ? s2 : s1;
+            double z = w ? z2 : z1;
+            uint32_t &f = w ? f2 : f1;
+            bool up = (f & AMC_FLAG_REL_UP) || z > p.up_thr, down = (f & AMC_FLAG_REL_DOWN) || z < p.down_thr;
+            if ((up && !(f & AMC_FLAG_REL_UP)) || (down && !(f & AMC_FLAG_REL_DOWN))) {
+                if (!(f & (AMC_FLAG_REL_UP | AMC_FLAG_REL_DOWN | AMC_FLAG_GHOST))) {
+                    int j = atomicAdd(p.rel_count, 1);
+                    if (j < p.rel_cap) { p.rel_id[j] = S.id[w ? m2 : m1]; p.rel_slot[j] = s; } else atomicAdd(p.slab_overflow, 1ull);
+                }
+                f |= (up ? AMC_FLAG_REL_UP : 0u) | (down ? AMC_FLAG_REL_DOWN : 0u);
+            }
+            for (int dir = 0; dir < 2; dir++) {
+                unsigned bit = dir == 0 ? AMC_FLAG_DIRTY_UP : AMC_FLAG_DIRTY_DOWN;
+                if ((dir == 0 ? up : down) && !(f & bit)) { /* once per group and direction */
+                    f |= bit;
+                    int j = atomicAdd(&p.bnd_n[dir], 1);
+                    if (j < p.bnd_cap) p.bnd_dirty[dir][j] = s; else atomicAdd(p.slab_overflow, 1ull);
+                }
+            }
+        }
+    }
     if (p.pp_mode == AMC_PP_GROUPS) {
         // A moved particle whose owner cell changed can no longer be found through the sorted
         // layout: publish its member cell for every later colour group in the escaped list.
@@ -328,8 +399,8 @@ __device__ __noinline__ void resolve_pair(const P &p, CellShared &S, int m1, int
             for (int g2 = group + 1; g2 < 8; g2++) {
                 int cx = member_axis(p.edge[0], p.lo[0], p.nc[0], o[0], (g2 >> 2) & 1, x);
                 int cy = member_axis(p.edge[1], p.lo[1], p.nc[1], o[1], (g2 >> 1) & 1, y);
-                int cz = member_axis(p.edge[2], p.lo[2], p.nc[2], o[2], g2 & 1, z);
-                int32_t cc = (cx < 0 || cy < 0 || cz < 0) ? -1 : ((cx >> 1) * (p.nc[1] >> 1) + (cy >> 1)) * (p.nc[2] >> 1) + (cz >> 1);
+                int cz = member_axis(p.edge[2], p.lo[2], p.nc[2], o[2], (g2 ^ p.zoff) & 1, z);
+                int32_t cc = (cx < 0 || cy < 0 || cz < 0) ? -1 : ((cx >> 1) * p.nh[1] + (cy >> 1)) * p.nh[2] + (cz >> 1);
                 p.esc_cell[e * 8 + g2] = cc;
                 if (cc >= 0 && atomicExch(&p.cell_active[(size_t)g2 * p.wl_stride + cc], 1) == 0)
                     p.wl[(size_t)g2 * p.wl_stride + atomicAdd(&p.wl_count[g2], 1)] = cc; /* group g2 has not started yet */
@@ -473,8 +544,8 @@ __global__ void __launch_bounds__(ADVECT_THREADS) k_build_worklist(const __grid_
         int oc = ((kx + 1 - (nb >> 2)) * p.pnc[1] + (ky + 1 - ((nb >> 1) & 1))) * p.pnc[2] + (kz + 1 - (nb & 1));
         total += nb == 0 ? p.cell_start[oc + 1] - p.cell_start[oc] : p.band_count[oc];
     }
-    int group = ((kx & 1) << 2) | ((ky & 1) << 1) | (kz & 1);
-    int cell = ((kx >> 1) * (p.nc[1] >> 1) + (ky >> 1)) * (p.nc[2] >> 1) + (kz >> 1);
+    int group = ((kx & 1) << 2) | ((ky & 1) << 1) | ((kz + p.zoff) & 1); /* colour group from the GLOBAL z parity */
+    int cell = ((kx >> 1) * p.nh[1] + (ky >> 1)) * p.nh[2] + (kz >> 1);
     int active = total >= 2;
     p.cell_active[(size_t)group * p.wl_stride + cell] = active;
     if (active) p.wl[(size_t)group * p.wl_stride + atomicAdd(&p.wl_count[group], 1)] = cell;
@@ -487,7 +558,7 @@ __global__ void __launch_bounds__(PAIR_THREADS, 8) k_pairs_group(const __grid_co
     __shared__ double s_lo[3], s_hi[3];
     __shared__ int s_ne;
     const int tid = threadIdx.x;
-    const int nhy = p.nc[1] >> 1, nhz = p.nc[2] >> 1;
+    const int nhy = p.nh[1], nhz = p.nh[2];
     const Arrays &A = p.a;
     const int nwork = p.wl_count[group];
     const int32_t *wl = p.wl + (size_t)group * p.wl_stride;
@@ -500,7 +571,7 @@ __global__ void __launch_bounds__(PAIR_THREADS, 8) k_pairs_group(const __grid_co
             // lanes 0..7: the 8 candidate owner-cell ranges (own cell: all of it; the 7 low-side
             // neighbours: their band prefix); lanes 0..2 also fetch the bounds of one axis
             const int hz = cell % nhz, hy = (cell / nhz) % nhy, hx = cell / (nhz * nhy);
-            const int kx = 2 * hx + ((group >> 2) & 1), ky = 2 * hy + ((group >> 1) & 1), kz = 2 * hz + (group & 1);
+            const int kx = 2 * hx + ((group >> 2) & 1), ky = 2 * hy + ((group >> 1) & 1), kz = 2 * hz + ((group ^ p.zoff) & 1);
             int ox = kx + 1 - (tid >> 2), oy = ky + 1 - ((tid >> 1) & 1), oz = kz + 1 - (tid & 1);
             int oc = (ox * p.pnc[1] + oy) * p.pnc[2] + oz;
             int beg = p.cell_start[oc], len = tid == 0 ? p.cell_start[oc + 1] - beg : p.band_count[oc];
@@ -693,4 +764,161 @@ __global__ void k_iota(int32_t *ids, int64_t n)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) ids[i] = (int32_t)i;
+}
+
+// ================================================================================================
+// Slab decomposition along z (multi-GPU).  Records are AMC_REC doubles: 10 state values, the global
+// particle id and flag bits; every buffer starts with one header record whose first double is the
+// record count.  Buffers are exchanged by the host side (NCCL through torch.distributed, or plain
+// device copies when several ranks share one GPU in the tests).
+
+// write the per-destination counts into the header records of the transfer buffer
+__global__ void k_xfer_headers(const __grid_constant__ P p)
+{
+    int d = threadIdx.x;
+    if (d < p.nranks) {
+        int c = p.xf_count[d];
+        p.xf_send[(size_t)d * (p.xf_cap + 1) * AMC_REC] = (double)(c < p.xf_cap ? c : p.xf_cap);
+    }
+}
+
+// unpack immigrants and ghost copies received from every rank behind the current particles
+// (slots n .. n + n_in) and give them owner keys / ranks like k_advect does
+__global__ void __launch_bounds__(ADVECT_THREADS) k_xfer_unpack(const __grid_constant__ P p)
+{
+    int src = blockIdx.y;
+    const double *blk = p.xf_recv + (size_t)src * (p.xf_cap + 1) * AMC_REC;
+    int cnt = (int)blk[0];
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= cnt) return;
+    const double *r = blk + (size_t)(1 + j) * AMC_REC;
+    int64_t s = p.n + atomicAdd(p.n_in, 1);
+    Part q;
+    q.x = r[0]; q.y = r[1]; q.z = r[2]; q.vx = r[3]; q.vy = r[4]; q.vz = r[5]; q.d = r[6]; q.dx = r[7]; q.dy = r[8]; q.dz = r[9];
+    q.flag = (uint32_t)r[11];
+    int o[3];
+    int32_t k = owner_key(p, q.x, q.y, q.z, o);
+    if (!(q.flag & AMC_FLAG_GHOST) && p.srank + 1 < p.nranks && q.z > p.up_thr && k != p.ncell_pad)
+        q.flag |= AMC_FLAG_REL_UP | AMC_FLAG_LATE_UP; /* immigrant inside the band below the upper cut */
+    store_part(p.a, s, q);
+    p.a.id[s] = (int32_t)r[10];
+    p.key[s] = k;
+    if (k != p.ncell_pad && any_band(p, q.x, q.y, q.z, o)) p.rank[s] = atomicAdd(&p.band_count[k], 1);
+    else p.rank[s] = ~atomicAdd(&p.rest_count[k], 1);
+}
+
+// after a colour group: turn the dirty slots of one direction into update records
+__global__ void __launch_bounds__(ADVECT_THREADS) k_bnd_pack(const __grid_constant__ P p)
+{
+    int dir = blockIdx.y;
+    int cnt = min(p.bnd_n[dir], p.bnd_cap);
+    double *buf = p.bnd_send[dir];
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j == 0) buf[0] = (double)cnt;
+    if (j >= cnt) return;
+    int s = p.bnd_dirty[dir][j];
+    const Arrays &A = p.a;
+    double *r = buf + (size_t)(1 + j) * AMC_REC;
+    r[0] = A.x[s]; r[1] = A.y[s]; r[2] = A.z[s]; r[3] = A.vx[s]; r[4] = A.vy[s]; r[5] = A.vz[s];
+    r[6] = A.d[s]; r[7] = A.dx[s]; r[8] = A.dy[s]; r[9] = A.dz[s]; r[10] = (double)A.id[s];
+    r[11] = (double)(A.flag[s] & AMC_FLAG_PATH);
+    // clear this direction's "queued" bit (32-bit atomic on the word that holds the flag byte)
+    unsigned bit = dir == 0 ? AMC_FLAG_DIRTY_UP : AMC_FLAG_DIRTY_DOWN;
+    uintptr_t addr = (uintptr_t)(A.flag + s);
+    atomicAnd((unsigned *)(addr & ~(uintptr_t)3), ~(bit << (8 * (addr & 3))));
+}
+__global__ void k_bnd_reset(const __grid_constant__ P p)
+{
+    if (threadIdx.x < 2) p.bnd_n[threadIdx.x] = 0;
+}
+
+// apply the update records received from one neighbour (dir 0: from the rank above, 1: from below).
+// One CTA per record: find the particle by id among the related particles, or append it as a new
+// foreign copy; then make sure the later colour groups of this pass can find it (escaped list).
+__global__ void __launch_bounds__(128) k_bnd_apply(const __grid_constant__ P p, const int dir)
+{
+    __shared__ int s_slot, s_esc;
+    const double *buf = p.bnd_recv[dir];
+    int cnt = (int)buf[0];
+    int j = blockIdx.x;
+    if (j >= cnt) return;
+    const double *r = buf + (size_t)(1 + j) * AMC_REC;
+    const int32_t id = (int32_t)r[10];
+    const int tid = threadIdx.x;
+    if (tid == 0) { s_slot = -1; s_esc = -1; }
+    __syncthreads();
+    int nrel = min(*p.rel_count, p.rel_cap);
+    for (int k = tid; k < nrel; k += blockDim.x)
+        if (p.rel_id[k] == id) s_slot = p.rel_slot[k];
+    __syncthreads();
+    const Arrays &A = p.a;
+    if (tid == 0 && s_slot < 0) { // unknown here: a particle the neighbour moved into this rank's reach
+        int f = atomicAdd(p.n_foreign, 1);
+        if (f >= p.foreign_cap) { atomicAdd(p.slab_overflow, 1ull); s_slot = -2; }
+        else {
+            int s = (int)p.n + f;
+            s_slot = s;
+            A.id[s] = id;
+            A.flag[s] = (uint8_t)(AMC_FLAG_GHOST | (dir == 0 ? AMC_FLAG_REL_UP : AMC_FLAG_REL_DOWN));
+            p.skey[s] = -1;
+            int k = atomicAdd(p.rel_count, 1);
+            if (k < p.rel_cap) { p.rel_id[k] = id; p.rel_slot[k] = s; } else atomicAdd(p.slab_overflow, 1ull);
+        }
+    }
+    __syncthreads();
+    const int s = s_slot;
+    if (s < 0) return;
+    const unsigned fl = A.flag[s];
+    if (fl & AMC_FLAG_ESC) { // already on the escaped list: find its entry
+        int ne = min(*p.esc_count, p.esc_cap);
+        for (int e = tid; e < ne; e += blockDim.x)
+            if (p.esc_slot[e] == s) s_esc = e;
+    }
+    __syncthreads();
+    if (tid != 0) return;
+    double x = r[0], y = r[1], z = r[2];
+    A.x[s] = x; A.y[s] = y; A.z[s] = z; A.vx[s] = r[3]; A.vy[s] = r[4]; A.vz[s] = r[5];
+    A.d[s] = r[6]; A.dx[s] = r[7]; A.dy[s] = r[8]; A.dz[s] = r[9];
+    unsigned nf = (fl & ~AMC_FLAG_PATH) | ((unsigned)r[11] & AMC_FLAG_PATH);
+    int o[3];
+    int32_t k = owner_key(p, x, y, z, o);
+    int e = s_esc;
+    bool findable = false;
+    if (e < 0) {
+        int32_t sk = p.skey[s];
+        findable = sk >= 0 && k == sk && (s < p.cell_start[sk] + p.band_count[sk] || !any_band(p, x, y, z, o));
+    }
+    if (!findable) {
+        if (e < 0) {
+            e = atomicAdd(p.esc_count, 1);
+            if (e >= p.esc_cap) { atomicAdd(&p.stats->esc_overflow, 1ull); e = -1; }
+            else { p.esc_slot[e] = s; nf |= AMC_FLAG_ESC; }
+        }
+        if (e >= 0)
+            for (int g2 = p.group_done + 1; g2 < 8; g2++) {
+                int cx = member_axis(p.edge[0], p.lo[0], p.nc[0], o[0], (g2 >> 2) & 1, x);
+                int cy = member_axis(p.edge[1], p.lo[1], p.nc[1], o[1], (g2 >> 1) & 1, y);
+                int cz = member_axis(p.edge[2], p.lo[2], p.nc[2], o[2], (g2 ^ p.zoff) & 1, z);
+                int32_t cc = (cx < 0 || cy < 0 || cz < 0) ? -1 : ((cx >> 1) * p.nh[1] + (cy >> 1)) * p.nh[2] + (cz >> 1);
+                p.esc_cell[e * 8 + g2] = cc;
+                if (cc >= 0 && atomicExch(&p.cell_active[(size_t)g2 * p.wl_stride + cc], 1) == 0)
+                    p.wl[(size_t)g2 * p.wl_stride + atomicAdd(&p.wl_count[g2], 1)] = cc;
+            }
+    }
+    A.flag[s] = (uint8_t)nf;
+}
+
+// compact the particles this rank owns (everything that is not a ghost copy) into the b arrays
+__global__ void __launch_bounds__(ADVECT_THREADS) k_compact_owned(const __grid_constant__ P p, int32_t *count)
+{
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= p.n) return;
+    unsigned fl = p.a.flag[s];
+    if (fl & AMC_FLAG_GHOST) return;
+    int t = atomicAdd(count, 1);
+    p.b.x[t] = p.a.x[s]; p.b.y[t] = p.a.y[s]; p.b.z[t] = p.a.z[s];
+    p.b.vx[t] = p.a.vx[s]; p.b.vy[t] = p.a.vy[s]; p.b.vz[t] = p.a.vz[s];
+    p.b.d[t] = p.a.d[s]; p.b.dx[t] = p.a.dx[s]; p.b.dy[t] = p.a.dy[s]; p.b.dz[t] = p.a.dz[s];
+    p.b.flag[t] = fl & AMC_FLAG_PATH;
+    p.b.id[t] = p.a.id[s];
 }

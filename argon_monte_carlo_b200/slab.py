@@ -1,0 +1,317 @@
+"""Slab decomposition of one simulation along the pore axis z over several GPUs (BASELINE.json
+north_star: 1/2/4/8 B200 with halo exchange and particle migration every step).
+
+The reference has nothing like this (its only parallelism is a process pool over the cells of a
+colour group, Open_Air_Pore_MC.py:522-549); the requirement is that the decomposed run leaves the
+same results as the single-domain run.  Each rank owns the reference cells of a contiguous range of
+global z layers, cut on cell boundaries and balanced by particle count (62 % of the pore's particles
+sit in the two end caps).  Per timestep:
+
+  1. advect + walls on the owned particles; emigrants and ghost copies (particles inside the overlap
+     band below the upper cut) are packed per destination rank           amc_slab_advect
+  2. one all-to-all moves them                                             transport.alltoall
+  3. unpack + counting sort of owned + ghost particles                     amc_slab_sort
+  4. for each of the 8 colour groups (plus one round before the first): the pair kernel, then the few
+     particles moved by a collision that the neighbour also holds (or now needs) are exchanged with
+     the ranks above / below and applied                                   amc_slab_group / neighbors / amc_slab_apply
+  5. recapture, counters                                                   amc_slab_finish
+
+Every reference cell is processed by exactly one rank, in the same colour-group order, with members
+ordered by global particle index, and a particle touched on both sides of a cut is handed over after
+each group, so the N-rank run is bit-identical to the 1-rank run (tests/test_gpu_slab.py).
+
+Transports: `LocalTransport` (all ranks in this process, device copies; used by the single-GPU tests)
+and `DistTransport` (one rank per process over torch.distributed: NCCL on GPUs, gloo for the CPU
+test of the host logic).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from types import SimpleNamespace
+
+import numpy as np
+
+from . import amc
+
+REC = 12  # doubles per exchanged record
+
+
+class AmcSlabConfig(C.Structure):
+    _fields_ = [("rank", C.c_int32), ("nranks", C.c_int32), ("cuts", C.POINTER(C.c_int32)), ("gncz", C.c_int32),
+                ("gz_edge", amc.c_double_p), ("gz_lo", amc.c_double_p), ("xfer_capacity", C.c_int32),
+                ("bnd_capacity", C.c_int32), ("xfer_send", C.c_void_p), ("xfer_recv", C.c_void_p),
+                ("bnd_send_up", C.c_void_p), ("bnd_send_down", C.c_void_p), ("bnd_recv_up", C.c_void_p),
+                ("bnd_recv_down", C.c_void_p)]
+
+
+def owner_layer(z, edges):
+    """Global z layer of each particle, clamped into [0, ncz-1] like the device does for routing."""
+    k = np.searchsorted(edges, z, side="right") - 1
+    return np.clip(k, 0, len(edges) - 2)
+
+
+def balanced_cuts(z, edges, nranks, min_layers=2):
+    """Cut indices (nranks+1) on z-cell boundaries with ~equal particle counts per slab."""
+    ncz = len(edges) - 1
+    if nranks * min_layers > ncz:
+        raise ValueError("too many ranks for %d z layers" % ncz)
+    hist = np.bincount(owner_layer(np.asarray(z), np.asarray(edges)), minlength=ncz).astype(np.float64)
+    cum = np.concatenate([[0.0], np.cumsum(hist)])
+    cuts = [0]
+    for r in range(1, nranks):
+        target = cum[-1] * r / nranks
+        k = int(np.searchsorted(cum, target))
+        k = max(k, cuts[-1] + min_layers)
+        k = min(k, ncz - (nranks - r) * min_layers)
+        cuts.append(k)
+    cuts.append(ncz)
+    return np.array(cuts, dtype=np.int32)
+
+
+def local_grid(grid, z0, z1):
+    """The part of the global cell grid a rank owns: all of x and y, z layers [z0, z1)."""
+    return SimpleNamespace(nc=(grid.nc[0], grid.nc[1], int(z1 - z0)), c0=(grid.c0[0], grid.c0[1], grid.c0[2] + int(z0)),
+                           edge=[grid.edge[0], grid.edge[1], np.ascontiguousarray(grid.edge[2][z0:z1 + 1])],
+                           lo=[grid.lo[0], grid.lo[1], np.ascontiguousarray(grid.lo[2][z0:z1])])
+
+
+class SlabRank:
+    """One rank: a libamc handle restricted to its z layers plus its exchange buffers (torch tensors)."""
+
+    def __init__(self, cfg, rank, cuts, device, xfer_capacity, bnd_capacity, max_particles, seed=None, kind=None,
+                 taps=0, cheb=None):
+        import torch
+        self.rank, self.nranks, self.cuts = rank, len(cuts) - 1, cuts
+        self.device = device
+        g = cfg.grid
+        self.sim = amc.Simulation(cfg, kind=kind, device=device, seed=seed, grid=local_grid(g, cuts[rank], cuts[rank + 1]),
+                                  max_particles=max_particles, taps=taps, cheb=cheb)
+        dev = torch.device("cuda", device)
+        with torch.cuda.device(dev):
+            z = lambda *s: torch.zeros(*s, dtype=torch.float64, device=dev)
+            self.xfer_send, self.xfer_recv = z(self.nranks, xfer_capacity + 1, REC), z(self.nranks, xfer_capacity + 1, REC)
+            self.bnd_send_up, self.bnd_send_down = z(bnd_capacity + 1, REC), z(bnd_capacity + 1, REC)
+            self.bnd_recv_up, self.bnd_recv_down = z(bnd_capacity + 1, REC), z(bnd_capacity + 1, REC)
+            stream = torch.cuda.current_stream(dev).cuda_stream
+        c = AmcSlabConfig()
+        c.rank, c.nranks = rank, self.nranks
+        self._cuts = np.ascontiguousarray(cuts, dtype=np.int32)
+        self._edge = np.ascontiguousarray(g.edge[2], dtype=np.float64)
+        self._lo = np.ascontiguousarray(g.lo[2], dtype=np.float64)
+        c.cuts = self._cuts.ctypes.data_as(C.POINTER(C.c_int32))
+        c.gncz, c.gz_edge, c.gz_lo = g.nc[2], amc._dp(self._edge), amc._dp(self._lo)
+        c.xfer_capacity, c.bnd_capacity = xfer_capacity, bnd_capacity
+        c.xfer_send, c.xfer_recv = self.xfer_send.data_ptr(), self.xfer_recv.data_ptr()
+        c.bnd_send_up, c.bnd_send_down = self.bnd_send_up.data_ptr(), self.bnd_send_down.data_ptr()
+        c.bnd_recv_up, c.bnd_recv_down = self.bnd_recv_up.data_ptr(), self.bnd_recv_down.data_ptr()
+        lib, h = self.sim.lib, self.sim.h
+        self.sim._check(lib.amc_set_stream(h, C.c_void_p(stream)), "amc_set_stream")
+        self.sim._check(lib.amc_slab_enable(h, C.byref(c)), "amc_slab_enable")
+
+    def call(self, name, *args):
+        self.sim._check(getattr(self.sim.lib, name)(self.sim.h, *args), name)
+
+
+class LocalTransport:
+    """All ranks live in this process (possibly on one GPU): exchanges are device copies."""
+
+    def alltoall(self, ranks):
+        for dst in ranks:
+            for src in ranks:
+                dst.xfer_recv[src.rank].copy_(src.xfer_send[dst.rank], non_blocking=True)
+
+    def neighbors(self, ranks):
+        by_rank = {r.rank: r for r in ranks}
+        for r in ranks:
+            if r.rank + 1 in by_rank:
+                by_rank[r.rank + 1].bnd_recv_down.copy_(r.bnd_send_up, non_blocking=True)
+            if r.rank - 1 in by_rank:
+                by_rank[r.rank - 1].bnd_recv_up.copy_(r.bnd_send_down, non_blocking=True)
+
+    def allreduce_sum(self, value):
+        return value
+
+
+class DistTransport:
+    """One rank per process over torch.distributed (NCCL over NVLink on the GPU box; gloo on CPU tensors
+    in the host-logic test).  Fixed-size buffers, so no size negotiation and no host synchronisation."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist, self.group = dist, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.native_a2a = dist.get_backend(group) == "nccl"
+
+    def alltoall(self, ranks):
+        (r,) = ranks
+        if self.native_a2a:
+            self.dist.all_to_all_single(r.xfer_recv, r.xfer_send, group=self.group)
+            return
+        ops = []
+        for peer in range(self.world):
+            if peer == self.rank:
+                r.xfer_recv[peer].copy_(r.xfer_send[peer])
+                continue
+            ops.append(self.dist.P2POp(self.dist.isend, r.xfer_send[peer], peer, self.group))
+            ops.append(self.dist.P2POp(self.dist.irecv, r.xfer_recv[peer], peer, self.group))
+        for req in (self.dist.batch_isend_irecv(ops) if ops else []):
+            req.wait()
+
+    def neighbors(self, ranks):
+        (r,) = ranks
+        ops = []
+        if self.rank + 1 < self.world:
+            ops.append(self.dist.P2POp(self.dist.isend, r.bnd_send_up, self.rank + 1, self.group))
+            ops.append(self.dist.P2POp(self.dist.irecv, r.bnd_recv_up, self.rank + 1, self.group))
+        if self.rank > 0:
+            ops.append(self.dist.P2POp(self.dist.isend, r.bnd_send_down, self.rank - 1, self.group))
+            ops.append(self.dist.P2POp(self.dist.irecv, r.bnd_recv_down, self.rank - 1, self.group))
+        for req in (self.dist.batch_isend_irecv(ops) if ops else []):
+            req.wait()
+
+    def allreduce_sum(self, value):
+        import torch
+        t = torch.as_tensor(np.asarray(value, dtype=np.float64))
+        if self.dist.get_backend(self.group) == "nccl":
+            t = t.cuda()
+        self.dist.all_reduce(t, group=self.group)
+        return t.cpu().numpy()
+
+
+SUM_KEYS = ("wall_collisions", "pp_collisions", "pair_checks_ref", "pair_checks_exec", "oob_after_walls", "oob_after_pp",
+            "oob_after_walls_recapture", "oob_after_pp_recapture", "errors", "completed_paths", "dpz", "e_cold", "e_hot",
+            "collisions")
+
+
+class SlabSimulation:
+    """A simulation decomposed into `nranks` z slabs.  `local_ranks`: the ranks this process drives
+    (all of them with LocalTransport, exactly one with DistTransport)."""
+
+    def __init__(self, cfg, nranks, z_for_cuts, transport=None, local_ranks=None, devices=None, xfer_capacity=None,
+                 bnd_capacity=1024, slack=1.35, seed=None, kind=None, taps=0, cuts=None):
+        self.cfg, self.nranks = cfg, nranks
+        self.transport = transport or LocalTransport()
+        self.local_ranks = list(range(nranks)) if local_ranks is None else list(local_ranks)
+        g = cfg.grid
+        self.cuts = balanced_cuts(z_for_cuts, g.edge[2], nranks) if cuts is None else np.asarray(cuts, dtype=np.int32)
+        layer = owner_layer(np.asarray(z_for_cuts), g.edge[2])
+        per_rank = np.array([np.count_nonzero((layer >= self.cuts[r]) & (layer < self.cuts[r + 1])) for r in range(nranks)])
+        if xfer_capacity is None:   # migration + ghosts per step are a few 1e-3 of a slab's particles
+            xfer_capacity = int(max(4096, 0.02 * per_rank.max()))
+        cheb = None
+        if cfg.kind == "temp":
+            from .config import gap_energy_chebyshev
+            cheb = gap_energy_chebyshev(cfg, 16)
+        devices = devices or [0] * len(self.local_ranks)
+        self.ranks = [SlabRank(cfg, r, self.cuts, devices[i], xfer_capacity, bnd_capacity,
+                               int(per_rank[r] * slack) + nranks * xfer_capacity + 16 * bnd_capacity + 4096,
+                               seed=seed, kind=kind, taps=taps, cheb=cheb)
+                      for i, r in enumerate(self.local_ranks)]
+        self.n_global = 0
+
+    def set_state(self, x, y, z, vx, vy, vz, dist=None, dist_x=None, dist_y=None, dist_z=None, flag=None):
+        """Global arrays in original particle index order; each local rank takes the particles whose z
+        layer it owns (ids = global indices)."""
+        n = len(x)
+        self.n_global = n
+        layer = owner_layer(np.asarray(z), self.cfg.grid.edge[2])
+        opt = lambda a, m: None if a is None else np.asarray(a)[m]
+        for r in self.ranks:
+            m = (layer >= self.cuts[r.rank]) & (layer < self.cuts[r.rank + 1])
+            ids = np.nonzero(m)[0].astype(np.int64)
+            r.sim.set_state(np.asarray(x)[m], np.asarray(y)[m], np.asarray(z)[m], np.asarray(vx)[m], np.asarray(vy)[m],
+                            np.asarray(vz)[m], opt(dist, m), opt(dist_x, m), opt(dist_y, m), opt(dist_z, m), opt(flag, m))
+            r.call("amc_set_ids", ids.ctypes.data_as(amc.c_int64_p))
+
+    def step(self, n_steps=1, reduce=True):
+        """n_steps timesteps; returns per-step counter dicts summed over this process's ranks (and over
+        all processes when the transport is distributed and reduce=True)."""
+        out = []
+        T, R = self.transport, self.ranks
+        for _ in range(n_steps):
+            for r in R:
+                r.call("amc_slab_advect")
+            T.alltoall(R)
+            for r in R:
+                r.call("amc_slab_sort", None)
+            for r in R:
+                r.call("amc_slab_pairs_begin")
+            T.neighbors(R)
+            for r in R:
+                r.call("amc_slab_apply", C.c_int32(-1))
+            for g in range(8):
+                for r in R:
+                    r.call("amc_slab_group", C.c_int32(g))
+                T.neighbors(R)
+                for r in R:
+                    r.call("amc_slab_apply", C.c_int32(g))
+            tot = None
+            for r in R:
+                st = amc.AmcStepStats()
+                r.call("amc_slab_finish", C.byref(st))
+                d = st.as_dict()
+                if tot is None:
+                    tot = d
+                else:
+                    for k in SUM_KEYS:
+                        tot[k] = tot[k] + d[k]
+                    tot["wall_hits"] = tot["wall_hits"] + d["wall_hits"]
+            if reduce and not isinstance(T, LocalTransport):
+                vec = np.concatenate([[float(tot[k]) for k in SUM_KEYS], tot["wall_hits"].astype(np.float64)])
+                vec = T.allreduce_sum(vec)
+                for i, k in enumerate(SUM_KEYS):
+                    tot[k] = type(tot[k])(vec[i]) if not isinstance(tot[k], float) else float(vec[i])
+                tot["wall_hits"] = vec[len(SUM_KEYS):].astype(np.int64)
+            out.append(tot)
+        return out
+
+    def owned(self):
+        """Per local rank: (ids, dict of state arrays) of the particles it currently owns."""
+        res = []
+        keys = ("x", "y", "z", "vx", "vy", "vz", "dist", "dist_x", "dist_y", "dist_z")
+        for r in self.ranks:
+            cap = max(int(amc.load_library().amc_num_particles(r.sim.h)), 1)
+            ids = np.zeros(cap, dtype=np.int64)
+            arrs = {k: np.zeros(cap) for k in keys}
+            flag = np.zeros(cap, dtype=np.uint8)
+            n = C.c_int64(0)
+            r.call("amc_slab_get_owned", C.c_int64(cap), C.byref(n), ids.ctypes.data_as(amc.c_int64_p),
+                   *[amc._dp(arrs[k]) for k in keys], flag.ctypes.data_as(amc.c_uint8_p))
+            k = int(n.value)
+            d = {key: a[:k] for key, a in arrs.items()}
+            d["flag"] = flag[:k]
+            res.append((ids[:k], d))
+        return res
+
+    def get_state(self):
+        """Global arrays in original index order assembled from the local ranks (all ranks local)."""
+        keys = ("x", "y", "z", "vx", "vy", "vz", "dist", "dist_x", "dist_y", "dist_z")
+        out = {k: np.full(self.n_global, np.nan) for k in keys}
+        out["flag"] = np.zeros(self.n_global, dtype=np.uint8)
+        seen = 0
+        for ids, d in self.owned():
+            for k in keys + ("flag",):
+                out[k][ids] = d[k]
+            seen += len(ids)
+        out["_owned_total"] = seen
+        return out
+
+    def histograms(self):
+        counts, n, sums = None, 0, None
+        for r in self.ranks:
+            c, k, s = r.sim.histograms()
+            counts = c if counts is None else counts + c
+            n += k
+            sums = s if sums is None else sums + s
+        return counts, n, sums
+
+    def pair_list(self):
+        parts = [r.sim.pair_list() for r in self.ranks]
+        return tuple(np.concatenate([p[i] for p in parts]) for i in range(4))
+
+    def particles_per_rank(self):
+        return [int(amc.load_library().amc_num_particles(r.sim.h)) for r in self.ranks]
+
+    def close(self):
+        for r in self.ranks:
+            r.sim.close()

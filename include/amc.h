@@ -180,6 +180,42 @@ int amc_set_step_index(amc_handle *h, int64_t step);
  * launches: number of kernel launches in that call. */
 int amc_last_timing(amc_handle *h, double ms[5], int64_t *launches);
 
+/* ------------------------------------------------------------------------------------------------
+ * Slab decomposition along z over several GPUs (one handle = one rank = the reference cells of the
+ * global z layers [cuts[rank], cuts[rank+1]); no counterpart in the reference, results are identical
+ * to the single-domain run).  The handle is created with the z tables of its own layers; the exchange
+ * buffers are device memory owned by the caller (e.g. torch tensors), who also moves them between
+ * ranks (NCCL all-to-all / neighbour send-recv) between the calls below.  Record = 12 doubles
+ * (10 state values, particle id, flag bits); every buffer starts with one header record (count).
+ *   per step:  amc_slab_advect -> [all-to-all xfer_send -> xfer_recv] -> amc_slab_sort
+ *              -> amc_slab_pairs_begin -> [neighbour exchange] -> amc_slab_apply(-1)
+ *              -> for g in 0..7: amc_slab_group(g) -> [neighbour exchange] -> amc_slab_apply(g)
+ *              -> amc_slab_finish */
+typedef struct amc_slab_config {
+    int32_t rank, nranks;
+    const int32_t *cuts;     /* nranks+1 global z-layer cuts, cuts[0] = 0, cuts[nranks] = global cell count in z */
+    int32_t gncz;            /* global number of cells in z */
+    const double *gz_edge;   /* global z edges, gncz+1 */
+    const double *gz_lo;     /* global z low-side bounds, gncz */
+    int32_t xfer_capacity;   /* records per destination rank */
+    int32_t bnd_capacity;    /* records per neighbour and colour group */
+    void *xfer_send, *xfer_recv;                 /* nranks * (xfer_capacity+1) * 96 bytes each */
+    void *bnd_send_up, *bnd_send_down;           /* (bnd_capacity+1) * 96 bytes each */
+    void *bnd_recv_up, *bnd_recv_down;           /* received from the rank above / below */
+} amc_slab_config;
+
+int amc_slab_enable(amc_handle *h, const amc_slab_config *cfg);
+int amc_set_stream(amc_handle *h, void *cuda_stream);   /* run on the caller's stream (e.g. torch's current stream) */
+int amc_set_ids(amc_handle *h, const int64_t *ids);     /* global particle indices of the state set by amc_set_state */
+int amc_slab_advect(amc_handle *h);
+int amc_slab_sort(amc_handle *h, int64_t *n_resident);
+int amc_slab_pairs_begin(amc_handle *h);
+int amc_slab_group(amc_handle *h, int32_t group);
+int amc_slab_apply(amc_handle *h, int32_t group_done);
+int amc_slab_finish(amc_handle *h, amc_step_stats *stats);
+int amc_slab_get_owned(amc_handle *h, int64_t cap, int64_t *n, int64_t *ids, double *x, double *y, double *z, double *vx,
+                       double *vy, double *vz, double *dist, double *dist_x, double *dist_y, double *dist_z, uint8_t *flag);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,74 @@
+"""Slab decomposition: the N-rank run must be bit-identical to the single-domain run.
+All ranks live on one GPU here (LocalTransport: device copies instead of NCCL), which exercises every
+device-side piece of the protocol -- migration, ghost copies, per-group hand-over of particles moved
+by a collision at a cut -- deterministically; the NCCL transport itself is covered by
+tests/test_slab_transport.py (gloo, CPU) and by bench.py on several GPUs."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+KEYS = ("x", "y", "z", "vx", "vy", "vz", "dist", "dist_x", "dist_y", "dist_z")
+
+
+def run_single(cfg, init, steps, **kw):
+    from argon_monte_carlo_b200 import amc
+    sim = amc.Simulation(cfg, taps=amc.TAP_PAIRS, **kw)
+    sim.set_state(*init)
+    stats = sim.step(steps)
+    out = sim.get_state(), stats, sim.pair_list(), sim.histograms()
+    sim.close()
+    return out
+
+
+def run_slabs(cfg, init, steps, nranks, cuts=None, **kw):
+    from argon_monte_carlo_b200 import amc, slab
+    sim = slab.SlabSimulation(cfg, nranks, init[2], taps=amc.TAP_PAIRS, cuts=cuts, **kw)
+    sim.set_state(*init)
+    stats = sim.step(steps)
+    out = sim.get_state(), stats, sim.pair_list(), sim.histograms(), sim.cuts
+    sim.close()
+    return out
+
+
+def compare(single, slabs, n):
+    (st1, stats1, pairs1, hist1), (st2, stats2, pairs2, hist2, cuts) = single, slabs
+    assert st2["_owned_total"] == n, "particles lost or duplicated across ranks (cuts %s)" % cuts
+    for a, b in zip(stats1, stats2):
+        for k in ("wall_collisions", "pp_collisions", "pair_checks_ref", "oob_after_walls", "oob_after_pp", "errors",
+                  "completed_paths"):
+            assert a[k] == b[k], (k, a[k], b[k])
+        assert np.array_equal(a["wall_hits"], b["wall_hits"])
+        for k in ("dpz", "e_cold", "e_hot"):
+            assert abs(a[k] - b[k]) <= 1e-14 * abs(a[k])
+    for k in KEYS:
+        bad = np.nonzero(st1[k] != st2[k])[0]
+        assert len(bad) == 0, "%s differs for %d particles (first id %d), cuts %s" % (k, len(bad), bad[0], cuts)
+    assert np.array_equal(st1["flag"], st2["flag"])
+    key = lambda p: sorted(zip(p[0].tolist(), p[1].tolist(), p[2].tolist()))
+    assert key(pairs1) == key(pairs2)
+    assert np.array_equal(hist1[0], hist2[0]) and hist1[1] == hist2[1]
+
+
+@pytest.mark.parametrize("nranks,cuts", [(2, None), (3, None), (4, [0, 2, 5, 144, 148])])
+def test_pore_slabs_bit_identical(pore_cfg, pore_init, nranks, cuts):
+    single = run_single(pore_cfg, pore_init, 4)
+    slabs = run_slabs(pore_cfg, pore_init, 4, nranks, cuts)
+    compare(single, slabs, len(pore_init[0]))
+
+
+def test_temp_slabs_bit_identical_device_rng(temp_cfg, temp_init):
+    single = run_single(temp_cfg, temp_init, 4, seed=17)
+    slabs = run_slabs(temp_cfg, temp_init, 4, 3, seed=17)
+    compare(single, slabs, len(temp_init[0]))
+
+
+def test_dense_cut_many_boundary_collisions(oracle):
+    """A small, dense synthetic pore (overlapping start) cut through its end caps: thousands of
+    collisions per step, many of them at the cuts."""
+    from argon_monte_carlo_b200 import config, init_state
+    cfg = config.pore_config(False, scale=0.5)
+    init = init_state.synthetic_pore_state(cfg, seed=11)
+    single = run_single(cfg, init, 6)
+    for nranks, cuts in ((2, [0, 2, cfg.grid.nc[2]]), (3, [0, 3, 70, cfg.grid.nc[2]])):
+        compare(single, run_slabs(cfg, init, 6, nranks, cuts), len(init[0]))
