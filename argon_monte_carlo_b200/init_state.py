@@ -147,3 +147,43 @@ def synthetic_cube_state(cfg, n: int, seed: int = 127):
     z = rng.uniform(0, cfg.cube_z, n)
     v = rng.normal(0.0, cfg.a_shape, (3, n))
     return x, y, z, v[0].copy(), v[1].copy(), v[2].copy()
+
+
+def synthetic_pore_chunk(cfg, seed: int, chunk_index: int, chunk_size: int):
+    """Chunk `chunk_index` of a synthetic Maxwellian pore state that is defined chunk by chunk (each
+    chunk has its own Generator seeded by (seed, chunk_index) and draws every particle's region at
+    random with the region volumes as weights), so any process can generate any part of a very large
+    state without holding the rest.  Returns (first global id, x, y, z, vx, vy, vz)."""
+    n_total = cfg.num_molecules
+    start = chunk_index * chunk_size
+    m = max(0, min(chunk_size, n_total - start))
+    rng = np.random.default_rng([seed, chunk_index])
+    a = cfg.argon_radius
+    vols = np.array([cfg.open_air_volume, cfg.hot_volume, cfg.gap_volume, cfg.cold_volume, cfg.open_air_volume])
+    region = rng.choice(5, size=m, p=vols / vols.sum())
+    h = cfg.open_air_height
+    radii = np.array([cfg.open_air_radius - a, cfg.pore_coated_radius - a, cfg.gap_radius - a,
+                      cfg.pore_coated_radius - a, cfg.open_air_radius - a])
+    zlo = np.array([a, h, cfg.gap_bottom_height + a, cfg.gap_top_height, cfg.total_height - h + a])
+    zhi = np.array([h - a, cfg.gap_bottom_height, cfg.gap_top_height - a, cfg.total_height - h, cfg.total_height - a])
+    th = rng.uniform(0, 2 * np.pi, m)
+    rr = radii[region] * np.sqrt(rng.uniform(0, 1, m))
+    x, y = rr * np.cos(th), rr * np.sin(th)
+    z = zlo[region] + (zhi[region] - zlo[region]) * rng.uniform(0, 1, m)
+    v = rng.normal(0.0, cfg.a_shape, (3, m))
+    return start, x, y, z, v[0].copy(), v[1].copy(), v[2].copy()
+
+
+def synthetic_pore_chunked(cfg, seed: int = 17, chunk_size: int = 1 << 22, keep=None):
+    """Concatenate all chunks (optionally only the particles for which keep(z) is True).
+    Returns (global ids, x, y, z, vx, vy, vz)."""
+    nchunks = (cfg.num_molecules + chunk_size - 1) // chunk_size
+    parts = []
+    for c in range(nchunks):
+        start, *arrs = synthetic_pore_chunk(cfg, seed, c, chunk_size)
+        ids = start + np.arange(len(arrs[0]), dtype=np.int64)
+        if keep is not None:
+            m = keep(arrs[2])
+            ids, arrs = ids[m], [a[m] for a in arrs]
+        parts.append((ids, *arrs))
+    return tuple(np.concatenate([p[i] for p in parts]) for i in range(7))

@@ -188,16 +188,23 @@ class SlabSimulation:
     (all of them with LocalTransport, exactly one with DistTransport)."""
 
     def __init__(self, cfg, nranks, z_for_cuts, transport=None, local_ranks=None, devices=None, xfer_capacity=None,
-                 bnd_capacity=1024, slack=1.35, seed=None, kind=None, taps=0, cuts=None):
+                 bnd_capacity=1024, slack=1.35, seed=None, kind=None, taps=0, cuts=None, n_total=None):
         self.cfg, self.nranks = cfg, nranks
         self.transport = transport or LocalTransport()
         self.local_ranks = list(range(nranks)) if local_ranks is None else list(local_ranks)
         g = cfg.grid
         self.cuts = balanced_cuts(z_for_cuts, g.edge[2], nranks) if cuts is None else np.asarray(cuts, dtype=np.int32)
         layer = owner_layer(np.asarray(z_for_cuts), g.edge[2])
+        # z_for_cuts may be a sample of a larger state of n_total particles
+        sample_scale = 1.0 if n_total is None else max(1.0, float(n_total) / max(len(layer), 1))
         per_rank = np.array([np.count_nonzero((layer >= self.cuts[r]) & (layer < self.cuts[r + 1])) for r in range(nranks)])
-        if xfer_capacity is None:   # migration + ghosts per step are a few 1e-3 of a slab's particles
-            xfer_capacity = int(max(4096, 0.02 * per_rank.max()))
+        per_rank = (per_rank * sample_scale).astype(np.int64)
+        if xfer_capacity is None:
+            # per step and cut: ghosts = the particles of the layer below the cut that lie within one
+            # collision range of it, plus the migrants (about a fifth of that at dt = tau/1000)
+            hist = np.bincount(layer, minlength=g.nc[2])
+            band = float(cfg.collision_range) / float(g.edge[2][1] - g.edge[2][0])
+            xfer_capacity = int(max(4096, 4 * hist.max() * band * sample_scale + 2048))
         cheb = None
         if cfg.kind == "temp":
             from .config import gap_energy_chebyshev
@@ -208,6 +215,17 @@ class SlabSimulation:
                                seed=seed, kind=kind, taps=taps, cheb=cheb)
                       for i, r in enumerate(self.local_ranks)]
         self.n_global = 0
+        self.phase_ms = None        # set by step(timing=True): [advect, exchange+sort, pair groups+hand-over, finish]
+        self.debug_counts = False   # True: tally exchanged records per step (host sync; tests only)
+        self.exchanged = {"xfer": 0, "boundary": 0}
+
+    def _tally(self, kind):
+        if self.debug_counts:
+            for r in self.ranks:
+                if kind == "xfer":
+                    self.exchanged["xfer"] += int(r.xfer_send[:, 0, 0].sum().item())
+                else:
+                    self.exchanged["boundary"] += int(r.bnd_send_up[0, 0].item()) + int(r.bnd_send_down[0, 0].item())
 
     def set_state(self, x, y, z, vx, vy, vz, dist=None, dist_x=None, dist_y=None, dist_z=None, flag=None):
         """Global arrays in original particle index order; each local rank takes the particles whose z
@@ -223,28 +241,56 @@ class SlabSimulation:
                             np.asarray(vz)[m], opt(dist, m), opt(dist_x, m), opt(dist_y, m), opt(dist_z, m), opt(flag, m))
             r.call("amc_set_ids", ids.ctypes.data_as(amc.c_int64_p))
 
-    def step(self, n_steps=1, reduce=True):
+    def set_local_state(self, ids, x, y, z, vx, vy, vz, dist=None, dist_x=None, dist_y=None, dist_z=None, flag=None,
+                        n_global=None):
+        """Distributed use: this process's single rank receives exactly the particles it owns."""
+        (r,) = self.ranks
+        r.sim.set_state(x, y, z, vx, vy, vz, dist, dist_x, dist_y, dist_z, flag)
+        ids = np.ascontiguousarray(ids, dtype=np.int64)
+        r.call("amc_set_ids", ids.ctypes.data_as(amc.c_int64_p))
+        self.n_global = n_global if n_global is not None else self.n_global
+
+    def step(self, n_steps=1, reduce=True, timing=False):
         """n_steps timesteps; returns per-step counter dicts summed over this process's ranks (and over
-        all processes when the transport is distributed and reduce=True)."""
+        all processes when the transport is distributed and reduce=True).  timing=True additionally
+        brackets the phases with CUDA events on the current stream (self.phase_ms, summed over steps)."""
         out = []
         T, R = self.transport, self.ranks
+        marks = []
+        if timing:
+            import torch
+
+            def mark():
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                marks.append(e)
+        else:
+            def mark():
+                pass
         for _ in range(n_steps):
+            mark()
             for r in R:
                 r.call("amc_slab_advect")
+            mark()
+            self._tally("xfer")
             T.alltoall(R)
             for r in R:
                 r.call("amc_slab_sort", None)
+            mark()
             for r in R:
                 r.call("amc_slab_pairs_begin")
+            self._tally("boundary")
             T.neighbors(R)
             for r in R:
                 r.call("amc_slab_apply", C.c_int32(-1))
             for g in range(8):
                 for r in R:
                     r.call("amc_slab_group", C.c_int32(g))
+                self._tally("boundary")
                 T.neighbors(R)
                 for r in R:
                     r.call("amc_slab_apply", C.c_int32(g))
+            mark()
             tot = None
             for r in R:
                 st = amc.AmcStepStats()
@@ -262,7 +308,16 @@ class SlabSimulation:
                 for i, k in enumerate(SUM_KEYS):
                     tot[k] = type(tot[k])(vec[i]) if not isinstance(tot[k], float) else float(vec[i])
                 tot["wall_hits"] = vec[len(SUM_KEYS):].astype(np.int64)
+            mark()
             out.append(tot)
+        if timing:
+            import torch
+            torch.cuda.synchronize()
+            ms = np.zeros(4)
+            for k in range(n_steps):
+                for j in range(4):
+                    ms[j] += marks[5 * k + j].elapsed_time(marks[5 * k + j + 1])
+            self.phase_ms = ms
         return out
 
     def owned(self):

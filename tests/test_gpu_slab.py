@@ -24,9 +24,11 @@ def run_single(cfg, init, steps, **kw):
 def run_slabs(cfg, init, steps, nranks, cuts=None, **kw):
     from argon_monte_carlo_b200 import amc, slab
     sim = slab.SlabSimulation(cfg, nranks, init[2], taps=amc.TAP_PAIRS, cuts=cuts, **kw)
+    sim.debug_counts = True
     sim.set_state(*init)
     stats = sim.step(steps)
     out = sim.get_state(), stats, sim.pair_list(), sim.histograms(), sim.cuts
+    run_slabs.last_exchanged = dict(sim.exchanged)
     sim.close()
     return out
 
@@ -72,3 +74,6 @@ def test_dense_cut_many_boundary_collisions(oracle):
     single = run_single(cfg, init, 6)
     for nranks, cuts in ((2, [0, 2, cfg.grid.nc[2]]), (3, [0, 3, 70, cfg.grid.nc[2]])):
         compare(single, run_slabs(cfg, init, 6, nranks, cuts), len(init[0]))
+        ex = run_slabs.last_exchanged
+        print("exchanged records:", ex)
+        assert ex["xfer"] > 100 and ex["boundary"] > 0, ex   # the protocol was actually exercised

@@ -1,0 +1,102 @@
+"""Host-side logic of the multi-GPU path without GPUs: cut selection, partitioning, and the
+torch.distributed transport on 2 gloo ranks with CPU tensors."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+
+def test_balanced_cuts_and_owner_layers(pore_cfg, pore_init):
+    from argon_monte_carlo_b200 import slab
+    z, edges = pore_init[2], pore_cfg.grid.edge[2]
+    layer = slab.owner_layer(z, edges)
+    assert layer.min() >= 0 and layer.max() <= 147
+    k = np.arange(len(z))[::997]
+    assert all(edges[layer[i]] <= z[i] < edges[layer[i] + 1] for i in k)
+    for nranks in (1, 2, 4, 8):
+        cuts = slab.balanced_cuts(z, edges, nranks)
+        assert cuts[0] == 0 and cuts[-1] == 148 and len(cuts) == nranks + 1 and (np.diff(cuts) >= 2).all()
+        per = np.array([np.count_nonzero((layer >= cuts[r]) & (layer < cuts[r + 1])) for r in range(nranks)])
+        assert per.sum() == len(z)
+        # 62 % of the particles sit in 6 % of the length: equal-length slabs would be hopeless, these are not
+        assert per.max() <= 1.35 * len(z) / nranks + 40000
+    with pytest.raises(ValueError):
+        slab.balanced_cuts(z, edges, 100)
+
+
+def test_local_grid_is_a_window_of_the_global_tables(pore_cfg):
+    from argon_monte_carlo_b200 import slab
+    g = pore_cfg.grid
+    lg = slab.local_grid(g, 5, 9)
+    assert lg.nc == (14, 14, 4) and lg.c0 == (-7, -7, 5)
+    assert np.array_equal(lg.edge[2], g.edge[2][5:10]) and np.array_equal(lg.lo[2], g.lo[2][5:9])
+    assert lg.edge[0] is g.edge[0]
+
+
+def test_chunked_synthetic_state_is_chunk_deterministic():
+    from argon_monte_carlo_b200 import config, init_state
+    cfg = config.pore_config(True, scale=0.5)
+    a = init_state.synthetic_pore_chunked(cfg, seed=5, chunk_size=20000)
+    b = init_state.synthetic_pore_chunked(cfg, seed=5, chunk_size=20000, keep=lambda z: z > 1e-6)
+    assert len(a[0]) == cfg.num_molecules and np.array_equal(a[0], np.arange(cfg.num_molecules))
+    m = a[3] > 1e-6
+    assert np.array_equal(b[0], a[0][m]) and np.array_equal(b[4], a[4][m])
+    r = np.hypot(a[1], a[2])
+    assert r.max() <= cfg.open_air_radius and a[3].min() > 0 and a[3].max() < cfg.total_height
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, out):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from types import SimpleNamespace
+    from argon_monte_carlo_b200 import slab
+    cap, bcap = 5, 3
+    r = SimpleNamespace(rank=rank,
+                        xfer_send=torch.zeros(world, cap + 1, slab.REC, dtype=torch.float64),
+                        xfer_recv=torch.zeros(world, cap + 1, slab.REC, dtype=torch.float64),
+                        bnd_send_up=torch.full((bcap + 1, slab.REC), 100.0 + rank, dtype=torch.float64),
+                        bnd_send_down=torch.full((bcap + 1, slab.REC), 200.0 + rank, dtype=torch.float64),
+                        bnd_recv_up=torch.zeros(bcap + 1, slab.REC, dtype=torch.float64),
+                        bnd_recv_down=torch.zeros(bcap + 1, slab.REC, dtype=torch.float64))
+    for dst in range(world):
+        r.xfer_send[dst] = 10 * rank + dst          # block (src -> dst) tagged 10*src + dst
+    T = slab.DistTransport()
+    T.alltoall([r])
+    ok = all(bool((r.xfer_recv[src] == 10 * src + rank).all()) for src in range(world))
+    T.neighbors([r])
+    if rank + 1 < world:
+        ok &= bool((r.bnd_recv_up == 200.0 + rank + 1).all())     # what the rank above sent down
+    else:
+        ok &= bool((r.bnd_recv_up == 0).all())
+    if rank > 0:
+        ok &= bool((r.bnd_recv_down == 100.0 + rank - 1).all())   # what the rank below sent up
+    else:
+        ok &= bool((r.bnd_recv_down == 0).all())
+    tot = T.allreduce_sum(np.array([1.0 + rank, 2.0]))
+    ok &= bool(np.allclose(tot, [sum(1.0 + k for k in range(world)), 2.0 * world]))
+    out[rank] = ok
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_dist_transport_gloo(world):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    out = ctx.Manager().dict()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(k, world, port, out)) for k in range(world)]
+    [p.start() for p in procs]
+    [p.join(120) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    assert all(out.get(k) for k in range(world)), dict(out)
