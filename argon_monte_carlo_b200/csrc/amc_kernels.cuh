@@ -23,6 +23,19 @@ __device__ __forceinline__ void store_part(const Arrays &a, int64_t s, const Par
     a.d[s] = q.d; a.dx[s] = q.dx; a.dy[s] = q.dy; a.dz[s] = q.dz; a.flag[s] = (uint8_t)q.flag;
 }
 
+// rank of this lane among all particles incrementing `counter` (identified by `tag` within the warp):
+// the lanes with equal tag elect a leader that adds their number once
+__device__ __forceinline__ int warp_rank(int32_t *counter, int tag)
+{
+    unsigned active = __activemask();
+    unsigned peers = __match_any_sync(active, tag);
+    int leader = __ffs(peers) - 1, lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(counter, __popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    return base + __popc(peers & ((1u << lane) - 1));
+}
+
 // ------------------------------------------------------------------------------------------------
 // K1 + K4.  One thread per particle slot; `phase` selects the parts of the step to run so the same
 // code serves the fused step and the phase-level parity entry points.
@@ -111,9 +124,12 @@ __global__ void __launch_bounds__(ADVECT_THREADS) k_advect(const __grid_constant
         int32_t k = owner_key(p, q.x, q.y, q.z, o);
         p.key[s] = k;
         // band particles go to the front of their owner cell's segment so that neighbouring reference
-        // cells only have to read that prefix; rank >= 0: band, rank < 0: ~rank among the others
-        if (k != p.ncell_pad && any_band(p, q.x, q.y, q.z, o)) p.rank[s] = atomicAdd(&p.band_count[k], 1);
-        else p.rank[s] = ~atomicAdd(&p.rest_count[k], 1);
+        // cells only have to read that prefix; rank >= 0: band, rank < 0: ~rank among the others.
+        // The state is nearly sorted, so the lanes of a warp share one or two counters: one atomic per
+        // distinct counter and warp instead of one per particle.
+        bool band = k != p.ncell_pad && any_band(p, q.x, q.y, q.z, o);
+        int r = warp_rank(band ? &p.band_count[k] : &p.rest_count[k], (k << 1) | (int)band);
+        p.rank[s] = band ? r : ~r;
     }
 }
 
