@@ -79,6 +79,23 @@ static int alloc_arrays(amc_handle *h, Arrays &a, int64_t n)
     return AMC_OK;
 }
 
+// largest double t with sqrt(t) <= R: then sqrt(v) > R <=> v > t for every double v
+static double sq_threshold_gt(double R)
+{
+    double t = R * R;
+    while (std::sqrt(t) <= R) t = std::nextafter(t, INFINITY);
+    while (std::sqrt(t) > R) t = std::nextafter(t, 0.0);
+    return t;
+}
+// smallest double t with sqrt(t) >= R: then sqrt(v) < R <=> v < t
+static double sq_threshold_lt(double R)
+{
+    double t = R * R;
+    while (std::sqrt(t) >= R) t = std::nextafter(t, 0.0);
+    while (std::sqrt(t) < R) t = std::nextafter(t, INFINITY);
+    return t;
+}
+
 static inline unsigned grid_for(int64_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
 
 static void stats_to_host(const amc_handle *h, const StatsDev &s, amc_step_stats *o)
@@ -163,6 +180,10 @@ static int create_impl(amc_handle *h, const amc_config *cfg, int device)
     for (int a = 0; a < 3; a++) p.cube[a] = cfg->cube[a];
     p.g = cfg->geom;
     p.cr = cfg->geom.collision_range; p.mass = cfg->geom.argon_mass; p.overlap_sq = cfg->overlap_sq;
+    if (cfg->kind != AMC_KIND_CUBE) {
+        p.gt_Roa = sq_threshold_gt(cfg->geom.R_oa); p.gt_Rp = sq_threshold_gt(cfg->geom.R_p); p.gt_Rg = sq_threshold_gt(cfg->geom.R_g);
+        p.lt_Rp = sq_threshold_lt(cfg->geom.R_p); p.lt_Rg = sq_threshold_lt(cfg->geom.R_g);
+    }
     int64_t ncell = 1;
     for (int a = 0; a < 3; a++) {
         p.nc[a] = cfg->nc[a]; p.pnc[a] = cfg->nc[a] + 1;

@@ -59,6 +59,9 @@ struct P {
     const double *lo[3];
     double e0[3], inv_d[3];
     double overlap_sq, cr, mass;
+    /* exact squared-radius thresholds: sqrt(v) > R <=> v > gt_*,  sqrt(v) < R <=> v < lt_* (sqrt is monotone and
+       correctly rounded; the values are found on the host by stepping through neighbouring doubles) */
+    double gt_Roa, gt_Rp, gt_Rg, lt_Rp, lt_Rg;
     uint32_t key0, key1;
     int64_t step;
     const double *cheb;
@@ -235,22 +238,23 @@ __device__ __forceinline__ void pore_plane_wall(const P &p, Part &q, double zp)
     q.z = zp + t * q.vz;
 }
 
-// Pore wall cases 1..6 against the progressively mutated particle (Pore:442-485); returns hit bits
+// Pore wall cases 1..6 against the progressively mutated particle (Pore:442-485); returns hit bits.
+// `np.sqrt(x**2 + y**2) > R` is evaluated as `x*x + y*y > gt_R` (exactly equivalent, see P).
 __device__ __forceinline__ uint32_t pore_walls(const P &p, Part &q)
 {
     const amc_geom &g = p.g;
     uint32_t bits = 0;
-    if (sqrt(q.x * q.x + q.y * q.y) > g.R_oa) { bits |= 1u << 0; pore_side_wall(p, q, g.R_oa_c); }
+    if (q.x * q.x + q.y * q.y > p.gt_Roa) { bits |= 1u << 0; pore_side_wall(p, q, g.R_oa_c); }
     if (q.z < 0) { bits |= 1u << 1; pore_plane_wall(p, q, 0.0); }
     if (q.z > g.H) { bits |= 1u << 2; pore_plane_wall(p, q, g.H); }
-    if (q.pz > g.z_cold && q.z < g.z_cold && sqrt(q.x * q.x + q.y * q.y) > g.R_p) { bits |= 1u << 3; pore_plane_wall(p, q, g.z_cold); }
-    if (q.pz < g.oah && q.z > g.oah && sqrt(q.x * q.x + q.y * q.y) > g.R_p) { bits |= 1u << 4; pore_plane_wall(p, q, g.oah); }
-    double pr = sqrt(q.px * q.px + q.py * q.py);
+    if (q.pz > g.z_cold && q.z < g.z_cold && q.x * q.x + q.y * q.y > p.gt_Rp) { bits |= 1u << 3; pore_plane_wall(p, q, g.z_cold); }
+    if (q.pz < g.oah && q.z > g.oah && q.x * q.x + q.y * q.y > p.gt_Rp) { bits |= 1u << 4; pore_plane_wall(p, q, g.oah); }
+    double pr2 = q.px * q.px + q.py * q.py;
     bool pz_in_gap = q.pz < g.z_gt_pore && q.pz > g.z_gb;
-    if (pz_in_gap && pr < g.R_g && sqrt(q.x * q.x + q.y * q.y) > g.R_g) { bits |= 1u << 5; pore_side_wall(p, q, g.R_g_c); }
-    if (pr > g.R_p && q.z < g.z_gb && pz_in_gap) { bits |= 1u << 6; pore_plane_wall(p, q, g.z_gb); }
-    if (pr > g.R_p && q.z > g.z_gt_pore && pz_in_gap) { bits |= 1u << 7; pore_plane_wall(p, q, g.z_gt_pore); }
-    if (pr < g.R_p && sqrt(q.x * q.x + q.y * q.y) > g.R_p &&
+    if (pz_in_gap && pr2 < p.lt_Rg && q.x * q.x + q.y * q.y > p.gt_Rg) { bits |= 1u << 5; pore_side_wall(p, q, g.R_g_c); }
+    if (pr2 > p.gt_Rp && q.z < g.z_gb && pz_in_gap) { bits |= 1u << 6; pore_plane_wall(p, q, g.z_gb); }
+    if (pr2 > p.gt_Rp && q.z > g.z_gt_pore && pz_in_gap) { bits |= 1u << 7; pore_plane_wall(p, q, g.z_gt_pore); }
+    if (pr2 < p.lt_Rp && q.x * q.x + q.y * q.y > p.gt_Rp &&
         ((q.z < g.z_cold && q.z > g.z_gt_pore) || (q.z < g.z_gb && q.z > g.oah))) { bits |= 1u << 8; pore_side_wall(p, q, g.R_p_c); }
     return bits;
 }
@@ -268,11 +272,12 @@ __device__ __forceinline__ int pore_recapture(const amc_geom &g, Part &q)
 }
 
 // ---------------------------------------------------------------- Temp walls
-__device__ __forceinline__ bool temp_mask(const amc_geom &g, int c, const Part &q)
+__device__ __forceinline__ bool temp_mask(const P &p, int c, const Part &q)
 {
+    const amc_geom &g = p.g;
     double r2 = q.x * q.x + q.y * q.y, pr2 = q.px * q.px + q.py * q.py;
     switch (c) {
-    case AMC_CASE_1: return sqrt(r2) > g.R_oa;                                                       /* Temp:693 */
+    case AMC_CASE_1: return r2 > p.gt_Roa;   /* np.sqrt(x**2 + y**2) > open_air_radius */                /* Temp:693 */
     case AMC_CASE_2A: return q.z < 0;                                                                 /* Temp:699 */
     case AMC_CASE_2B: return q.z > g.H;                                                               /* Temp:702 */
     case AMC_CASE_3C: return q.pz >= g.zc3 && q.z < g.zc3 && r2 > g.R_p_sq;                           /* Temp:708 */
@@ -431,13 +436,30 @@ __device__ __forceinline__ double cheb_eval(const P &p, double z)
     return (p.cheb[0] + u * b1) - b2;
 }
 
+// true when at least one of the ten wall masks holds for the (unmutated) particle.  The cases only
+// change a particle they hit, so when this is false the sequential case loop is a no-op: 99.9 % of the
+// particles skip it.
+__device__ __forceinline__ bool temp_any_mask(const P &p, const Part &q)
+{
+    const amc_geom &g = p.g;
+    double r2 = q.x * q.x + q.y * q.y, pr2 = q.px * q.px + q.py * q.py, z = q.z, pz = q.pz;
+    bool pz_gap_open = pz < g.zgt_m && pz > g.zgb_p, pz_gap_closed = pz <= g.zgt_m && pz >= g.zgb_p;
+    bool crossed_p = pr2 <= g.R_p_c_sq && r2 > g.R_p_c_sq;
+    return r2 > p.gt_Roa || z < 0 || z > g.H ||
+           (pz >= g.zc3 && z < g.zc3 && r2 > g.R_p_sq) || (pz <= g.zh3 && z > g.zh3 && r2 > g.R_p_sq) ||
+           (pz_gap_open && pr2 <= g.R_g_c_sq && r2 > g.R_g_c_sq) ||
+           (pr2 >= g.R_p_c_sq && pz_gap_closed && (z < g.zgb_p || z > g.zgt_m)) ||
+           (crossed_p && ((z <= g.zgb_p && z >= g.zh3) || (z < g.zc3 && z > g.zgt_m)));
+}
+
 // all ten Temp cases on one particle with device RNG (Temp:693-753)
 __device__ __forceinline__ uint32_t temp_walls_device(const P &p, Part &q, int64_t id)
 {
     uint32_t bits = 0;
+    if (!temp_any_mask(p, q)) return 0;
 #pragma unroll 1
     for (int c = 0; c < AMC_NUM_CASES; c++) {
-        if (!temp_mask(p.g, c, q)) continue;
+        if (!temp_mask(p, c, q)) continue;
         bits |= 1u << c;
         if (c <= AMC_CASE_2B) { temp_specular(p, c, q); continue; }
         double t, col[3], nrm[3], dir[3], dpz, dE;

@@ -729,7 +729,7 @@ __global__ void __launch_bounds__(ADVECT_THREADS) k_case_specular(const __grid_c
     Part q;
     load_part(p.a, s, q);
     q.px = p.px[s]; q.py = p.py[s]; q.pz = p.pz[s];
-    if (!temp_mask(p.g, c, q)) return;
+    if (!temp_mask(p, c, q)) return;
     atomicAdd(&p.stats->wall_hits[c], 1ull);
     if (p.wall_bits) p.wall_bits[p.a.id[s]] |= (uint16_t)(1u << c);
     temp_specular(p, c, q);
@@ -745,7 +745,7 @@ __global__ void __launch_bounds__(ADVECT_THREADS) k_case_detect(const __grid_con
     Part q;
     load_part(p.a, s, q);
     q.px = p.px[s]; q.py = p.py[s]; q.pz = p.pz[s];
-    if (!temp_mask(p.g, c, q)) return;
+    if (!temp_mask(p, c, q)) return;
     int k = atomicAdd(count, 1);
     if (k >= cap) return;
     double t, col[3], nrm[3];
