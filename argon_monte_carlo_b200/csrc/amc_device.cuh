@@ -23,7 +23,7 @@
 
 #define AMC_MAX_MEMBERS 512  /* particles per reference cell incl. overlap band (reference: <= 308) */
 #define AMC_MAX_CAND 128     /* simultaneously overlapping pairs per cell visit */
-#define AMC_SUBGRID 8        /* sub-cells per axis of the in-CTA neighbour search */
+#define AMC_XBINS 64         /* slabs along x of the in-CTA neighbour search (multiple of 32) */
 #define AMC_SUB_MIN_N 48     /* below this many members the plain all-pairs scan is cheaper */
 
 enum { PH_DRIFT = 1, PH_WALLS = 2, PH_RECAP = 4, PH_KEYS = 8, PH_SAVE_PRIOR = 16, PH_LOAD_PRIOR = 32, PH_RECAP_POST = 64 };

@@ -292,15 +292,15 @@ struct CellShared {
     unsigned long long cursor;
     int moved_a, moved_b;
     int kx, ky, kz; /* 0-based cell indices of this visit (colour-group mode) */
-    /* sub-cell neighbour search */
-    double lo[3], inv_s[3];
-    int sub_ok;
+    /* neighbour search: members binned into slabs along x */
+    double lo[3], inv_s[3]; /* [0]: low bound and 1/slab width along x */
+    int sub_ok, nb;
     unsigned int nexec;          /* distance tests executed by this CTA since the last flush */
     unsigned long long nref;      /* reference-equivalent tests, thread 0 only */
     int rbeg[8], rcum[9];         /* the 8 candidate owner-cell ranges of this visit */
     uint16_t sub_of[AMC_MAX_MEMBERS], pos_of[AMC_MAX_MEMBERS], order[AMC_MAX_MEMBERS];
-    int sub_off[AMC_SUBGRID * AMC_SUBGRID * AMC_SUBGRID + 1];
-    int sub_cnt[AMC_SUBGRID * AMC_SUBGRID * AMC_SUBGRID];
+    int sub_off[AMC_XBINS + 2];
+    int sub_cnt[AMC_XBINS];
 };
 
 __device__ __forceinline__ unsigned long long pair_key(int32_t ia, int32_t ib)
@@ -441,24 +441,21 @@ __device__ void cell_process(const P &p, CellShared &S, int group, int cell)
         }
         if (tid == 0) atomicAdd(&S.nexec, (unsigned int)(n * (n - 1) / 2));
     } else {
-        // Bin the members into AMC_SUBGRID^3 sub-cells (edge >= 1.05 collision ranges, checked per
-        // cell), z fastest.  Two spheres closer than the collision range differ by at most one
-        // sub-cell per axis, so testing each member against the members of its own (x,y) row of
-        // sub-cells that come later in sub-cell order, and of the four "forward" neighbour rows,
-        // each restricted to iz-1..iz+1, visits every candidate pair exactly once.
-        // (S.sub_cnt was zeroed while the members were gathered.)
-        constexpr int G = AMC_SUBGRID, G3 = G * G * G;
+        // Sweep along x: bin the members into S.nb slabs of width >= 1.05 collision ranges and order them
+        // by slab.  Two spheres closer than the collision range are in the same or in adjacent slabs, so
+        // testing every member against the members that follow it in slab order up to the end of the
+        // next slab visits each candidate pair exactly once -- one contiguous range per member.
+        // (S.sub_cnt is zero on entry: zeroed at kernel start and again by the scan below.)
+        const int nb = S.nb;
+        const double lo = S.lo[0], inv_w = S.inv_s[0];
         for (int k = tid; k < n; k += nthreads) {
-            int ix = min(G - 1, max(0, (int)((S.x[k] - S.lo[0]) * S.inv_s[0])));
-            int iy = min(G - 1, max(0, (int)((S.y[k] - S.lo[1]) * S.inv_s[1])));
-            int iz = min(G - 1, max(0, (int)((S.z[k] - S.lo[2]) * S.inv_s[2])));
-            int c = (ix * G + iy) * G + iz;
+            int c = min(nb - 1, max(0, (int)((S.x[k] - lo) * inv_w)));
             S.sub_of[k] = (uint16_t)c;
             S.pos_of[k] = (uint16_t)atomicAdd(&S.sub_cnt[c], 1);
         }
         __syncthreads();
-        if (warp == 0) { // exclusive scan of the G3 counters by one warp: G3/32 consecutive counters per lane
-            constexpr int PER = G3 / 32;
+        if (warp == 0) { // exclusive scan of the slab counters by one warp
+            constexpr int PER = AMC_XBINS / 32;
             int v[PER], sum = 0;
 #pragma unroll
             for (int k = 0; k < PER; k++) { v[k] = S.sub_cnt[lane * PER + k]; sum += v[k]; }
@@ -468,7 +465,7 @@ __device__ void cell_process(const P &p, CellShared &S, int group, int cell)
             int ex = inc - sum;
 #pragma unroll
             for (int k = 0; k < PER; k++) { S.sub_off[lane * PER + k] = ex; ex += v[k]; S.sub_cnt[lane * PER + k] = 0; }
-            if (lane == 31) S.sub_off[G3] = ex;
+            if (lane == 31) { S.sub_off[AMC_XBINS] = ex; S.sub_off[AMC_XBINS + 1] = ex; }
         }
         __syncthreads();
         for (int k = tid; k < n; k += nthreads) {
@@ -478,21 +475,13 @@ __device__ void cell_process(const P &p, CellShared &S, int group, int cell)
         }
         __syncthreads();
         unsigned int mine = 0;
-        for (int item = tid; item < 5 * n; item += nthreads) { // (member, row) work items: balanced over the CTA
-            int a = item / 5, r = item - 5 * a;
-            int c = S.sub_of[a];
-            int ix = c / (G * G), iy = (c / G) % G, iz = c % G;
-            // rows: 0 = own row (later partners only), 1 = (ix, iy+1), 2..4 = (ix+1, iy-1..iy+1)
-            int jx = ix + (r >= 2), jy = r == 0 ? iy : (r == 1 ? iy + 1 : iy + r - 3);
-            if (jx >= G || jy < 0 || jy >= G) continue;
-            int row = (jx * G + jy) * G;
-            int beg = S.sub_off[row + max(iz - 1, 0)], end = S.sub_off[row + min(iz + 1, G - 1) + 1];
-            if (r == 0) beg = S.pos_of[a] + 1;
-            if (beg >= end) continue;
+        for (int q0 = tid; q0 < n; q0 += nthreads) { // walk in slab order so neighbouring lanes have similar ranges
+            int a = S.order[q0];
+            int end = S.sub_off[S.sub_of[a] + 2];
             double xa = S.x[a], ya = S.y[a], za = S.z[a];
-            for (int q = beg; q < end; q++) {
+            mine += end - (q0 + 1);
+            for (int q = q0 + 1; q < end; q++) {
                 int b2 = S.order[q];
-                mine++;
                 if (overlap(p, xa, ya, za, S.x[b2], S.y[b2], S.z[b2])) push_cand(S, p, a, b2);
             }
         }
@@ -579,7 +568,7 @@ __global__ void __launch_bounds__(PAIR_THREADS, 8) k_pairs_group(const __grid_co
     const int nwork = p.wl_count[group];
     const int32_t *wl = p.wl + (size_t)group * p.wl_stride;
     if (tid == 0) { S.nexec = 0; S.nref = 0; }
-    for (int c = tid; c < AMC_SUBGRID * AMC_SUBGRID * AMC_SUBGRID; c += PAIR_THREADS) S.sub_cnt[c] = 0; /* kept zero by the scan */
+    for (int c = tid; c < AMC_XBINS; c += PAIR_THREADS) S.sub_cnt[c] = 0; /* kept zero by the scan */
     for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
         const int cell = wl[w];
         __syncthreads(); /* previous cell fully processed before S is reused */
@@ -596,18 +585,17 @@ __global__ void __launch_bounds__(PAIR_THREADS, 8) k_pairs_group(const __grid_co
 #pragma unroll
             for (int o = 1; o < 8; o <<= 1) { int t = __shfl_up_sync(0xffu, inc, o); if (tid >= o) inc += t; }
             S.rcum[tid + 1] = inc;
-            bool wide = true; /* sub-cells of this axis are wider than 1.05 collision ranges */
             if (tid < 3) {
                 int k = tid == 0 ? kx : (tid == 1 ? ky : kz);
                 double lo = p.lo[tid][k], hi = p.edge[tid][k + 1];
                 s_lo[tid] = lo; s_hi[tid] = hi;
-                S.lo[tid] = lo;
-                S.inv_s[tid] = (double)AMC_SUBGRID / (hi - lo);
-                wide = (hi - lo) / AMC_SUBGRID >= 1.05 * p.cr;
+                if (tid == 0) { /* slabs along x, at least 1.05 collision ranges wide */
+                    int nb = (int)fmin((double)AMC_XBINS, floor((hi - lo) / (1.05 * p.cr)));
+                    S.nb = nb; S.sub_ok = nb >= 2;
+                    S.lo[0] = lo; S.inv_s[0] = (double)nb / (hi - lo);
+                }
             }
-            unsigned widem = __ballot_sync(0xffu, wide);
             if (tid == 0) {
-                S.sub_ok = widem == 0xffu;
                 S.rcum[0] = 0; S.n = 0; S.ncand = 0; S.kx = kx; S.ky = ky; S.kz = kz;
                 int ne = *p.esc_count;
                 s_ne = ne > p.esc_cap ? p.esc_cap : ne;
