@@ -159,13 +159,16 @@ class DistTransport:
 
     def neighbors(self, ranks):
         (r,) = ranks
-        ops = []
-        if self.rank + 1 < self.world:
-            ops.append(self.dist.P2POp(self.dist.isend, r.bnd_send_up, self.rank + 1, self.group))
-            ops.append(self.dist.P2POp(self.dist.irecv, r.bnd_recv_up, self.rank + 1, self.group))
-        if self.rank > 0:
-            ops.append(self.dist.P2POp(self.dist.isend, r.bnd_send_down, self.rank - 1, self.group))
-            ops.append(self.dist.P2POp(self.dist.irecv, r.bnd_recv_down, self.rank - 1, self.group))
+        ops = getattr(r, "_nbr_ops", None)
+        if ops is None:     # the buffers are fixed: build the P2P descriptors once
+            ops = []
+            if self.rank + 1 < self.world:
+                ops.append(self.dist.P2POp(self.dist.isend, r.bnd_send_up, self.rank + 1, self.group))
+                ops.append(self.dist.P2POp(self.dist.irecv, r.bnd_recv_up, self.rank + 1, self.group))
+            if self.rank > 0:
+                ops.append(self.dist.P2POp(self.dist.isend, r.bnd_send_down, self.rank - 1, self.group))
+                ops.append(self.dist.P2POp(self.dist.irecv, r.bnd_recv_down, self.rank - 1, self.group))
+            r._nbr_ops = ops
         for req in (self.dist.batch_isend_irecv(ops) if ops else []):
             req.wait()
 
@@ -320,22 +323,28 @@ class SlabSimulation:
             self.phase_ms = ms
         return out
 
-    def owned(self):
-        """Per local rank: (ids, dict of state arrays) of the particles it currently owns."""
+    def owned(self, out=None):
+        """Per local rank: (ids, dict of state arrays) of the particles it currently owns.
+        out: optional list (one per local rank) of dicts with preallocated -- e.g. pinned -- arrays
+        'ids' (int64), the ten float64 state arrays and 'flag' (uint8)."""
         res = []
         keys = ("x", "y", "z", "vx", "vy", "vz", "dist", "dist_x", "dist_y", "dist_z")
-        for r in self.ranks:
-            cap = max(int(amc.load_library().amc_num_particles(r.sim.h)), 1)
-            ids = np.zeros(cap, dtype=np.int64)
-            arrs = {k: np.zeros(cap) for k in keys}
-            flag = np.zeros(cap, dtype=np.uint8)
+        for i, r in enumerate(self.ranks):
+            if out is not None:
+                buf = out[i]
+                cap = len(buf["ids"])
+            else:
+                cap = max(int(amc.load_library().amc_num_particles(r.sim.h)), 1)
+                buf = {k: np.empty(cap) for k in keys}
+                buf["ids"] = np.empty(cap, dtype=np.int64)
+                buf["flag"] = np.empty(cap, dtype=np.uint8)
             n = C.c_int64(0)
-            r.call("amc_slab_get_owned", C.c_int64(cap), C.byref(n), ids.ctypes.data_as(amc.c_int64_p),
-                   *[amc._dp(arrs[k]) for k in keys], flag.ctypes.data_as(amc.c_uint8_p))
+            r.call("amc_slab_get_owned", C.c_int64(cap), C.byref(n), buf["ids"].ctypes.data_as(amc.c_int64_p),
+                   *[amc._dp(buf[k]) for k in keys], buf["flag"].ctypes.data_as(amc.c_uint8_p))
             k = int(n.value)
-            d = {key: a[:k] for key, a in arrs.items()}
-            d["flag"] = flag[:k]
-            res.append((ids[:k], d))
+            d = {key: buf[key][:k] for key in keys}
+            d["flag"] = buf["flag"][:k]
+            res.append((buf["ids"][:k], d))
         return res
 
     def get_state(self):

@@ -212,7 +212,7 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu:
         out["cpu_baseline"] = cpu_baseline(steps=8, warmup=2)
     if rank == 0:
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
 
@@ -261,10 +261,14 @@ def run_slabs(args, world, rank, local, dev, hbm_peak, peak_src, barrier, max_ov
     # e2e: host buffers in and out every step
     keys = ("x", "y", "z", "vx", "vy", "vz", "dist", "dist_x", "dist_y", "dist_z")
     e2e_steps = max(1, min(args.steps, 3))
+    cap = int(n * 1.1) + 65536
+    pinned = {k: torch.empty(cap, dtype=torch.float64).pin_memory().numpy() for k in keys}
+    pinned["ids"] = torch.empty(cap, dtype=torch.int64).pin_memory().numpy()
+    pinned["flag"] = torch.empty(cap, dtype=torch.uint8).pin_memory().numpy()
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        (oid, od), = sim.owned()
+        (oid, od), = sim.owned(out=[pinned])
         sim.set_local_state(oid, *[od[k] for k in keys], flag=od["flag"])
         sim.step(1, reduce=False)
     torch.cuda.synchronize()
@@ -291,7 +295,7 @@ def run_slabs(args, world, rank, local, dev, hbm_peak, peak_src, barrier, max_ov
         "collisions_per_step": collisions, "wall_s": wall, "resident_particles": int(n_now),
     }
     if rank == 0:
-        print(json.dumps(out))
+        emit(out)
     dist.destroy_process_group()
 
 
@@ -360,10 +364,29 @@ def run_reference(args):
                                   "557,649 particles; throughput per particle is size-independent at fixed density)"},
            "cpu_baseline": cb,
            "e2e": {"value": cb["value"], "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out))
+    emit(out)
+
+
+_REAL_STDOUT = None
+
+
+def protect_stdout():
+    """Libraries (NCCL prints its version banner) write to fd 1; the contract is ONE JSON line on stdout.
+    Point fd 1 at stderr for the whole run and keep the real stdout for the result line."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(obj):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(obj) + "\n")
+    out.flush()
 
 
 def main():
+    protect_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
