@@ -756,6 +756,7 @@ extern "C" int amc_slab_enable(amc_handle *h, const amc_slab_config *c)
     p.g_inv_dz = (double)c->gncz / (c->gz_edge[c->gncz] - c->gz_edge[0]);
     p.up_thr = c->rank + 1 < c->nranks ? c->gz_lo[c->cuts[c->rank + 1]] : INFINITY;
     p.down_thr = c->rank > 0 ? c->gz_edge[c->cuts[c->rank]] : -INFINITY;
+    p.down_band = c->rank > 0 ? c->gz_lo[c->cuts[c->rank]] : INFINITY;
     p.xf_cap = c->xfer_capacity; p.bnd_cap = c->bnd_capacity;
     p.xf_send = (double *)c->xfer_send; p.xf_recv = (const double *)c->xfer_recv;
     p.bnd_send[0] = (double *)c->bnd_send_up; p.bnd_send[1] = (double *)c->bnd_send_down;
@@ -768,13 +769,22 @@ extern "C" int amc_slab_enable(amc_handle *h, const amc_slab_config *c)
     p.rel_count = h->d_counters + c->nranks + 3; p.n_foreign = h->d_counters + c->nranks + 4;
     ALLOC(p.bnd_dirty[0], p.bnd_cap); ALLOC(p.bnd_dirty[1], p.bnd_cap);
     ALLOC(p.rel_id, p.rel_cap); ALLOC(p.rel_slot, p.rel_cap); ALLOC(p.skey, h->cap);
-    ALLOC(h->d_slab_overflow, 1);
-    CK(cudaMemset(h->d_slab_overflow, 0, sizeof(unsigned long long)));
+    ALLOC(h->d_slab_overflow, 4);
+    CK(cudaMemset(h->d_slab_overflow, 0, 4 * sizeof(unsigned long long)));
     p.slab_overflow = h->d_slab_overflow;
     p.group_done = -1;
     h->slab = true;
     CK(cudaDeviceSynchronize());
     return AMC_OK;
+}
+
+static int slab_overflow_error(amc_handle *h, const unsigned long long ovf[4])
+{
+    if (!(ovf[0] | ovf[1] | ovf[2] | ovf[3])) return AMC_OK;
+    char msg[256];
+    snprintf(msg, sizeof(msg), "slab exchange overflow: %llu transfer records beyond xfer_capacity=%d, %llu relation-table entries, "
+             "%llu boundary records beyond bnd_capacity=%d, %llu foreign copies", ovf[0], h->p.xf_cap, ovf[1], ovf[2], h->p.bnd_cap, ovf[3]);
+    return h->fail(AMC_E_CAPACITY, msg);
 }
 
 static int slab_check(amc_handle *h)
@@ -823,10 +833,10 @@ extern "C" int amc_slab_sort(amc_handle *h, int64_t *n_resident)
     int32_t counts[2] = {0, 0}; // resident = start of the GONE bucket; n_in for the capacity check
     CK(cudaMemcpyAsync(&counts[0], p.cell_start + (p.ncell_pad + 1), sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(&counts[1], p.n_in, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
-    unsigned long long ovf = 0;
-    CK(cudaMemcpyAsync(&ovf, h->d_slab_overflow, sizeof(ovf), cudaMemcpyDeviceToHost, h->stream));
+    unsigned long long ovf[4] = {0, 0, 0, 0};
+    CK(cudaMemcpyAsync(ovf, h->d_slab_overflow, sizeof(ovf), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    if (ovf) return h->fail(AMC_E_CAPACITY, "slab exchange buffer overflow (raise xfer_capacity / bnd_capacity)");
+    if ((rc = slab_overflow_error(h, ovf)) != AMC_OK) return rc;
     if (h->n + counts[1] > h->cap) return h->fail(AMC_E_CAPACITY, "max_particles too small for the immigrants of this step");
     h->n = counts[0];
     p.n = h->n;
@@ -887,11 +897,11 @@ extern "C" int amc_slab_finish(amc_handle *h, amc_step_stats *stats)
     int32_t nf = 0;
     CK(cudaMemcpyAsync(&nf, p.n_foreign, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
     if (h->n && p.kind != AMC_KIND_CUBE) k_recapture_post<<<grid_for(h->n, ADVECT_THREADS), ADVECT_THREADS, 0, h->stream>>>(p);
-    unsigned long long ovf = 0;
-    CK(cudaMemcpyAsync(&ovf, h->d_slab_overflow, sizeof(ovf), cudaMemcpyDeviceToHost, h->stream));
+    unsigned long long ovf[4] = {0, 0, 0, 0};
+    CK(cudaMemcpyAsync(ovf, h->d_slab_overflow, sizeof(ovf), cudaMemcpyDeviceToHost, h->stream));
     rc = phase_end(h, stats);
     if (rc != AMC_OK) return rc;
-    if (ovf) return h->fail(AMC_E_CAPACITY, "slab exchange buffer overflow (raise xfer_capacity / bnd_capacity)");
+    if ((rc = slab_overflow_error(h, ovf)) != AMC_OK) return rc;
     h->n += nf; // foreign copies appended behind the sorted particles; dropped by the next amc_slab_advect
     p.n = h->n;
     return AMC_OK;

@@ -93,6 +93,7 @@ struct P {
     int32_t gncz;
     double g_e0z, g_inv_dz;
     double up_thr, down_thr;  /* lo_global[Z_{r+1}] (+inf on the last rank), edge_global[Z_r] (-inf on rank 0) */
+    double down_band;         /* lo_global[Z_r]: above it a particle of the rank below is a band member of this rank's cells */
     double *xf_send;          /* [nranks][xf_cap+1] records, record 0 = header (count) */
     const double *xf_recv;
     int32_t *xf_count;        /* [nranks] */

@@ -100,6 +100,9 @@ __global__ void __launch_bounds__(ADVECT_THREADS) k_advect(const __grid_constant
         int dest = 0;
         while (dest + 1 < p.nranks && layer >= p.cuts[dest + 1]) dest++;
         bool ghost_up = dest == p.srank && p.srank + 1 < p.nranks && q.z > p.up_thr;
+        // a particle that just crossed the lower cut lands inside the band this rank's bottom cells
+        // read: hand ownership down but keep the local copy as the ghost (no round trip needed)
+        bool stay_as_ghost = dest == p.srank - 1 && q.z > p.down_band;
         if (ghost_up) q.flag |= AMC_FLAG_REL_UP;
         if (dest != p.srank || ghost_up) {
             int to = dest != p.srank ? dest : p.srank + 1;
@@ -108,15 +111,19 @@ __global__ void __launch_bounds__(ADVECT_THREADS) k_advect(const __grid_constant
                 double *r = p.xf_send + ((size_t)to * (p.xf_cap + 1) + 1 + j) * AMC_REC;
                 r[0] = q.x; r[1] = q.y; r[2] = q.z; r[3] = q.vx; r[4] = q.vy; r[5] = q.vz;
                 r[6] = q.d; r[7] = q.dx; r[8] = q.dy; r[9] = q.dz; r[10] = (double)id;
-                r[11] = (double)((q.flag & AMC_FLAG_PATH) | (dest != p.srank ? 0u : (AMC_FLAG_GHOST | AMC_FLAG_REL_DOWN)));
-            } else atomicAdd(p.slab_overflow, 1ull);
+                unsigned rf = q.flag & AMC_FLAG_PATH;
+                if (dest == p.srank) rf |= AMC_FLAG_GHOST | AMC_FLAG_REL_DOWN; /* ghost copy for the rank above */
+                else if (stay_as_ghost) rf |= AMC_FLAG_REL_UP;                 /* new owner: the rank above keeps a copy */
+                r[11] = (double)rf;
+            } else atomicAdd(p.slab_overflow + 0, 1ull);
         }
-        if (dest != p.srank) { // emigrant: leaves this rank's arrays at the coming sort
+        if (dest != p.srank && !stay_as_ghost) { // emigrant: leaves this rank's arrays at the coming sort
             store_part(p.a, s, q);
             p.key[s] = p.ncell_pad + 1;
             p.rank[s] = ~atomicAdd(&p.rest_count[p.ncell_pad + 1], 1);
             return;
         }
+        if (stay_as_ghost) q.flag = (q.flag & AMC_FLAG_PATH) | AMC_FLAG_GHOST | AMC_FLAG_REL_DOWN;
     }
     if (phase & (PH_DRIFT | PH_WALLS | PH_RECAP | PH_RECAP_POST)) store_part(p.a, s, q);
     if (phase & PH_KEYS) {
@@ -216,11 +223,11 @@ __global__ void __launch_bounds__(ADVECT_THREADS) k_scatter(const __grid_constan
         p.skey[t] = k;
         if (k <= p.ncell_pad && (fl & (AMC_FLAG_GHOST | AMC_FLAG_REL_UP | AMC_FLAG_REL_DOWN))) {
             int j = atomicAdd(p.rel_count, 1);
-            if (j < p.rel_cap) { p.rel_id[j] = id; p.rel_slot[j] = (int32_t)t; } else atomicAdd(p.slab_overflow, 1ull);
+            if (j < p.rel_cap) { p.rel_id[j] = id; p.rel_slot[j] = (int32_t)t; } else atomicAdd(p.slab_overflow + 1, 1ull);
         }
         if (k <= p.ncell_pad && (fl & AMC_FLAG_LATE_UP)) {
             int j = atomicAdd(&p.bnd_n[0], 1);
-            if (j < p.bnd_cap) p.bnd_dirty[0][j] = (int32_t)t; else atomicAdd(p.slab_overflow, 1ull);
+            if (j < p.bnd_cap) p.bnd_dirty[0][j] = (int32_t)t; else atomicAdd(p.slab_overflow + 2, 1ull);
         }
     }
 }
@@ -374,7 +381,7 @@ __device__ __noinline__ void resolve_pair(const P &p, CellShared &S, int m1, int
             if ((up && !(f & AMC_FLAG_REL_UP)) || (down && !(f & AMC_FLAG_REL_DOWN))) {
                 if (!(f & (AMC_FLAG_REL_UP | AMC_FLAG_REL_DOWN | AMC_FLAG_GHOST))) {
                     int j = atomicAdd(p.rel_count, 1);
-                    if (j < p.rel_cap) { p.rel_id[j] = S.id[w ? m2 : m1]; p.rel_slot[j] = s; } else atomicAdd(p.slab_overflow, 1ull);
+                    if (j < p.rel_cap) { p.rel_id[j] = S.id[w ? m2 : m1]; p.rel_slot[j] = s; } else atomicAdd(p.slab_overflow + 1, 1ull);
                 }
                 f |= (up ? AMC_FLAG_REL_UP : 0u) | (down ? AMC_FLAG_REL_DOWN : 0u);
             }
@@ -383,7 +390,7 @@ __device__ __noinline__ void resolve_pair(const P &p, CellShared &S, int m1, int
                 if ((dir == 0 ? up : down) && !(f & bit)) { /* once per group and direction */
                     f |= bit;
                     int j = atomicAdd(&p.bnd_n[dir], 1);
-                    if (j < p.bnd_cap) p.bnd_dirty[dir][j] = s; else atomicAdd(p.slab_overflow, 1ull);
+                    if (j < p.bnd_cap) p.bnd_dirty[dir][j] = s; else atomicAdd(p.slab_overflow + 2, 1ull);
                 }
             }
         }
@@ -802,7 +809,7 @@ __global__ void __launch_bounds__(ADVECT_THREADS) k_xfer_unpack(const __grid_con
     q.flag = (uint32_t)r[11];
     int o[3];
     int32_t k = owner_key(p, q.x, q.y, q.z, o);
-    if (!(q.flag & AMC_FLAG_GHOST) && p.srank + 1 < p.nranks && q.z > p.up_thr && k != p.ncell_pad)
+    if (!(q.flag & (AMC_FLAG_GHOST | AMC_FLAG_REL_UP)) && p.srank + 1 < p.nranks && q.z > p.up_thr && k != p.ncell_pad)
         q.flag |= AMC_FLAG_REL_UP | AMC_FLAG_LATE_UP; /* immigrant inside the band below the upper cut */
     store_part(p.a, s, q);
     p.a.id[s] = (int32_t)r[10];
@@ -858,7 +865,7 @@ __global__ void __launch_bounds__(128) k_bnd_apply(const __grid_constant__ P p, 
     const Arrays &A = p.a;
     if (tid == 0 && s_slot < 0) { // unknown here: a particle the neighbour moved into this rank's reach
         int f = atomicAdd(p.n_foreign, 1);
-        if (f >= p.foreign_cap) { atomicAdd(p.slab_overflow, 1ull); s_slot = -2; }
+        if (f >= p.foreign_cap) { atomicAdd(p.slab_overflow + 3, 1ull); s_slot = -2; }
         else {
             int s = (int)p.n + f;
             s_slot = s;
@@ -866,7 +873,7 @@ __global__ void __launch_bounds__(128) k_bnd_apply(const __grid_constant__ P p, 
             A.flag[s] = (uint8_t)(AMC_FLAG_GHOST | (dir == 0 ? AMC_FLAG_REL_UP : AMC_FLAG_REL_DOWN));
             p.skey[s] = -1;
             int k = atomicAdd(p.rel_count, 1);
-            if (k < p.rel_cap) { p.rel_id[k] = id; p.rel_slot[k] = s; } else atomicAdd(p.slab_overflow, 1ull);
+            if (k < p.rel_cap) { p.rel_id[k] = id; p.rel_slot[k] = s; } else atomicAdd(p.slab_overflow + 1, 1ull);
         }
     }
     __syncthreads();

@@ -191,7 +191,7 @@ class SlabSimulation:
     (all of them with LocalTransport, exactly one with DistTransport)."""
 
     def __init__(self, cfg, nranks, z_for_cuts, transport=None, local_ranks=None, devices=None, xfer_capacity=None,
-                 bnd_capacity=1024, slack=1.35, seed=None, kind=None, taps=0, cuts=None, n_total=None):
+                 bnd_capacity=2048, slack=1.35, seed=None, kind=None, taps=0, cuts=None, n_total=None):
         self.cfg, self.nranks = cfg, nranks
         self.transport = transport or LocalTransport()
         self.local_ranks = list(range(nranks)) if local_ranks is None else list(local_ranks)
