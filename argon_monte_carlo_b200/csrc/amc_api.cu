@@ -883,8 +883,8 @@ extern "C" int amc_slab_apply(amc_handle *h, int32_t group_done)
     if (rc != AMC_OK) return rc;
     P &p = h->p;
     p.group_done = group_done;
-    if (p.srank + 1 < p.nranks) k_bnd_apply<<<p.bnd_cap, 128, 0, h->stream>>>(p, 0);
-    if (p.srank > 0) k_bnd_apply<<<p.bnd_cap, 128, 0, h->stream>>>(p, 1);
+    if (p.srank + 1 < p.nranks) k_bnd_apply<<<64, 128, 0, h->stream>>>(p, 0);
+    if (p.srank > 0) k_bnd_apply<<<64, 128, 0, h->stream>>>(p, 1);
     CK(cudaGetLastError());
     return AMC_OK;
 }

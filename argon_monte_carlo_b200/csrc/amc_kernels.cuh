@@ -851,8 +851,8 @@ __global__ void __launch_bounds__(128) k_bnd_apply(const __grid_constant__ P p, 
     __shared__ int s_slot, s_esc;
     const double *buf = p.bnd_recv[dir];
     int cnt = (int)buf[0];
-    int j = blockIdx.x;
-    if (j >= cnt) return;
+    for (int j = blockIdx.x; j < cnt; j += gridDim.x) {
+    __syncthreads();
     const double *r = buf + (size_t)(1 + j) * AMC_REC;
     const int32_t id = (int32_t)r[10];
     const int tid = threadIdx.x;
@@ -878,7 +878,7 @@ __global__ void __launch_bounds__(128) k_bnd_apply(const __grid_constant__ P p, 
     }
     __syncthreads();
     const int s = s_slot;
-    if (s < 0) return;
+    if (s < 0) continue;
     const unsigned fl = A.flag[s];
     if (fl & AMC_FLAG_ESC) { // already on the escaped list: find its entry
         int ne = min(*p.esc_count, p.esc_cap);
@@ -886,7 +886,7 @@ __global__ void __launch_bounds__(128) k_bnd_apply(const __grid_constant__ P p, 
             if (p.esc_slot[e] == s) s_esc = e;
     }
     __syncthreads();
-    if (tid != 0) return;
+    if (tid != 0) continue;
     double x = r[0], y = r[1], z = r[2];
     A.x[s] = x; A.y[s] = y; A.z[s] = z; A.vx[s] = r[3]; A.vy[s] = r[4]; A.vz[s] = r[5];
     A.d[s] = r[6]; A.dx[s] = r[7]; A.dy[s] = r[8]; A.dz[s] = r[9];
@@ -917,6 +917,7 @@ __global__ void __launch_bounds__(128) k_bnd_apply(const __grid_constant__ P p, 
             }
     }
     A.flag[s] = (uint8_t)nf;
+    }
 }
 
 // compact the particles this rank owns (everything that is not a ghost copy) into the b arrays

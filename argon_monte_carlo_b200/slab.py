@@ -90,8 +90,15 @@ class SlabRank:
         with torch.cuda.device(dev):
             z = lambda *s: torch.zeros(*s, dtype=torch.float64, device=dev)
             self.xfer_send, self.xfer_recv = z(self.nranks, xfer_capacity + 1, REC), z(self.nranks, xfer_capacity + 1, REC)
-            self.bnd_send_up, self.bnd_send_down = z(bnd_capacity + 1, REC), z(bnd_capacity + 1, REC)
-            self.bnd_recv_up, self.bnd_recv_down = z(bnd_capacity + 1, REC), z(bnd_capacity + 1, REC)
+            # boundary buffers live inside one [nranks, ...] tensor per direction of travel so that the
+            # hand-over can also be done with a single all_to_all_single (block r = traffic with rank r)
+            self.bnd_send_all, self.bnd_recv_all = z(self.nranks, bnd_capacity + 1, REC), z(self.nranks, bnd_capacity + 1, REC)
+            spare = lambda: z(bnd_capacity + 1, REC)
+            up, down = rank + 1 < self.nranks, rank > 0
+            self.bnd_send_up = self.bnd_send_all[rank + 1] if up else spare()
+            self.bnd_recv_up = self.bnd_recv_all[rank + 1] if up else spare()
+            self.bnd_send_down = self.bnd_send_all[rank - 1] if down else spare()
+            self.bnd_recv_down = self.bnd_recv_all[rank - 1] if down else spare()
             stream = torch.cuda.current_stream(dev).cuda_stream
         c = AmcSlabConfig()
         c.rank, c.nranks = rank, self.nranks
@@ -140,6 +147,10 @@ class DistTransport:
         import torch.distributed as dist
         self.dist, self.group = dist, group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        import os
+        # neighbour hand-over as one all_to_all_single (about half the launch latency of a batch of four
+        # send/recv on NCCL) unless AMC_SLAB_P2P=1
+        self.nbr_a2a = dist.get_backend(group) == "nccl" and os.environ.get("AMC_SLAB_P2P", "0") != "1"
         self.native_a2a = dist.get_backend(group) == "nccl"
 
     def alltoall(self, ranks):
@@ -159,6 +170,9 @@ class DistTransport:
 
     def neighbors(self, ranks):
         (r,) = ranks
+        if self.nbr_a2a:
+            self.dist.all_to_all_single(r.bnd_recv_all, r.bnd_send_all, group=self.group)
+            return
         ops = getattr(r, "_nbr_ops", None)
         if ops is None:     # the buffers are fixed: build the P2P descriptors once
             ops = []

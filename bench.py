@@ -247,6 +247,10 @@ def run_slabs(args, world, rank, local, dev, hbm_peak, peak_src, barrier, max_ov
     barrier()
     clk = clocks.stop()
     dev_ms = max_over_ranks(float(ms.sum()))
+    per_rank = torch.zeros(world, 5, dtype=torch.float64, device=dev)
+    per_rank[rank, :4] = torch.as_tensor(ms / args.steps, dtype=torch.float64)
+    per_rank[rank, 4] = float(n)
+    dist.all_reduce(per_rank)
     total_particles = float(cfg.num_molecules)
     n_now = sum_over_ranks(float(sim.particles_per_rank()[0]))
     value = total_particles * args.steps / (dev_ms * 1e-3)
@@ -293,6 +297,8 @@ def run_slabs(args, world, rank, local, dev, hbm_peak, peak_src, barrier, max_ov
                                "pairs_and_handover": ms[2] / args.steps, "finish": ms[3] / args.steps},
         "collision_checks_per_s": {"reference_equivalent": checks_ref / (dev_ms / args.steps * 1e-3)},
         "collisions_per_step": collisions, "wall_s": wall, "resident_particles": int(n_now),
+        "per_rank": {"columns": ["advect_walls_ms", "exchange_sort_ms", "pairs_and_handover_ms", "finish_ms", "particles"],
+                     "rows": [[round(float(v), 4) for v in row] for row in per_rank.cpu().tolist()]},
     }
     if rank == 0:
         emit(out)

@@ -65,6 +65,7 @@ def _worker(rank, world, port, out):
     r = SimpleNamespace(rank=rank,
                         xfer_send=torch.zeros(world, cap + 1, slab.REC, dtype=torch.float64),
                         xfer_recv=torch.zeros(world, cap + 1, slab.REC, dtype=torch.float64),
+                        bnd_send_all=None, bnd_recv_all=None,
                         bnd_send_up=torch.full((bcap + 1, slab.REC), 100.0 + rank, dtype=torch.float64),
                         bnd_send_down=torch.full((bcap + 1, slab.REC), 200.0 + rank, dtype=torch.float64),
                         bnd_recv_up=torch.zeros(bcap + 1, slab.REC, dtype=torch.float64),

@@ -21,3 +21,33 @@ for k in range(steps):
     print(k, "collisions", st["collisions"], "per rank", sim.particles_per_rank(),
           "xfer", sim.exchanged["xfer"] - before["xfer"], "boundary", sim.exchanged["boundary"] - before["boundary"])
 sim.close()
+
+# ---- pure compute time of the phases per rank (ranks run one after the other here, so no waiting is included)
+import torch, ctypes as C
+sim = slab.SlabSimulation(cfg, nranks, zs, cuts=cuts, n_total=cfg.num_molecules, seed=17)
+sim.set_state(*state)
+sim.step(3)
+T, R = sim.transport, sim.ranks
+def timed(fn):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); fn(); e1.record(); torch.cuda.synchronize(); return e0.elapsed_time(e1)
+acc = np.zeros((nranks, 5))
+for it in range(3):
+    for i, r in enumerate(R): acc[i, 0] += timed(lambda: r.call("amc_slab_advect"))
+    T.alltoall(R)
+    for i, r in enumerate(R): acc[i, 1] += timed(lambda: r.call("amc_slab_sort", None))
+    for i, r in enumerate(R): acc[i, 2] += timed(lambda: r.call("amc_slab_pairs_begin"))
+    T.neighbors(R)
+    for i, r in enumerate(R): acc[i, 3] += timed(lambda: r.call("amc_slab_apply", C.c_int32(-1)))
+    for g in range(8):
+        for i, r in enumerate(R): acc[i, 2] += timed(lambda: r.call("amc_slab_group", C.c_int32(g)))
+        T.neighbors(R)
+        for i, r in enumerate(R): acc[i, 3] += timed(lambda: r.call("amc_slab_apply", C.c_int32(g)))
+    for i, r in enumerate(R):
+        from argon_monte_carlo_b200 import amc
+        st = amc.AmcStepStats()
+        acc[i, 4] += timed(lambda: r.call("amc_slab_finish", C.byref(st)))
+print("per rank ms/step: advect, sort, pairs(begin+8 groups+pack), apply(9 rounds), finish ; particles")
+for i in range(nranks):
+    print(i, np.round(acc[i] / 3, 3), sim.particles_per_rank()[i])
+sim.close()
