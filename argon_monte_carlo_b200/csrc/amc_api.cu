@@ -320,6 +320,7 @@ extern "C" int amc_set_state(amc_handle *h, int64_t n, const double *x, const do
 static int unsort(amc_handle *h)
 {
     if (h->n == 0) return AMC_OK;
+    k_inverse_perm<<<grid_for(h->n, ADVECT_THREADS), ADVECT_THREADS, 0, h->stream>>>(h->p);
     k_unsort<<<grid_for(h->n, ADVECT_THREADS), ADVECT_THREADS, 0, h->stream>>>(h->p);
     CK(cudaGetLastError());
     std::swap(h->p.a, h->p.b);
@@ -415,7 +416,10 @@ extern "C" int amc_step(amc_handle *h, int32_t n_steps, amc_step_stats *stats)
             p.stats = h->d_stats + s;
             p.step = h->step_index++;
             if (h->n > 0) {
-                int phase = PH_DRIFT | PH_WALLS | (has_recap ? PH_RECAP : 0) | (sweep ? 0 : PH_KEYS);
+                // the recapture that closes step s-1's pair pass rides along in step s's advect kernel
+                const bool fuse_prev = has_recap && s > 0;
+                p.stats_prev = fuse_prev ? h->d_stats + (s - 1) : h->d_stats + s;
+                int phase = PH_DRIFT | PH_WALLS | (has_recap ? PH_RECAP : 0) | (sweep ? 0 : PH_KEYS) | (fuse_prev ? PH_RECAP_POST : 0);
                 if (!sweep) {
                     CK(cudaMemsetAsync(p.band_count, 0, (h->n_buckets + 1) * sizeof(int32_t), h->stream));
                     CK(cudaMemsetAsync(p.rest_count, 0, (h->n_buckets + 1) * sizeof(int32_t), h->stream));
@@ -428,7 +432,7 @@ extern "C" int amc_step(amc_handle *h, int32_t n_steps, amc_step_stats *stats)
                 rc = run_pairs(h, &h->last_launches);
                 if (rc != AMC_OK) return rc;
                 CK(cudaEventRecord(h->events[4 * s + 3], h->stream));
-                if (has_recap) {
+                if (has_recap && s == chunk - 1) { // last step of the call: close it now
                     k_recapture_post<<<grid_for(h->n, ADVECT_THREADS), ADVECT_THREADS, 0, h->stream>>>(p);
                     h->last_launches += 1;
                 }

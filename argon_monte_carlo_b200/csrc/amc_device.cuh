@@ -116,6 +116,7 @@ struct P {
     int32_t *esc_slot;
     int32_t *esc_cell; /* [esc_cap][8] member cell per colour group, -1 = none */
     StatsDev *stats;
+    StatsDev *stats_prev; /* counters of the previous step (recapture fused into the next step's k_advect) */
 };
 
 // ---------------------------------------------------------------- deterministic accumulation

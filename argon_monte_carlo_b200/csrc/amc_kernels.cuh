@@ -59,7 +59,11 @@ __global__ void __launch_bounds__(ADVECT_THREADS) k_advect(const __grid_constant
         int cnt = p.kind == AMC_KIND_TEMP ? temp_oob(p.g, q) : 0;
         int moved = p.kind == AMC_KIND_TEMP ? temp_recapture(p.g, q) : pore_recapture(p.g, q);
         if (p.kind != AMC_KIND_TEMP) cnt = moved;
-        if (cnt) atomicAdd(&p.stats->oob_pp, (unsigned long long)cnt);
+        if (cnt) atomicAdd(&p.stats_prev->oob_pp, (unsigned long long)cnt);
+        if (p.kind == AMC_KIND_TEMP && moved) {
+            int after = temp_oob(p.g, q);
+            if (after) atomicAdd(&p.stats_prev->oob_pp_after, (unsigned long long)after);
+        }
     }
     if (phase & PH_DRIFT) {
         q.px = q.x; q.py = q.y; q.pz = q.z;
@@ -232,12 +236,18 @@ __global__ void __launch_bounds__(ADVECT_THREADS) k_scatter(const __grid_constan
     }
 }
 
-// gather back to original index order (amc_get_state)
-__global__ void __launch_bounds__(ADVECT_THREADS) k_unsort(const __grid_constant__ P p)
+// back to original index order (amc_get_state): first the inverse permutation (4-byte scatter), then a
+// gather with coalesced writes -- random 8-byte reads cost far less than random 8-byte writes
+__global__ void __launch_bounds__(ADVECT_THREADS) k_inverse_perm(const __grid_constant__ P p)
 {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= p.n) return;
-    int64_t t = p.a.id[s];
+    if (s < p.n) p.key[p.a.id[s]] = (int32_t)s;
+}
+__global__ void __launch_bounds__(ADVECT_THREADS) k_unsort(const __grid_constant__ P p)
+{
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= p.n) return;
+    int64_t s = p.key[t];
     p.b.x[t] = p.a.x[s]; p.b.y[t] = p.a.y[s]; p.b.z[t] = p.a.z[s];
     p.b.vx[t] = p.a.vx[s]; p.b.vy[t] = p.a.vy[s]; p.b.vz[t] = p.a.vz[s];
     p.b.d[t] = p.a.d[s]; p.b.dx[t] = p.a.dx[s]; p.b.dy[t] = p.a.dy[s]; p.b.dz[t] = p.a.dz[s];

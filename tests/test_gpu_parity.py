@@ -138,3 +138,27 @@ def test_cube_steps_bit_exact(oracle, cube_cfg, cube_init):
     for a, b in zip(sim.completed_paths(), sink.arrays()):
         assert np.array_equal(np.sort(a), np.sort(b))
     sim.close()
+
+
+def test_multi_step_call_equals_single_steps(oracle, temp_cfg, temp_init):
+    """amc_step(h, 5) fuses the closing recapture of each step into the next step's advect kernel;
+    results and per-step counters must equal five amc_step(h, 1) calls and the oracle."""
+    from argon_monte_carlo_b200 import amc, config
+    from oracle import steps
+    cheb = config.gap_energy_chebyshev(temp_cfg, 16)
+    a = amc.Simulation(temp_cfg, seed=5, cheb=cheb)
+    b = amc.Simulation(temp_cfg, seed=5, cheb=cheb)
+    a.set_state(*temp_init)
+    b.set_state(*temp_init)
+    sa = a.step(5)
+    sb = [b.step(1)[0] for _ in range(5)]
+    st = oracle.ParticleState(*temp_init)
+    so = [steps.temp_step_philox(st, temp_cfg, 5, k, cheb) for k in range(5)]
+    for x, y, o in zip(sa, sb, so):
+        for k in ("collisions", "oob_after_walls", "oob_after_pp", "oob_after_pp_recapture", "completed_paths", "dpz", "e_cold"):
+            assert x[k] == y[k], k
+        assert x["collisions"] == o["collisions"] and x["oob_after_pp"] == o["oob_after_pp"]
+    ga, gb = a.get_state(), b.get_state()
+    for k in KEYS:
+        assert np.array_equal(ga[k], gb[k]) and np.array_equal(ga[k], getattr(st, k)), k
+    a.close(); b.close()
