@@ -74,6 +74,7 @@ EXPORTS = ("amc_create", "amc_destroy", "amc_last_error", "amc_abi_version", "am
            "amc_num_particles", "amc_step", "amc_drift", "amc_walls", "amc_recapture", "amc_pairs", "amc_wall_case",
            "amc_wall_hits_pending", "amc_wall_apply_directions", "amc_get_histograms", "amc_get_pair_list",
            "amc_get_wall_bits", "amc_get_completed_paths", "amc_clear_taps", "amc_set_step_index", "amc_last_timing",
+           "amc_get_outputs_raw", "amc_set_outputs_raw", "amc_get_step_index",
            "amc_slab_enable", "amc_set_stream", "amc_set_ids", "amc_slab_advect", "amc_slab_sort", "amc_slab_pairs_begin",
            "amc_slab_group", "amc_slab_apply", "amc_slab_finish", "amc_slab_get_owned")
 
@@ -90,6 +91,8 @@ def load_library():
         L.amc_last_error.argtypes = [C.c_void_p]
         L.amc_num_particles.restype = C.c_int64
         L.amc_num_particles.argtypes = [C.c_void_p]
+        L.amc_get_step_index.restype = C.c_int64
+        L.amc_get_step_index.argtypes = [C.c_void_p]
         if L.amc_abi_version() != ABI_VERSION:
             raise AmcError("libamc.so ABI version mismatch")
         _lib = L
@@ -358,6 +361,36 @@ class Simulation:
         self._check(rc, "amc_get_completed_paths")
         k = int(n.value)
         return tuple(a[:k].copy() for a in arrs)
+
+    # ------------------------------------------------------------------ checkpoint / resume
+    def checkpoint(self, path=None):
+        """Everything needed to continue the run exactly: particle state, histograms, free-path sums
+        (raw fixed-point limbs) and the step index that keys the device RNG.  Returns the dict and, if
+        `path` is given, writes it with np.savez."""
+        st = self.get_state()
+        counts = np.zeros((4, NUM_BINS), dtype=np.uint64)
+        n = C.c_uint64(0)
+        limbs = np.zeros(8, dtype=np.uint64)
+        rc = self.lib.amc_get_outputs_raw(self.h, counts.ctypes.data_as(C.POINTER(C.c_uint64)), C.byref(n),
+                                          limbs.ctypes.data_as(C.POINTER(C.c_uint64)))
+        self._check(rc, "amc_get_outputs_raw")
+        st.update(hist_counts=counts, n_paths=np.uint64(n.value), path_limbs=limbs,
+                  step_index=np.int64(self.lib.amc_get_step_index(self.h)))
+        if path is not None:
+            np.savez(path, **st)
+        return st
+
+    def restore(self, ck):
+        """ck: dict from checkpoint() or the path of an .npz written by it."""
+        if isinstance(ck, (str, bytes)) or hasattr(ck, "__fspath__"):
+            ck = dict(np.load(ck))
+        self.set_state(*[ck[k] for k in ("x", "y", "z", "vx", "vy", "vz", "dist", "dist_x", "dist_y", "dist_z")], flag=ck["flag"])
+        counts = np.ascontiguousarray(ck["hist_counts"], dtype=np.uint64)
+        limbs = np.ascontiguousarray(ck["path_limbs"], dtype=np.uint64)
+        rc = self.lib.amc_set_outputs_raw(self.h, counts.ctypes.data_as(C.POINTER(C.c_uint64)), C.c_uint64(int(ck["n_paths"])),
+                                          limbs.ctypes.data_as(C.POINTER(C.c_uint64)))
+        self._check(rc, "amc_set_outputs_raw")
+        self.set_step_index(int(ck["step_index"]))
 
     def clear_taps(self):
         self._check(self.lib.amc_clear_taps(self.h), "amc_clear_taps")

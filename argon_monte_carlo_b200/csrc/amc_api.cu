@@ -701,6 +701,30 @@ extern "C" int amc_clear_taps(amc_handle *h)
     return AMC_OK;
 }
 
+extern "C" int amc_get_outputs_raw(amc_handle *h, uint64_t *counts, uint64_t *n_paths, uint64_t *limbs8)
+{
+    if (!h) return AMC_E_INVALID;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    if (counts) CK(cudaMemcpy(counts, h->p.hist, 4 * AMC_NUM_BINS * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    if (n_paths) CK(cudaMemcpy(n_paths, h->p.path_count, sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    if (limbs8) CK(cudaMemcpy(limbs8, h->p.path_sums, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    return AMC_OK;
+}
+
+extern "C" int amc_set_outputs_raw(amc_handle *h, const uint64_t *counts, uint64_t n_paths, const uint64_t *limbs8)
+{
+    if (!h || !counts || !limbs8) return AMC_E_INVALID;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(h->p.hist, counts, 4 * AMC_NUM_BINS * sizeof(uint64_t), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->p.path_count, &n_paths, sizeof(uint64_t), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->p.path_sums, limbs8, 8 * sizeof(uint64_t), cudaMemcpyHostToDevice));
+    return AMC_OK;
+}
+
+extern "C" int64_t amc_get_step_index(const amc_handle *h) { return h ? h->step_index : -1; }
+
 extern "C" int amc_set_step_index(amc_handle *h, int64_t step)
 {
     if (!h) return AMC_E_INVALID;

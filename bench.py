@@ -161,9 +161,13 @@ def run_ours(args):
     pair_ms = ms[2] / args.steps
     checks_ref = float(np.mean([s["pair_checks_ref"] for s in stats]))
     collisions = float(np.mean([s["collisions"] for s in stats]))
+    # per launch: algorithmic bytes = 32 B x particles / 8 colour groups, duration = pair time / 8; traffic from the
+    # ncu --set full capture of this workload (profiles/r1_v5_ncu_full_summary.csv: 87.3 MB read + 3.6 MB written)
     roofline = {"bound": "hbm", "kernel": "k_pairs_group (8 launches per step)",
                 "achieved": B_PAIR * n / (pair_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                "peak_source": peak_src, "traffic": None}
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": B_PAIR * n / 8,
+                "avg_launch_ms": pair_ms / 8,
+                "traffic": 90.9e6 * n / 12499989 if abs(n - 12499989) < 1e5 else None}
     roofline["frac"] = roofline["achieved"] / hbm_peak
     whole = {"achieved": B_STEP * n * args.steps / (ms[4] * 1e-3) / 1e9, "unit": "GB/s"}
     whole["frac"] = whole["achieved"] / hbm_peak

@@ -172,6 +172,13 @@ int amc_get_wall_bits(amc_handle *h, uint16_t *bits);  /* bit c set: AMC_CASE c 
 int amc_get_completed_paths(amc_handle *h, int64_t cap, int64_t *n, double *total, double *cx, double *cy, double *cz);
 int amc_clear_taps(amc_handle *h);
 
+/* checkpoint / resume (the reference keeps everything in module globals and cannot restart a run): together with
+ * amc_get_state / amc_set_state and the step index these restore a handle exactly.  limbs8: the four free-path
+ * sums as two 64-bit fixed-point limbs each (see amc_get_histograms for their decoded value). */
+int amc_get_outputs_raw(amc_handle *h, uint64_t *counts, uint64_t *n_paths, uint64_t *limbs8);
+int amc_set_outputs_raw(amc_handle *h, const uint64_t *counts, uint64_t n_paths, const uint64_t *limbs8);
+int64_t amc_get_step_index(const amc_handle *h);
+
 /* set the step counter that keys the device RNG (default: counts amc_step / amc_walls calls from 0) */
 int amc_set_step_index(amc_handle *h, int64_t step);
 
