@@ -17,7 +17,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 
 
 def library_path() -> str:
-    return os.path.join(_HERE, "libamc.so")
+    return os.environ.get("AMC_LIBRARY") or os.path.join(_HERE, "libamc.so")
 
 
 def _nvcc() -> str:
@@ -36,14 +36,14 @@ def is_stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_library(force: bool = False, verbose: bool = False) -> str:
-    lib = library_path()
-    if not force and not is_stale():
+def build_library(force: bool = False, verbose: bool = False, defines=(), output=None) -> str:
+    lib = output or library_path()
+    if not force and not is_stale() and not output:
         return lib
     env = dict(os.environ)
     env.pop("CC", None)   # the image exports a CC that is not a usable nvcc host compiler
     env.pop("CXX", None)
-    cmd = [_nvcc(), *NVCC_FLAGS, "-I", _INCLUDE, "-o", lib] + [os.path.join(_CSRC, f) for f in SOURCES]
+    cmd = [_nvcc(), *NVCC_FLAGS, *["-D" + d for d in defines], "-I", _INCLUDE, "-o", lib] + [os.path.join(_CSRC, f) for f in SOURCES]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")

@@ -238,7 +238,7 @@ static int create_impl(amc_handle *h, const amc_config *cfg, int device)
     {
         int64_t per_group = (int64_t)(cfg->nc[0] / 2 + 1) * (cfg->nc[1] / 2 + 1) * (cfg->nc[2] / 2 + 1);
         p.wl_stride = (int32_t)per_group;
-        ALLOC(p.wl, per_group * 8); ALLOC(p.wl_count, 8); ALLOC(p.cell_active, per_group * 8);
+        ALLOC(p.wl, (size_t)per_group * 8 * AMC_WI); ALLOC(p.wl_count, 8); ALLOC(p.cell_active, per_group * 8);
         CK(cudaMemset(p.wl_count, 0, 8 * sizeof(int32_t)));
         CK(cudaMemset(p.cell_active, 0, per_group * 8 * sizeof(int32_t)));
     }
@@ -962,3 +962,13 @@ extern "C" int amc_slab_get_owned(amc_handle *h, int64_t cap, int64_t *n, int64_
     if (ids) for (int32_t k = 0; k < c; k++) ids[k] = tmp[(size_t)k];
     return AMC_OK;
 }
+
+#ifdef AMC_PHASE_CLOCK
+extern "C" int amc_debug_phase_clocks(unsigned long long out[16], int reset)
+{
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, g_phase_clk, 16 * sizeof(unsigned long long));
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_phase_clk, z, sizeof(z)); }
+    return 0;
+}
+#endif

@@ -23,6 +23,7 @@
 
 #define AMC_MAX_MEMBERS 512  /* particles per reference cell incl. overlap band (reference: <= 308) */
 #define AMC_MAX_CAND 128     /* simultaneously overlapping pairs per cell visit */
+#define AMC_WI 32            /* ints per work item: cell, kx, ky, kz, beg[8], len[8], 6 doubles of bounds = 128 bytes */
 #define AMC_XBINS 64         /* slabs along x of the in-CTA neighbour search (multiple of 32) */
 #define AMC_SUB_MIN_N 48     /* below this many members the plain all-pairs scan is cheaper */
 
@@ -80,7 +81,7 @@ struct P {
     unsigned long long *tap_path_count;
     double *tap_paths[4];
     uint16_t *wall_bits;
-    int32_t *wl;          /* [8][wl_stride] reference cells of each colour group that can hold a pair */
+    int32_t *wl;          /* [8][wl_stride][AMC_WI] work items: the cells of each colour group that can hold a pair */
     int32_t *wl_count;    /* [8] */
     int32_t *cell_active; /* [8][wl_stride] 1 = cell is in its group's worklist */
     int32_t wl_stride;    /* reference cells per colour group */
@@ -534,4 +535,23 @@ __device__ __forceinline__ int member_axis(const double *edge, const double *lo,
     for (int kk = k; kk <= k + 1 && kk < nc; kk++)
         if ((kk & 1) == par && lo[kk] < v && v < edge[kk + 1]) return kk;
     return -1;
+}
+
+// One work item of the pair pass = everything a CTA needs to start on a reference cell, in one 128-byte
+// record: cell id, cell indices, the 8 candidate ranges (owner cell: all of it; 7 low-side neighbours:
+// their band prefix) and the cell's membership bounds (Pore:527-529).
+__device__ __forceinline__ void write_work_item(const P &p, int32_t *w, int cell, int kx, int ky, int kz)
+{
+    w[0] = cell; w[1] = kx; w[2] = ky; w[3] = kz;
+#pragma unroll
+    for (int nb = 0; nb < 8; nb++) {
+        int oc = ((kx + 1 - (nb >> 2)) * p.pnc[1] + (ky + 1 - ((nb >> 1) & 1))) * p.pnc[2] + (kz + 1 - (nb & 1));
+        int beg = p.cell_start[oc];
+        w[4 + nb] = beg;
+        w[12 + nb] = nb == 0 ? p.cell_start[oc + 1] - beg : p.band_count[oc];
+    }
+    double *d = reinterpret_cast<double *>(w + 20);
+    d[0] = p.lo[0][kx]; d[1] = p.edge[0][kx + 1];
+    d[2] = p.lo[1][ky]; d[3] = p.edge[1][ky + 1];
+    d[4] = p.lo[2][kz]; d[5] = p.edge[2][kz + 1];
 }

@@ -300,6 +300,14 @@ __global__ void __launch_bounds__(ADVECT_THREADS) k_recapture_post(const __grid_
 // those two against all members for keys above the cursor.  That reproduces the sequential sweep
 // exactly: pairs below the cursor were already passed, pairs not involving a moved particle keep
 // their first-scan verdict.
+#ifdef AMC_PHASE_CLOCK
+// debug build only (tools/phase_clocks.py): cycles spent by thread 0 between the phase boundaries of a cell visit
+__device__ unsigned long long g_phase_clk[16];
+#define PHASE_MARK(k) do { if (threadIdx.x == 0) { long long now_ = clock64(); atomicAdd(&g_phase_clk[k], (unsigned long long)(now_ - S.t_last)); S.t_last = now_; } } while (0)
+#else
+#define PHASE_MARK(k) do { } while (0)
+#endif
+
 struct CellShared {
     double x[AMC_MAX_MEMBERS], y[AMC_MAX_MEMBERS], z[AMC_MAX_MEMBERS];
     int32_t id[AMC_MAX_MEMBERS], slot[AMC_MAX_MEMBERS], src[AMC_MAX_MEMBERS];
@@ -309,6 +317,7 @@ struct CellShared {
     unsigned long long cursor;
     int moved_a, moved_b;
     int kx, ky, kz; /* 0-based cell indices of this visit (colour-group mode) */
+    long long t_last;
     /* neighbour search: members binned into slabs along x */
     double lo[3], inv_s[3]; /* [0]: low bound and 1/slab width along x */
     int sub_ok, nb;
@@ -435,8 +444,8 @@ __device__ __noinline__ void resolve_pair(const P &p, CellShared &S, int m1, int
                 int cz = member_axis(p.edge[2], p.lo[2], p.nc[2], o[2], (g2 ^ p.zoff) & 1, z);
                 int32_t cc = (cx < 0 || cy < 0 || cz < 0) ? -1 : ((cx >> 1) * p.nh[1] + (cy >> 1)) * p.nh[2] + (cz >> 1);
                 p.esc_cell[e * 8 + g2] = cc;
-                if (cc >= 0 && atomicExch(&p.cell_active[(size_t)g2 * p.wl_stride + cc], 1) == 0)
-                    p.wl[(size_t)g2 * p.wl_stride + atomicAdd(&p.wl_count[g2], 1)] = cc; /* group g2 has not started yet */
+                if (cc >= 0 && atomicExch(&p.cell_active[(size_t)g2 * p.wl_stride + cc], 1) == 0) /* group g2 has not started yet */
+                    write_work_item(p, p.wl + ((size_t)g2 * p.wl_stride + atomicAdd(&p.wl_count[g2], 1)) * AMC_WI, cc, cx, cy, cz);
             }
         }
     }
@@ -471,6 +480,7 @@ __device__ void cell_process(const P &p, CellShared &S, int group, int cell)
             S.pos_of[k] = (uint16_t)atomicAdd(&S.sub_cnt[c], 1);
         }
         __syncthreads();
+        PHASE_MARK(2); /* bin */
         if (warp == 0) { // exclusive scan of the slab counters by one warp
             constexpr int PER = AMC_XBINS / 32;
             int v[PER], sum = 0;
@@ -485,19 +495,29 @@ __device__ void cell_process(const P &p, CellShared &S, int group, int cell)
             if (lane == 31) { S.sub_off[AMC_XBINS] = ex; S.sub_off[AMC_XBINS + 1] = ex; }
         }
         __syncthreads();
+        PHASE_MARK(3); /* scan */
         for (int k = tid; k < n; k += nthreads) {
             int pos = S.sub_off[S.sub_of[k]] + S.pos_of[k];
             S.pos_of[k] = (uint16_t)pos;
             S.order[pos] = (uint16_t)k;
         }
         __syncthreads();
+        PHASE_MARK(4); /* order */
         unsigned int mine = 0;
         for (int q0 = tid; q0 < n; q0 += nthreads) { // walk in slab order so neighbouring lanes have similar ranges
             int a = S.order[q0];
             int end = S.sub_off[S.sub_of[a] + 2];
             double xa = S.x[a], ya = S.y[a], za = S.z[a];
             mine += end - (q0 + 1);
-            for (int q = q0 + 1; q < end; q++) {
+            int q = q0 + 1;
+            for (; q + 1 < end; q += 2) { // two independent tests in flight
+                int b2 = S.order[q], b3 = S.order[q + 1];
+                bool h2 = overlap(p, xa, ya, za, S.x[b2], S.y[b2], S.z[b2]);
+                bool h3 = overlap(p, xa, ya, za, S.x[b3], S.y[b3], S.z[b3]);
+                if (h2) push_cand(S, p, a, b2);
+                if (h3) push_cand(S, p, a, b3);
+            }
+            if (q < end) {
                 int b2 = S.order[q];
                 if (overlap(p, xa, ya, za, S.x[b2], S.y[b2], S.z[b2])) push_cand(S, p, a, b2);
             }
@@ -506,6 +526,7 @@ __device__ void cell_process(const P &p, CellShared &S, int group, int cell)
         if (lane == 0 && mine) atomicAdd(&S.nexec, mine);
     }
     __syncthreads();
+    PHASE_MARK(5); /* search */
     if (S.ncand == 0) return;
     if (tid == 0) { S.cursor = 0; S.done = 0; if (S.ncand > AMC_MAX_CAND) S.ncand = AMC_MAX_CAND; }
     __syncthreads();
@@ -556,7 +577,6 @@ __device__ void cell_process(const P &p, CellShared &S, int group, int cell)
 __global__ void __launch_bounds__(ADVECT_THREADS) k_build_worklist(const __grid_constant__ P p)
 {
     int cid = blockIdx.x * blockDim.x + threadIdx.x; /* linear over (kx, ky, kz), z fastest */
-    if (threadIdx.x < 8 && blockIdx.x == 0) { /* wl_count is zeroed by the host before this launch */ }
     int ncell = p.nc[0] * p.nc[1] * p.nc[2];
     if (cid >= ncell) return;
     int kz = cid % p.nc[2], ky = (cid / p.nc[2]) % p.nc[1], kx = cid / (p.nc[2] * p.nc[1]);
@@ -570,7 +590,7 @@ __global__ void __launch_bounds__(ADVECT_THREADS) k_build_worklist(const __grid_
     int cell = ((kx >> 1) * p.nh[1] + (ky >> 1)) * p.nh[2] + (kz >> 1);
     int active = total >= 2;
     p.cell_active[(size_t)group * p.wl_stride + cell] = active;
-    if (active) p.wl[(size_t)group * p.wl_stride + atomicAdd(&p.wl_count[group], 1)] = cell;
+    if (active) write_work_item(p, p.wl + ((size_t)group * p.wl_stride + atomicAdd(&p.wl_count[group], 1)) * AMC_WI, cell, kx, ky, kz);
 }
 
 // one colour group (Pore:522-549): persistent CTAs walk the group's worklist
@@ -580,45 +600,52 @@ __global__ void __launch_bounds__(PAIR_THREADS, 8) k_pairs_group(const __grid_co
     __shared__ double s_lo[3], s_hi[3];
     __shared__ int s_ne;
     const int tid = threadIdx.x;
-    const int nhy = p.nh[1], nhz = p.nh[2];
     const Arrays &A = p.a;
     const int nwork = p.wl_count[group];
-    const int32_t *wl = p.wl + (size_t)group * p.wl_stride;
-    if (tid == 0) { S.nexec = 0; S.nref = 0; }
+    const int32_t *wl = p.wl + (size_t)group * p.wl_stride * AMC_WI;
+    __shared__ __align__(16) int s_hdr[AMC_WI];
+    if (tid == 0) {
+        S.nexec = 0; S.nref = 0;
+        int ne = *p.esc_count; /* entries appended while this group runs belong to later groups */
+        s_ne = ne > p.esc_cap ? p.esc_cap : ne;
+    }
     for (int c = tid; c < AMC_XBINS; c += PAIR_THREADS) S.sub_cnt[c] = 0; /* kept zero by the scan */
+    // warp 0 fetches a work item with one coalesced 128-byte load and already has the next one in flight
+    // while the CTA works on the current cell
+    int next_hdr = 0;
+    if (tid < AMC_WI && (int)blockIdx.x < nwork) next_hdr = wl[(size_t)blockIdx.x * AMC_WI + tid];
     for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
-        const int cell = wl[w];
         __syncthreads(); /* previous cell fully processed before S is reused */
-        if (tid < 8) {
-            // lanes 0..7: the 8 candidate owner-cell ranges (own cell: all of it; the 7 low-side
-            // neighbours: their band prefix); lanes 0..2 also fetch the bounds of one axis
-            const int hz = cell % nhz, hy = (cell / nhz) % nhy, hx = cell / (nhz * nhy);
-            const int kx = 2 * hx + ((group >> 2) & 1), ky = 2 * hy + ((group >> 1) & 1), kz = 2 * hz + ((group ^ p.zoff) & 1);
-            int ox = kx + 1 - (tid >> 2), oy = ky + 1 - ((tid >> 1) & 1), oz = kz + 1 - (tid & 1);
-            int oc = (ox * p.pnc[1] + oy) * p.pnc[2] + oz;
-            int beg = p.cell_start[oc], len = tid == 0 ? p.cell_start[oc + 1] - beg : p.band_count[oc];
-            S.rbeg[tid] = beg;
-            int inc = len;
+#ifdef AMC_PHASE_CLOCK
+        if (tid == 0) { S.t_last = clock64(); atomicAdd(&g_phase_clk[15], 1ull); }
+#endif
+        if (tid < AMC_WI) {
+            s_hdr[tid] = next_hdr;
+            int wn = w + gridDim.x;
+            if (wn < nwork) next_hdr = wl[(size_t)wn * AMC_WI + tid];
+            __syncwarp();
+            if (tid < 8) {
+                S.rbeg[tid] = s_hdr[4 + tid];
+                int inc = s_hdr[12 + tid];
 #pragma unroll
-            for (int o = 1; o < 8; o <<= 1) { int t = __shfl_up_sync(0xffu, inc, o); if (tid >= o) inc += t; }
-            S.rcum[tid + 1] = inc;
+                for (int o = 1; o < 8; o <<= 1) { int t = __shfl_up_sync(0xffu, inc, o); if (tid >= o) inc += t; }
+                S.rcum[tid + 1] = inc;
+            }
             if (tid < 3) {
-                int k = tid == 0 ? kx : (tid == 1 ? ky : kz);
-                double lo = p.lo[tid][k], hi = p.edge[tid][k + 1];
+                const double *d = reinterpret_cast<const double *>(s_hdr + 20);
+                double lo = d[2 * tid], hi = d[2 * tid + 1];
                 s_lo[tid] = lo; s_hi[tid] = hi;
                 if (tid == 0) { /* slabs along x, at least 1.05 collision ranges wide */
                     int nb = (int)fmin((double)AMC_XBINS, floor((hi - lo) / (1.05 * p.cr)));
                     S.nb = nb; S.sub_ok = nb >= 2;
                     S.lo[0] = lo; S.inv_s[0] = (double)nb / (hi - lo);
+                    S.rcum[0] = 0; S.n = 0; S.ncand = 0; S.kx = s_hdr[1]; S.ky = s_hdr[2]; S.kz = s_hdr[3];
                 }
-            }
-            if (tid == 0) {
-                S.rcum[0] = 0; S.n = 0; S.ncand = 0; S.kx = kx; S.ky = ky; S.kz = kz;
-                int ne = *p.esc_count;
-                s_ne = ne > p.esc_cap ? p.esc_cap : ne;
             }
         }
         __syncthreads();
+        PHASE_MARK(0); /* header */
+        const int cell = s_hdr[0];
         const double lox = s_lo[0], hix = s_hi[0], loy = s_lo[1], hiy = s_hi[1], loz = s_lo[2], hiz = s_hi[2];
         {
             // membership is decided on the live position (Pore:527-530); the 8 ranges are walked as one
@@ -631,9 +658,10 @@ __global__ void __launch_bounds__(PAIR_THREADS, 8) k_pairs_group(const __grid_co
                 int s = S.rbeg[nb] + (t - S.rcum[nb]);
                 unsigned fl = A.flag[s];
                 double x = A.x[s], y = A.y[s], z = A.z[s];
+                int id = A.id[s]; /* issued with the other loads: one round trip per iteration */
                 if (!(fl & AMC_FLAG_ESC) && lox < x && x < hix && loy < y && y < hiy && loz < z && z < hiz) {
                     int k = atomicAdd(&S.n, 1);
-                    if (k < AMC_MAX_MEMBERS) { S.x[k] = x; S.y[k] = y; S.z[k] = z; S.id[k] = A.id[s]; S.slot[k] = s; S.src[k] = -1 - nb; }
+                    if (k < AMC_MAX_MEMBERS) { S.x[k] = x; S.y[k] = y; S.z[k] = z; S.id[k] = id; S.slot[k] = s; S.src[k] = -1 - nb; }
                 }
             }
             for (int e = tid; e < s_ne; e += PAIR_THREADS) { /* particles that left their sorted owner cell earlier in this pass */
@@ -644,12 +672,14 @@ __global__ void __launch_bounds__(PAIR_THREADS, 8) k_pairs_group(const __grid_co
             }
         }
         __syncthreads();
+        PHASE_MARK(1); /* gather */
         if (S.n > AMC_MAX_MEMBERS) {
             __syncthreads();
             if (tid == 0) { atomicAdd(&p.stats->cell_overflow, 1ull); S.n = AMC_MAX_MEMBERS; }
             __syncthreads();
         }
         if (S.n >= 2) cell_process(p, S, group, cell);
+        PHASE_MARK(7); /* resolution loop (cells with candidates) */
     }
     __syncthreads();
     if (tid == 0) { /* one pair of global atomics per CTA instead of per cell */
@@ -923,7 +953,7 @@ __global__ void __launch_bounds__(128) k_bnd_apply(const __grid_constant__ P p, 
                 int32_t cc = (cx < 0 || cy < 0 || cz < 0) ? -1 : ((cx >> 1) * p.nh[1] + (cy >> 1)) * p.nh[2] + (cz >> 1);
                 p.esc_cell[e * 8 + g2] = cc;
                 if (cc >= 0 && atomicExch(&p.cell_active[(size_t)g2 * p.wl_stride + cc], 1) == 0)
-                    p.wl[(size_t)g2 * p.wl_stride + atomicAdd(&p.wl_count[g2], 1)] = cc;
+                    write_work_item(p, p.wl + ((size_t)g2 * p.wl_stride + atomicAdd(&p.wl_count[g2], 1)) * AMC_WI, cc, cx, cy, cz);
             }
     }
     A.flag[s] = (uint8_t)nf;
