@@ -43,7 +43,7 @@ __device__ __forceinline__ int warp_rank(int32_t *counter, int tag)
 //   walls         Pore:442-485 / Temp:693-753 (device RNG) / Cube:192-226
 //   recapture     Pore:354-375 / Temp:560-616
 //   keys          owner cell of the final position + rank inside that cell (counting sort, pass 1)
-__global__ void __launch_bounds__(ADVECT_THREADS) k_advect(const __grid_constant__ P p, const int phase)
+__global__ void __launch_bounds__(ADVECT_THREADS, 4) k_advect(const __grid_constant__ P p, const int phase)
 {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= p.n) return;
