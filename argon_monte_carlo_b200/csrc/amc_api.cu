@@ -872,7 +872,7 @@ extern "C" int amc_slab_sort(amc_handle *h, int64_t *n_resident)
     return AMC_OK;
 }
 
-extern "C" int amc_slab_pairs_begin(amc_handle *h)
+extern "C" int amc_slab_pairs_begin(amc_handle *h, int32_t pre_round)
 {
     int rc = slab_check(h);
     if (rc != AMC_OK) return rc;
@@ -882,9 +882,7 @@ extern "C" int amc_slab_pairs_begin(amc_handle *h)
     CK(cudaMemsetAsync(p.wl_count, 0, 8 * sizeof(int32_t), h->stream));
     int ncell = p.nc[0] * p.nc[1] * p.nc[2];
     k_build_worklist<<<grid_for(ncell, ADVECT_THREADS), ADVECT_THREADS, 0, h->stream>>>(p);
-    dim3 pg(grid_for(p.bnd_cap, ADVECT_THREADS), 2);
-    k_bnd_pack<<<pg, ADVECT_THREADS, 0, h->stream>>>(p); // immigrants that landed in the top band
-    k_bnd_reset<<<1, 32, 0, h->stream>>>(p);
+    if (pre_round) k_bnd_pack<<<2, ADVECT_THREADS, 0, h->stream>>>(p); // immigrants that landed in the top band; else they travel after group 0
     CK(cudaGetLastError());
     return AMC_OK;
 }
@@ -898,9 +896,7 @@ extern "C" int amc_slab_group(amc_handle *h, int32_t g)
     int ncell = p.nc[0] * p.nc[1] * p.nc[2];
     unsigned grid = (unsigned)std::min<int64_t>((int64_t)h->pair_grid, std::max<int64_t>(ncell / 8, 1));
     if (h->n) k_pairs_group<<<grid, PAIR_THREADS, 0, h->stream>>>(p, g);
-    dim3 pg(grid_for(p.bnd_cap, ADVECT_THREADS), 2);
-    k_bnd_pack<<<pg, ADVECT_THREADS, 0, h->stream>>>(p);
-    k_bnd_reset<<<1, 32, 0, h->stream>>>(p);
+    k_bnd_pack<<<2, ADVECT_THREADS, 0, h->stream>>>(p);
     CK(cudaGetLastError());
     return AMC_OK;
 }
@@ -911,8 +907,7 @@ extern "C" int amc_slab_apply(amc_handle *h, int32_t group_done)
     if (rc != AMC_OK) return rc;
     P &p = h->p;
     p.group_done = group_done;
-    if (p.srank + 1 < p.nranks) k_bnd_apply<<<64, 128, 0, h->stream>>>(p, 0);
-    if (p.srank > 0) k_bnd_apply<<<64, 128, 0, h->stream>>>(p, 1);
+    if (p.nranks > 1) k_bnd_apply<<<dim3(48, 2), 128, 0, h->stream>>>(p);
     CK(cudaGetLastError());
     return AMC_OK;
 }

@@ -858,37 +858,38 @@ __global__ void __launch_bounds__(ADVECT_THREADS) k_xfer_unpack(const __grid_con
     else p.rank[s] = ~atomicAdd(&p.rest_count[k], 1);
 }
 
-// after a colour group: turn the dirty slots of one direction into update records
+// after a colour group: turn the dirty slots into update records, one block per direction (up, down);
+// the block clears its queue counter when it is done
 __global__ void __launch_bounds__(ADVECT_THREADS) k_bnd_pack(const __grid_constant__ P p)
 {
-    int dir = blockIdx.y;
-    int cnt = min(p.bnd_n[dir], p.bnd_cap);
+    const int dir = blockIdx.x;
+    const int cnt = min(p.bnd_n[dir], p.bnd_cap);
     double *buf = p.bnd_send[dir];
-    int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j == 0) buf[0] = (double)cnt;
-    if (j >= cnt) return;
-    int s = p.bnd_dirty[dir][j];
     const Arrays &A = p.a;
-    double *r = buf + (size_t)(1 + j) * AMC_REC;
-    r[0] = A.x[s]; r[1] = A.y[s]; r[2] = A.z[s]; r[3] = A.vx[s]; r[4] = A.vy[s]; r[5] = A.vz[s];
-    r[6] = A.d[s]; r[7] = A.dx[s]; r[8] = A.dy[s]; r[9] = A.dz[s]; r[10] = (double)A.id[s];
-    r[11] = (double)(A.flag[s] & AMC_FLAG_PATH);
-    // clear this direction's "queued" bit (32-bit atomic on the word that holds the flag byte)
-    unsigned bit = dir == 0 ? AMC_FLAG_DIRTY_UP : AMC_FLAG_DIRTY_DOWN;
-    uintptr_t addr = (uintptr_t)(A.flag + s);
-    atomicAnd((unsigned *)(addr & ~(uintptr_t)3), ~(bit << (8 * (addr & 3))));
-}
-__global__ void k_bnd_reset(const __grid_constant__ P p)
-{
-    if (threadIdx.x < 2) p.bnd_n[threadIdx.x] = 0;
+    if (threadIdx.x == 0) buf[0] = (double)cnt;
+    for (int j = threadIdx.x; j < cnt; j += blockDim.x) {
+        int s = p.bnd_dirty[dir][j];
+        double *r = buf + (size_t)(1 + j) * AMC_REC;
+        r[0] = A.x[s]; r[1] = A.y[s]; r[2] = A.z[s]; r[3] = A.vx[s]; r[4] = A.vy[s]; r[5] = A.vz[s];
+        r[6] = A.d[s]; r[7] = A.dx[s]; r[8] = A.dy[s]; r[9] = A.dz[s]; r[10] = (double)A.id[s];
+        r[11] = (double)(A.flag[s] & AMC_FLAG_PATH);
+        // clear this direction's "queued" bit (32-bit atomic on the word that holds the flag byte)
+        unsigned bit = dir == 0 ? AMC_FLAG_DIRTY_UP : AMC_FLAG_DIRTY_DOWN;
+        uintptr_t addr = (uintptr_t)(A.flag + s);
+        atomicAnd((unsigned *)(addr & ~(uintptr_t)3), ~(bit << (8 * (addr & 3))));
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) p.bnd_n[dir] = 0;
 }
 
 // apply the update records received from one neighbour (dir 0: from the rank above, 1: from below).
 // One CTA per record: find the particle by id among the related particles, or append it as a new
 // foreign copy; then make sure the later colour groups of this pass can find it (escaped list).
-__global__ void __launch_bounds__(128) k_bnd_apply(const __grid_constant__ P p, const int dir)
+__global__ void __launch_bounds__(128) k_bnd_apply(const __grid_constant__ P p)
 {
     __shared__ int s_slot, s_esc;
+    const int dir = blockIdx.y;
+    if (dir == 0 ? p.srank + 1 >= p.nranks : p.srank == 0) return; /* no neighbour on that side */
     const double *buf = p.bnd_recv[dir];
     int cnt = (int)buf[0];
     for (int j = blockIdx.x; j < cnt; j += gridDim.x) {

@@ -50,7 +50,7 @@ def owner_layer(z, edges):
     return np.clip(k, 0, len(edges) - 2)
 
 
-def balanced_cuts(z, edges, nranks, min_layers=2):
+def balanced_cuts(z, edges, nranks, min_layers=2, prefer_odd=True):
     """Cut indices (nranks+1) on z-cell boundaries with ~equal particle counts per slab."""
     ncz = len(edges) - 1
     if nranks * min_layers > ncz:
@@ -63,6 +63,14 @@ def balanced_cuts(z, edges, nranks, min_layers=2):
         k = int(np.searchsorted(cum, target))
         k = max(k, cuts[-1] + min_layers)
         k = min(k, ncz - (nranks - r) * min_layers)
+        # prefer odd cuts: the cells just above an odd cut belong to the odd z colour groups, so a ghost
+        # that has to be exported late (an immigrant that lands in the band below the cut) is only needed
+        # from group 1 on and can travel with the hand-over after group 0 -- no extra round before it
+        if k % 2 == 0 and prefer_odd:
+            if k + 1 <= ncz - (nranks - r) * min_layers:
+                k += 1
+            elif k - 1 >= cuts[-1] + min_layers:
+                k -= 1
         cuts.append(k)
     cuts.append(ncz)
     return np.array(cuts, dtype=np.int32)
@@ -232,6 +240,8 @@ class SlabSimulation:
                                seed=seed, kind=kind, taps=taps, cheb=cheb)
                       for i, r in enumerate(self.local_ranks)]
         self.n_global = 0
+        # the hand-over round before the first colour group is only needed if some cut is even
+        self.pre_round = any(int(c) % 2 == 0 for c in self.cuts[1:-1])
         self.phase_ms = None        # set by step(timing=True): [advect, exchange+sort, pair groups+hand-over, finish]
         self.debug_counts = False   # True: tally exchanged records per step (host sync; tests only)
         self.exchanged = {"xfer": 0, "boundary": 0}
@@ -295,11 +305,12 @@ class SlabSimulation:
                 r.call("amc_slab_sort", None)
             mark()
             for r in R:
-                r.call("amc_slab_pairs_begin")
-            self._tally("boundary")
-            T.neighbors(R)
-            for r in R:
-                r.call("amc_slab_apply", C.c_int32(-1))
+                r.call("amc_slab_pairs_begin", C.c_int32(int(self.pre_round)))
+            if self.pre_round:
+                self._tally("boundary")
+                T.neighbors(R)
+                for r in R:
+                    r.call("amc_slab_apply", C.c_int32(-1))
             for g in range(8):
                 for r in R:
                     r.call("amc_slab_group", C.c_int32(g))

@@ -195,7 +195,7 @@ int amc_last_timing(amc_handle *h, double ms[5], int64_t *launches);
  * ranks (NCCL all-to-all / neighbour send-recv) between the calls below.  Record = 12 doubles
  * (10 state values, particle id, flag bits); every buffer starts with one header record (count).
  *   per step:  amc_slab_advect -> [all-to-all xfer_send -> xfer_recv] -> amc_slab_sort
- *              -> amc_slab_pairs_begin -> [neighbour exchange] -> amc_slab_apply(-1)
+ *              -> amc_slab_pairs_begin(pre_round) -> if pre_round: [neighbour exchange] -> amc_slab_apply(-1)
  *              -> for g in 0..7: amc_slab_group(g) -> [neighbour exchange] -> amc_slab_apply(g)
  *              -> amc_slab_finish */
 typedef struct amc_slab_config {
@@ -216,7 +216,7 @@ int amc_set_stream(amc_handle *h, void *cuda_stream);   /* run on the caller's s
 int amc_set_ids(amc_handle *h, const int64_t *ids);     /* global particle indices of the state set by amc_set_state */
 int amc_slab_advect(amc_handle *h);
 int amc_slab_sort(amc_handle *h, int64_t *n_resident);
-int amc_slab_pairs_begin(amc_handle *h);
+int amc_slab_pairs_begin(amc_handle *h, int32_t pre_round); /* pre_round != 0: pack the late exports now (needed when a cut is even) */
 int amc_slab_group(amc_handle *h, int32_t group);
 int amc_slab_apply(amc_handle *h, int32_t group_done);
 int amc_slab_finish(amc_handle *h, amc_step_stats *stats);

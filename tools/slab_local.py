@@ -36,7 +36,7 @@ for it in range(3):
     for i, r in enumerate(R): acc[i, 0] += timed(lambda: r.call("amc_slab_advect"))
     T.alltoall(R)
     for i, r in enumerate(R): acc[i, 1] += timed(lambda: r.call("amc_slab_sort", None))
-    for i, r in enumerate(R): acc[i, 2] += timed(lambda: r.call("amc_slab_pairs_begin"))
+    for i, r in enumerate(R): acc[i, 2] += timed(lambda: r.call("amc_slab_pairs_begin", C.c_int32(1)))
     T.neighbors(R)
     for i, r in enumerate(R): acc[i, 3] += timed(lambda: r.call("amc_slab_apply", C.c_int32(-1)))
     for g in range(8):
