@@ -789,7 +789,12 @@ extern "C" int amc_slab_enable(amc_handle *h, const amc_slab_config *c)
     p.xf_send = (double *)c->xfer_send; p.xf_recv = (const double *)c->xfer_recv;
     p.bnd_send[0] = (double *)c->bnd_send_up; p.bnd_send[1] = (double *)c->bnd_send_down;
     p.bnd_recv[0] = (const double *)c->bnd_recv_up; p.bnd_recv[1] = (const double *)c->bnd_recv_down;
-    p.rel_cap = (int32_t)std::min<int64_t>(std::max<int64_t>(h->cap / 8, 1 << 16), 1 << 24);
+    {
+        int64_t want = std::min<int64_t>(std::max<int64_t>(h->cap / 4, 1 << 16), 1 << 25);
+        int32_t pow2 = 1 << 16;
+        while (pow2 < want) pow2 <<= 1;
+        p.rel_cap = pow2;
+    }
     p.foreign_cap = std::max(c->bnd_capacity * 16, 4096);
     ALLOC(h->d_counters, c->nranks + 8);
     CK(cudaMemset(h->d_counters, 0, (c->nranks + 8) * sizeof(int32_t)));
@@ -832,6 +837,7 @@ extern "C" int amc_slab_advect(amc_handle *h)
     p.step = h->step_index++;
     CK(cudaMemsetAsync(h->d_stats, 0, sizeof(StatsDev), h->stream));
     CK(cudaMemsetAsync(h->d_counters, 0, (p.nranks + 8) * sizeof(int32_t), h->stream));
+    CK(cudaMemsetAsync(p.rel_id, 0xff, (size_t)p.rel_cap * sizeof(int32_t), h->stream));
     CK(cudaMemsetAsync(p.band_count, 0, (h->n_buckets + 1) * sizeof(int32_t), h->stream));
     CK(cudaMemsetAsync(p.rest_count, 0, (h->n_buckets + 1) * sizeof(int32_t), h->stream));
     int phase = PH_DRIFT | PH_WALLS | (p.kind != AMC_KIND_CUBE ? PH_RECAP : 0) | PH_KEYS;

@@ -105,8 +105,8 @@ struct P {
     int32_t bnd_cap;
     double *bnd_send[2];
     const double *bnd_recv[2];
-    int32_t *rel_id, *rel_slot, *rel_count; /* particles a neighbour may send updates for: id -> slot */
-    int32_t rel_cap;
+    int32_t *rel_id, *rel_slot, *rel_count; /* open-addressing hash: particles a neighbour may send updates for, id -> slot */
+    int32_t rel_cap;          /* power of two; rel_id[] == -1: empty */
     int32_t *skey;            /* owner key each slot was sorted into (-1: appended foreign copy) */
     int32_t *n_foreign;       /* foreign copies appended after the sort */
     int32_t foreign_cap;
@@ -554,4 +554,27 @@ __device__ __forceinline__ void write_work_item(const P &p, int32_t *w, int cell
     d[0] = p.lo[0][kx]; d[1] = p.edge[0][kx + 1];
     d[2] = p.lo[1][ky]; d[3] = p.edge[1][ky + 1];
     d[4] = p.lo[2][kz]; d[5] = p.edge[2][kz + 1];
+}
+
+// relation table of the slab decomposition: id -> slot, open addressing with linear probing
+__device__ __forceinline__ uint32_t rel_hash(int32_t id) { return (uint32_t)id * 2654435761u; }
+__device__ __forceinline__ void rel_insert(const P &p, int32_t id, int32_t slot)
+{
+    if (atomicAdd(p.rel_count, 1) >= p.rel_cap / 2) { atomicAdd(p.slab_overflow + 1, 1ull); return; }
+    uint32_t mask = (uint32_t)p.rel_cap - 1, h = rel_hash(id) & mask;
+    while (true) {
+        int32_t prev = atomicCAS(&p.rel_id[h], -1, id);
+        if (prev == -1 || prev == id) { p.rel_slot[h] = slot; return; }
+        h = (h + 1) & mask;
+    }
+}
+__device__ __forceinline__ int32_t rel_find(const P &p, int32_t id)
+{
+    uint32_t mask = (uint32_t)p.rel_cap - 1, h = rel_hash(id) & mask;
+    while (true) {
+        int32_t k = p.rel_id[h];
+        if (k == id) return p.rel_slot[h];
+        if (k == -1) return -1;
+        h = (h + 1) & mask;
+    }
 }

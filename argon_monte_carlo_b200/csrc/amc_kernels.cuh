@@ -226,8 +226,7 @@ __global__ void __launch_bounds__(ADVECT_THREADS) k_scatter(const __grid_constan
     if (p.slab) {
         p.skey[t] = k;
         if (k <= p.ncell_pad && (fl & (AMC_FLAG_GHOST | AMC_FLAG_REL_UP | AMC_FLAG_REL_DOWN))) {
-            int j = atomicAdd(p.rel_count, 1);
-            if (j < p.rel_cap) { p.rel_id[j] = id; p.rel_slot[j] = (int32_t)t; } else atomicAdd(p.slab_overflow + 1, 1ull);
+            rel_insert(p, id, (int32_t)t);
         }
         if (k <= p.ncell_pad && (fl & AMC_FLAG_LATE_UP)) {
             int j = atomicAdd(&p.bnd_n[0], 1);
@@ -399,8 +398,7 @@ __device__ __noinline__ void resolve_pair(const P &p, CellShared &S, int m1, int
             bool up = (f & AMC_FLAG_REL_UP) || z > p.up_thr, down = (f & AMC_FLAG_REL_DOWN) || z < p.down_thr;
             if ((up && !(f & AMC_FLAG_REL_UP)) || (down && !(f & AMC_FLAG_REL_DOWN))) {
                 if (!(f & (AMC_FLAG_REL_UP | AMC_FLAG_REL_DOWN | AMC_FLAG_GHOST))) {
-                    int j = atomicAdd(p.rel_count, 1);
-                    if (j < p.rel_cap) { p.rel_id[j] = S.id[w ? m2 : m1]; p.rel_slot[j] = s; } else atomicAdd(p.slab_overflow + 1, 1ull);
+                    rel_insert(p, S.id[w ? m2 : m1], s);
                 }
                 f |= (up ? AMC_FLAG_REL_UP : 0u) | (down ? AMC_FLAG_REL_DOWN : 0u);
             }
@@ -899,9 +897,7 @@ __global__ void __launch_bounds__(128) k_bnd_apply(const __grid_constant__ P p)
     const int tid = threadIdx.x;
     if (tid == 0) { s_slot = -1; s_esc = -1; }
     __syncthreads();
-    int nrel = min(*p.rel_count, p.rel_cap);
-    for (int k = tid; k < nrel; k += blockDim.x)
-        if (p.rel_id[k] == id) s_slot = p.rel_slot[k];
+    if (tid == 0) s_slot = rel_find(p, id);
     __syncthreads();
     const Arrays &A = p.a;
     if (tid == 0 && s_slot < 0) { // unknown here: a particle the neighbour moved into this rank's reach
@@ -913,8 +909,7 @@ __global__ void __launch_bounds__(128) k_bnd_apply(const __grid_constant__ P p)
             A.id[s] = id;
             A.flag[s] = (uint8_t)(AMC_FLAG_GHOST | (dir == 0 ? AMC_FLAG_REL_UP : AMC_FLAG_REL_DOWN));
             p.skey[s] = -1;
-            int k = atomicAdd(p.rel_count, 1);
-            if (k < p.rel_cap) { p.rel_id[k] = id; p.rel_slot[k] = s; } else atomicAdd(p.slab_overflow + 1, 1ull);
+            rel_insert(p, id, s);
         }
     }
     __syncthreads();

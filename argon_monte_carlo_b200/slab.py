@@ -156,9 +156,10 @@ class DistTransport:
         self.dist, self.group = dist, group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         import os
-        # neighbour hand-over as one all_to_all_single (about half the launch latency of a batch of four
-        # send/recv on NCCL) unless AMC_SLAB_P2P=1
-        self.nbr_a2a = dist.get_backend(group) == "nccl" and os.environ.get("AMC_SLAB_P2P", "0") != "1"
+        # neighbour hand-over: batched send/recv with the two neighbours (default; couples only adjacent
+        # ranks) or, with AMC_SLAB_A2A=1, one all_to_all_single (half the launch latency, but a global
+        # synchronisation point per round; measured slightly slower at 8 GPUs)
+        self.nbr_a2a = dist.get_backend(group) == "nccl" and os.environ.get("AMC_SLAB_A2A", "0") == "1"
         self.native_a2a = dist.get_backend(group) == "nccl"
 
     def alltoall(self, ranks):

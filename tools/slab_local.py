@@ -32,6 +32,7 @@ def timed(fn):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); fn(); e1.record(); torch.cuda.synchronize(); return e0.elapsed_time(e1)
 acc = np.zeros((nranks, 5))
+grp = np.zeros((nranks, 8))
 for it in range(3):
     for i, r in enumerate(R): acc[i, 0] += timed(lambda: r.call("amc_slab_advect"))
     T.alltoall(R)
@@ -40,7 +41,9 @@ for it in range(3):
     T.neighbors(R)
     for i, r in enumerate(R): acc[i, 3] += timed(lambda: r.call("amc_slab_apply", C.c_int32(-1)))
     for g in range(8):
-        for i, r in enumerate(R): acc[i, 2] += timed(lambda: r.call("amc_slab_group", C.c_int32(g)))
+        for i, r in enumerate(R):
+            t = timed(lambda: r.call("amc_slab_group", C.c_int32(g)))
+            acc[i, 2] += t; grp[i, g] += t
         T.neighbors(R)
         for i, r in enumerate(R): acc[i, 3] += timed(lambda: r.call("amc_slab_apply", C.c_int32(g)))
     for i, r in enumerate(R):
@@ -51,3 +54,7 @@ print("per rank ms/step: advect, sort, pairs(begin+8 groups+pack), apply(9 round
 for i in range(nranks):
     print(i, np.round(acc[i] / 3, 3), sim.particles_per_rank()[i])
 sim.close()
+
+print("per rank x colour group: pair kernel + pack (ms)")
+print(np.round(grp / 3, 3))
+print("sum over groups of the slowest rank: %.3f ms; slowest rank's own sum: %.3f ms" % ((grp / 3).max(axis=0).sum(), (grp / 3).sum(axis=1).max()))
