@@ -17,6 +17,7 @@ struct amc_handle {
     cudaStream_t stream = nullptr;
     bool own_stream = true;
     bool slab = false;
+    int32_t xf_total = 0;
     int32_t *d_counters = nullptr; // slab mode: xf_count[nranks], n_in, bnd_n[2], rel_count, n_foreign, compact count
     unsigned long long *d_slab_overflow = nullptr;
     P p;                        // kernel parameter block (device pointers)
@@ -785,7 +786,22 @@ extern "C" int amc_slab_enable(amc_handle *h, const amc_slab_config *c)
     p.up_thr = c->rank + 1 < c->nranks ? c->gz_lo[c->cuts[c->rank + 1]] : INFINITY;
     p.down_thr = c->rank > 0 ? c->gz_edge[c->cuts[c->rank]] : -INFINITY;
     p.down_band = c->rank > 0 ? c->gz_lo[c->cuts[c->rank]] : INFINITY;
-    p.xf_cap = c->xfer_capacity; p.bnd_cap = c->bnd_capacity;
+    p.xf_cap = std::max(c->xfer_capacity, c->xfer_capacity_far); p.bnd_cap = c->bnd_capacity;
+    {
+        std::vector<int32_t> off(c->nranks), capv(c->nranks);
+        int32_t o = 0;
+        for (int d = 0; d < c->nranks; d++) {
+            capv[d] = std::abs(d - c->rank) == 1 ? c->xfer_capacity : c->xfer_capacity_far;
+            off[d] = o;
+            o += capv[d] + 1;
+        }
+        int32_t *doff = nullptr, *dcap = nullptr;
+        ALLOC(doff, c->nranks); ALLOC(dcap, c->nranks);
+        CK(cudaMemcpy(doff, off.data(), c->nranks * sizeof(int32_t), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(dcap, capv.data(), c->nranks * sizeof(int32_t), cudaMemcpyHostToDevice));
+        p.xf_off = doff; p.xf_capv = dcap;
+        h->xf_total = o;
+    }
     p.xf_send = (double *)c->xfer_send; p.xf_recv = (const double *)c->xfer_recv;
     p.bnd_send[0] = (double *)c->bnd_send_up; p.bnd_send[1] = (double *)c->bnd_send_down;
     p.bnd_recv[0] = (const double *)c->bnd_recv_up; p.bnd_recv[1] = (const double *)c->bnd_recv_down;
@@ -852,7 +868,7 @@ extern "C" int amc_slab_sort(amc_handle *h, int64_t *n_resident)
     int rc = slab_check(h);
     if (rc != AMC_OK) return rc;
     P &p = h->p;
-    int64_t bound = h->n + (int64_t)p.nranks * p.xf_cap;
+    int64_t bound = h->n + (int64_t)h->xf_total;
     if (bound > h->cap) bound = h->cap;
     dim3 ug(grid_for(p.xf_cap, ADVECT_THREADS), p.nranks);
     k_xfer_unpack<<<ug, ADVECT_THREADS, 0, h->stream>>>(p);

@@ -95,10 +95,11 @@ struct P {
     double g_e0z, g_inv_dz;
     double up_thr, down_thr;  /* lo_global[Z_{r+1}] (+inf on the last rank), edge_global[Z_r] (-inf on rank 0) */
     double down_band;         /* lo_global[Z_r]: above it a particle of the rank below is a band member of this rank's cells */
-    double *xf_send;          /* [nranks][xf_cap+1] records, record 0 = header (count) */
+    double *xf_send;          /* per peer d: records [xf_off[d], xf_off[d] + xf_capv[d]], the first one = header (count) */
     const double *xf_recv;
     int32_t *xf_count;        /* [nranks] */
-    int32_t xf_cap;
+    int32_t xf_cap;           /* largest per-peer capacity */
+    const int32_t *xf_off, *xf_capv; /* [nranks] record offset / capacity of each peer's block (same layout for send and recv) */
     int32_t *n_in;            /* particles unpacked from xf_recv in this step */
     int32_t *bnd_dirty[2];    /* [0] = up, [1] = down: slots moved in the current group that the neighbour must see */
     int32_t *bnd_n;           /* [2] */

@@ -111,8 +111,8 @@ __global__ void __launch_bounds__(ADVECT_THREADS, 4) k_advect(const __grid_const
         if (dest != p.srank || ghost_up) {
             int to = dest != p.srank ? dest : p.srank + 1;
             int j = atomicAdd(&p.xf_count[to], 1);
-            if (j < p.xf_cap) {
-                double *r = p.xf_send + ((size_t)to * (p.xf_cap + 1) + 1 + j) * AMC_REC;
+            if (j < p.xf_capv[to]) {
+                double *r = p.xf_send + ((size_t)p.xf_off[to] + 1 + j) * AMC_REC;
                 r[0] = q.x; r[1] = q.y; r[2] = q.z; r[3] = q.vx; r[4] = q.vy; r[5] = q.vz;
                 r[6] = q.d; r[7] = q.dx; r[8] = q.dy; r[9] = q.dz; r[10] = (double)id;
                 unsigned rf = q.flag & AMC_FLAG_PATH;
@@ -827,7 +827,7 @@ __global__ void k_xfer_headers(const __grid_constant__ P p)
     int d = threadIdx.x;
     if (d < p.nranks) {
         int c = p.xf_count[d];
-        p.xf_send[(size_t)d * (p.xf_cap + 1) * AMC_REC] = (double)(c < p.xf_cap ? c : p.xf_cap);
+        p.xf_send[(size_t)p.xf_off[d] * AMC_REC] = (double)(c < p.xf_capv[d] ? c : p.xf_capv[d]);
     }
 }
 
@@ -836,7 +836,7 @@ __global__ void k_xfer_headers(const __grid_constant__ P p)
 __global__ void __launch_bounds__(ADVECT_THREADS) k_xfer_unpack(const __grid_constant__ P p)
 {
     int src = blockIdx.y;
-    const double *blk = p.xf_recv + (size_t)src * (p.xf_cap + 1) * AMC_REC;
+    const double *blk = p.xf_recv + (size_t)p.xf_off[src] * AMC_REC;
     int cnt = (int)blk[0];
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= cnt) return;

@@ -39,7 +39,7 @@ REC = 12  # doubles per exchanged record
 class AmcSlabConfig(C.Structure):
     _fields_ = [("rank", C.c_int32), ("nranks", C.c_int32), ("cuts", C.POINTER(C.c_int32)), ("gncz", C.c_int32),
                 ("gz_edge", amc.c_double_p), ("gz_lo", amc.c_double_p), ("xfer_capacity", C.c_int32),
-                ("bnd_capacity", C.c_int32), ("xfer_send", C.c_void_p), ("xfer_recv", C.c_void_p),
+                ("xfer_capacity_far", C.c_int32), ("bnd_capacity", C.c_int32), ("xfer_send", C.c_void_p), ("xfer_recv", C.c_void_p),
                 ("bnd_send_up", C.c_void_p), ("bnd_send_down", C.c_void_p), ("bnd_recv_up", C.c_void_p),
                 ("bnd_recv_down", C.c_void_p)]
 
@@ -87,7 +87,7 @@ class SlabRank:
     """One rank: a libamc handle restricted to its z layers plus its exchange buffers (torch tensors)."""
 
     def __init__(self, cfg, rank, cuts, device, xfer_capacity, bnd_capacity, max_particles, seed=None, kind=None,
-                 taps=0, cheb=None):
+                 taps=0, cheb=None, xfer_capacity_far=512):
         import torch
         self.rank, self.nranks, self.cuts = rank, len(cuts) - 1, cuts
         self.device = device
@@ -97,7 +97,11 @@ class SlabRank:
         dev = torch.device("cuda", device)
         with torch.cuda.device(dev):
             z = lambda *s: torch.zeros(*s, dtype=torch.float64, device=dev)
-            self.xfer_send, self.xfer_recv = z(self.nranks, xfer_capacity + 1, REC), z(self.nranks, xfer_capacity + 1, REC)
+            # one block per peer: large for the two neighbours (migrants + ghost copies), small for the rest
+            caps = [xfer_capacity if abs(d - rank) == 1 else xfer_capacity_far for d in range(self.nranks)]
+            self.xfer_splits = [(c + 1) * REC for c in caps]
+            self.xfer_offsets = np.concatenate([[0], np.cumsum(self.xfer_splits)]).astype(np.int64)
+            self.xfer_send, self.xfer_recv = z(int(self.xfer_offsets[-1])), z(int(self.xfer_offsets[-1]))
             # boundary buffers live inside one [nranks, ...] tensor per direction of travel so that the
             # hand-over can also be done with a single all_to_all_single (block r = traffic with rank r)
             self.bnd_send_all, self.bnd_recv_all = z(self.nranks, bnd_capacity + 1, REC), z(self.nranks, bnd_capacity + 1, REC)
@@ -115,7 +119,7 @@ class SlabRank:
         self._lo = np.ascontiguousarray(g.lo[2], dtype=np.float64)
         c.cuts = self._cuts.ctypes.data_as(C.POINTER(C.c_int32))
         c.gncz, c.gz_edge, c.gz_lo = g.nc[2], amc._dp(self._edge), amc._dp(self._lo)
-        c.xfer_capacity, c.bnd_capacity = xfer_capacity, bnd_capacity
+        c.xfer_capacity, c.xfer_capacity_far, c.bnd_capacity = xfer_capacity, xfer_capacity_far, bnd_capacity
         c.xfer_send, c.xfer_recv = self.xfer_send.data_ptr(), self.xfer_recv.data_ptr()
         c.bnd_send_up, c.bnd_send_down = self.bnd_send_up.data_ptr(), self.bnd_send_down.data_ptr()
         c.bnd_recv_up, c.bnd_recv_down = self.bnd_recv_up.data_ptr(), self.bnd_recv_down.data_ptr()
@@ -126,6 +130,9 @@ class SlabRank:
     def call(self, name, *args):
         self.sim._check(getattr(self.sim.lib, name)(self.sim.h, *args), name)
 
+    def xfer_block(self, buf, peer):
+        return buf[int(self.xfer_offsets[peer]):int(self.xfer_offsets[peer + 1])]
+
 
 class LocalTransport:
     """All ranks live in this process (possibly on one GPU): exchanges are device copies."""
@@ -133,7 +140,7 @@ class LocalTransport:
     def alltoall(self, ranks):
         for dst in ranks:
             for src in ranks:
-                dst.xfer_recv[src.rank].copy_(src.xfer_send[dst.rank], non_blocking=True)
+                dst.xfer_block(dst.xfer_recv, src.rank).copy_(src.xfer_block(src.xfer_send, dst.rank), non_blocking=True)
 
     def neighbors(self, ranks):
         by_rank = {r.rank: r for r in ranks}
@@ -164,16 +171,17 @@ class DistTransport:
 
     def alltoall(self, ranks):
         (r,) = ranks
-        if self.native_a2a:
-            self.dist.all_to_all_single(r.xfer_recv, r.xfer_send, group=self.group)
+        if self.native_a2a:   # block sizes are symmetric (|src - dst| decides), so send and receive splits coincide
+            self.dist.all_to_all_single(r.xfer_recv, r.xfer_send, output_split_sizes=r.xfer_splits,
+                                        input_split_sizes=r.xfer_splits, group=self.group)
             return
         ops = []
         for peer in range(self.world):
             if peer == self.rank:
-                r.xfer_recv[peer].copy_(r.xfer_send[peer])
+                r.xfer_block(r.xfer_recv, peer).copy_(r.xfer_block(r.xfer_send, peer))
                 continue
-            ops.append(self.dist.P2POp(self.dist.isend, r.xfer_send[peer], peer, self.group))
-            ops.append(self.dist.P2POp(self.dist.irecv, r.xfer_recv[peer], peer, self.group))
+            ops.append(self.dist.P2POp(self.dist.isend, r.xfer_block(r.xfer_send, peer), peer, self.group))
+            ops.append(self.dist.P2POp(self.dist.irecv, r.xfer_block(r.xfer_recv, peer), peer, self.group))
         for req in (self.dist.batch_isend_irecv(ops) if ops else []):
             req.wait()
 
@@ -237,7 +245,7 @@ class SlabSimulation:
             cheb = gap_energy_chebyshev(cfg, 16)
         devices = devices or [0] * len(self.local_ranks)
         self.ranks = [SlabRank(cfg, r, self.cuts, devices[i], xfer_capacity, bnd_capacity,
-                               int(per_rank[r] * slack) + nranks * xfer_capacity + 16 * bnd_capacity + 4096,
+                               int(per_rank[r] * slack) + 2 * xfer_capacity + nranks * 512 + 16 * bnd_capacity + 4096,
                                seed=seed, kind=kind, taps=taps, cheb=cheb)
                       for i, r in enumerate(self.local_ranks)]
         self.n_global = 0
@@ -251,7 +259,7 @@ class SlabSimulation:
         if self.debug_counts:
             for r in self.ranks:
                 if kind == "xfer":
-                    self.exchanged["xfer"] += int(r.xfer_send[:, 0, 0].sum().item())
+                    self.exchanged["xfer"] += int(sum(r.xfer_send[int(o)].item() for o in r.xfer_offsets[:-1]))
                 else:
                     self.exchanged["boundary"] += int(r.bnd_send_up[0, 0].item()) + int(r.bnd_send_down[0, 0].item())
 

@@ -204,9 +204,11 @@ typedef struct amc_slab_config {
     int32_t gncz;            /* global number of cells in z */
     const double *gz_edge;   /* global z edges, gncz+1 */
     const double *gz_lo;     /* global z low-side bounds, gncz */
-    int32_t xfer_capacity;   /* records per destination rank */
+    int32_t xfer_capacity;   /* records per neighbouring rank (rank +-1): migrants and ghost copies */
+    int32_t xfer_capacity_far; /* records per non-neighbouring rank (teleports across several slabs: rare) */
     int32_t bnd_capacity;    /* records per neighbour and colour group */
-    void *xfer_send, *xfer_recv;                 /* nranks * (xfer_capacity+1) * 96 bytes each */
+    void *xfer_send, *xfer_recv;                 /* sum over peers of (capacity+1) * 96 bytes each; block of peer d starts at
+                                                    record sum_{e<d} (capacity_e + 1), capacity_e = xfer_capacity if |e-rank|==1 else _far */
     void *bnd_send_up, *bnd_send_down;           /* (bnd_capacity+1) * 96 bytes each */
     void *bnd_recv_up, *bnd_recv_down;           /* received from the rank above / below */
 } amc_slab_config;

@@ -62,19 +62,23 @@ def _worker(rank, world, port, out):
     from types import SimpleNamespace
     from argon_monte_carlo_b200 import slab
     cap, bcap = 5, 3
-    r = SimpleNamespace(rank=rank,
-                        xfer_send=torch.zeros(world, cap + 1, slab.REC, dtype=torch.float64),
-                        xfer_recv=torch.zeros(world, cap + 1, slab.REC, dtype=torch.float64),
+    caps = [cap if abs(d - rank) == 1 else 2 for d in range(world)]          # big blocks for neighbours only
+    splits = [(c + 1) * slab.REC for c in caps]
+    offsets = np.concatenate([[0], np.cumsum(splits)])
+    r = SimpleNamespace(rank=rank, xfer_splits=splits, xfer_offsets=offsets,
+                        xfer_block=lambda buf, peer: buf[int(offsets[peer]):int(offsets[peer + 1])],
+                        xfer_send=torch.zeros(int(offsets[-1]), dtype=torch.float64),
+                        xfer_recv=torch.zeros(int(offsets[-1]), dtype=torch.float64),
                         bnd_send_all=None, bnd_recv_all=None,
                         bnd_send_up=torch.full((bcap + 1, slab.REC), 100.0 + rank, dtype=torch.float64),
                         bnd_send_down=torch.full((bcap + 1, slab.REC), 200.0 + rank, dtype=torch.float64),
                         bnd_recv_up=torch.zeros(bcap + 1, slab.REC, dtype=torch.float64),
                         bnd_recv_down=torch.zeros(bcap + 1, slab.REC, dtype=torch.float64))
     for dst in range(world):
-        r.xfer_send[dst] = 10 * rank + dst          # block (src -> dst) tagged 10*src + dst
+        r.xfer_block(r.xfer_send, dst)[:] = 10 * rank + dst          # block (src -> dst) tagged 10*src + dst
     T = slab.DistTransport()
     T.alltoall([r])
-    ok = all(bool((r.xfer_recv[src] == 10 * src + rank).all()) for src in range(world))
+    ok = all(bool((r.xfer_block(r.xfer_recv, src) == 10 * src + rank).all()) for src in range(world))
     T.neighbors([r])
     if rank + 1 < world:
         ok &= bool((r.bnd_recv_up == 200.0 + rank + 1).all())     # what the rank above sent down

@@ -12,7 +12,7 @@ _, _, _, zs, _, _, _ = init_state.synthetic_pore_chunk(cfg, 17, 0, 1 << 22)
 cuts = slab.balanced_cuts(zs, cfg.grid.edge[2], nranks)
 print("cuts", cuts, "cells", cfg.grid.nc)
 sim = slab.SlabSimulation(cfg, nranks, zs, cuts=cuts, n_total=cfg.num_molecules, seed=17)
-print("xfer_capacity", sim.ranks[0].xfer_send.shape)
+print("xfer buffer doubles", sim.ranks[0].xfer_send.shape)
 sim.debug_counts = True
 sim.set_state(*state)
 for k in range(steps):
