@@ -87,13 +87,14 @@ class SlabRank:
     """One rank: a libamc handle restricted to its z layers plus its exchange buffers (torch tensors)."""
 
     def __init__(self, cfg, rank, cuts, device, xfer_capacity, bnd_capacity, max_particles, seed=None, kind=None,
-                 taps=0, cheb=None, xfer_capacity_far=512):
+                 taps=0, cheb=None, xfer_capacity_far=512, grid=None):
         import torch
         self.rank, self.nranks, self.cuts = rank, len(cuts) - 1, cuts
         self.device = device
-        g = cfg.grid
-        self.sim = amc.Simulation(cfg, kind=kind, device=device, seed=seed, grid=local_grid(g, cuts[rank], cuts[rank + 1]),
-                                  max_particles=max_particles, taps=taps, cheb=cheb)
+        g = grid or cfg.grid
+        self.sim = amc.Simulation(cfg, kind=kind, pp_mode=amc.PP_GROUPS, device=device, seed=seed,
+                                  grid=local_grid(g, cuts[rank], cuts[rank + 1]), max_particles=max_particles, taps=taps,
+                                  cheb=cheb)
         dev = torch.device("cuda", device)
         with torch.cuda.device(dev):
             z = lambda *s: torch.zeros(*s, dtype=torch.float64, device=dev)
@@ -222,11 +223,14 @@ class SlabSimulation:
     (all of them with LocalTransport, exactly one with DistTransport)."""
 
     def __init__(self, cfg, nranks, z_for_cuts, transport=None, local_ranks=None, devices=None, xfer_capacity=None,
-                 bnd_capacity=2048, slack=1.35, seed=None, kind=None, taps=0, cuts=None, n_total=None):
+                 bnd_capacity=2048, slack=1.35, seed=None, kind=None, taps=0, cuts=None, n_total=None, grid=None):
+        """grid: cell grid to decompose (default cfg.grid); the cube stage passes a colour-group grid here
+        because its own serial sweep cannot be sharded (BASELINE config 4)."""
         self.cfg, self.nranks = cfg, nranks
+        self.grid = grid or cfg.grid
         self.transport = transport or LocalTransport()
         self.local_ranks = list(range(nranks)) if local_ranks is None else list(local_ranks)
-        g = cfg.grid
+        g = self.grid
         self.cuts = balanced_cuts(z_for_cuts, g.edge[2], nranks) if cuts is None else np.asarray(cuts, dtype=np.int32)
         layer = owner_layer(np.asarray(z_for_cuts), g.edge[2])
         # z_for_cuts may be a sample of a larger state of n_total particles
@@ -246,7 +250,7 @@ class SlabSimulation:
         devices = devices or [0] * len(self.local_ranks)
         self.ranks = [SlabRank(cfg, r, self.cuts, devices[i], xfer_capacity, bnd_capacity,
                                int(per_rank[r] * slack) + 2 * xfer_capacity + nranks * 512 + 16 * bnd_capacity + 4096,
-                               seed=seed, kind=kind, taps=taps, cheb=cheb)
+                               seed=seed, kind=kind, taps=taps, cheb=cheb, grid=g)
                       for i, r in enumerate(self.local_ranks)]
         self.n_global = 0
         # the hand-over round before the first colour group is only needed if some cut is even
@@ -268,7 +272,7 @@ class SlabSimulation:
         layer it owns (ids = global indices)."""
         n = len(x)
         self.n_global = n
-        layer = owner_layer(np.asarray(z), self.cfg.grid.edge[2])
+        layer = owner_layer(np.asarray(z), self.grid.edge[2])
         opt = lambda a, m: None if a is None else np.asarray(a)[m]
         for r in self.ranks:
             m = (layer >= self.cuts[r.rank]) & (layer < self.cuts[r.rank + 1])

@@ -94,3 +94,24 @@ def test_long_run_many_handovers():
     compare(single, run_slabs(cfg, init, 30, 4, [0, 1, 2, nz - 1, nz]), len(init[0]))
     print("exchanged records:", run_slabs.last_exchanged)
     assert run_slabs.last_exchanged["boundary"] >= 10
+
+
+def test_cube_geometry_slabs_bit_identical():
+    """BASELINE config 4 at small scale: Maxwellian gas in a cube with specular walls, colour-group pair
+    schedule, slab-decomposed along z -- identical to the single-domain run."""
+    from argon_monte_carlo_b200 import amc, config, init_state, slab
+    cfg = config.cube_config(scale=2.0, n_sub=10)
+    grid = config.Grid(nc=(10, 10, 10), c0=(0, 0, 0), d=(cfg.dx, cfg.dy, cfg.dz), band=(cfg.collision_range,) * 3)
+    n = 200000
+    init = init_state.synthetic_cube_state(cfg, n, seed=4)
+    one = amc.Simulation(cfg, kind=amc.KIND_CUBE, pp_mode=amc.PP_GROUPS, grid=grid, max_particles=n, taps=amc.TAP_PAIRS)
+    one.set_state(*init)
+    stats1 = one.step(5)
+    single = (one.get_state(), stats1, one.pair_list(), one.histograms())
+    one.close()
+    sim = slab.SlabSimulation(cfg, 3, init[2], kind=amc.KIND_CUBE, grid=grid, taps=amc.TAP_PAIRS)
+    sim.set_state(*init)
+    stats2 = sim.step(5)
+    slabs = (sim.get_state(), stats2, sim.pair_list(), sim.histograms(), sim.cuts)
+    sim.close()
+    compare(single, slabs, n)
