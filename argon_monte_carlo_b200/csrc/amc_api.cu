@@ -239,8 +239,9 @@ static int create_impl(amc_handle *h, const amc_config *cfg, int device)
     {
         int64_t per_group = (int64_t)(cfg->nc[0] / 2 + 1) * (cfg->nc[1] / 2 + 1) * (cfg->nc[2] / 2 + 1);
         p.wl_stride = (int32_t)per_group;
-        ALLOC(p.wl, (size_t)per_group * 8 * AMC_WI); ALLOC(p.wl_count, 8); ALLOC(p.cell_active, per_group * 8);
-        CK(cudaMemset(p.wl_count, 0, 8 * sizeof(int32_t)));
+        ALLOC(p.wl, (size_t)per_group * 8 * AMC_WI); ALLOC(p.wl_count, 16); ALLOC(p.cell_active, per_group * 8);
+        p.wl_next = p.wl_count + 8;
+        CK(cudaMemset(p.wl_count, 0, 16 * sizeof(int32_t)));
         CK(cudaMemset(p.cell_active, 0, per_group * 8 * sizeof(int32_t)));
     }
     p.esc_cap = (int32_t)std::min<int64_t>(std::max<int64_t>(h->cap / 64, 4096), 1 << 22);
@@ -369,7 +370,7 @@ static int run_pairs(amc_handle *h, int64_t *launches)
         if (launches) *launches += 1;
     } else {
         k_pp_begin<<<1, 256, 0, h->stream>>>(p);
-        CK(cudaMemsetAsync(p.wl_count, 0, 8 * sizeof(int32_t), h->stream));
+        CK(cudaMemsetAsync(p.wl_count, 0, 16 * sizeof(int32_t), h->stream));
         int ncell = p.nc[0] * p.nc[1] * p.nc[2];
         k_build_worklist<<<grid_for(ncell, ADVECT_THREADS), ADVECT_THREADS, 0, h->stream>>>(p);
         unsigned grid = (unsigned)std::min<int64_t>((int64_t)h->pair_grid, std::max<int64_t>(ncell / 8, 1));
@@ -901,7 +902,7 @@ extern "C" int amc_slab_pairs_begin(amc_handle *h, int32_t pre_round)
     P &p = h->p;
     p.group_done = -1;
     k_pp_begin<<<1, 256, 0, h->stream>>>(p);
-    CK(cudaMemsetAsync(p.wl_count, 0, 8 * sizeof(int32_t), h->stream));
+    CK(cudaMemsetAsync(p.wl_count, 0, 16 * sizeof(int32_t), h->stream));
     int ncell = p.nc[0] * p.nc[1] * p.nc[2];
     k_build_worklist<<<grid_for(ncell, ADVECT_THREADS), ADVECT_THREADS, 0, h->stream>>>(p);
     if (pre_round) k_bnd_pack<<<2, ADVECT_THREADS, 0, h->stream>>>(p); // immigrants that landed in the top band; else they travel after group 0

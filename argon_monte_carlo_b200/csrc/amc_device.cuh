@@ -83,6 +83,7 @@ struct P {
     uint16_t *wall_bits;
     int32_t *wl;          /* [8][wl_stride][AMC_WI] work items: the cells of each colour group that can hold a pair */
     int32_t *wl_count;    /* [8] */
+    int32_t *wl_next;     /* [8] ticket counters of the persistent pair kernel */
     int32_t *cell_active; /* [8][wl_stride] 1 = cell is in its group's worklist */
     int32_t wl_stride;    /* reference cells per colour group */
     int32_t nh[3];        /* reference cells per axis and parity class: (nc+1)/2 */

@@ -610,17 +610,28 @@ __global__ void __launch_bounds__(PAIR_THREADS, 8) k_pairs_group(const __grid_co
     for (int c = tid; c < AMC_XBINS; c += PAIR_THREADS) S.sub_cnt[c] = 0; /* kept zero by the scan */
     // warp 0 fetches a work item with one coalesced 128-byte load and already has the next one in flight
     // while the CTA works on the current cell
-    int next_hdr = 0;
-    if (tid < AMC_WI && (int)blockIdx.x < nwork) next_hdr = wl[(size_t)blockIdx.x * AMC_WI + tid];
-    for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
-        __syncthreads(); /* previous cell fully processed before S is reused */
+    // Work items are handed out dynamically (one atomic per cell on a per-group ticket) so a CTA that
+    // drew cheap cells simply takes more of them; the ticket for the NEXT cell is drawn before the
+    // current one is processed, which keeps its header load in flight.
+    __shared__ int s_w;
+    int next_hdr = 0, next_w = nwork;
+    if (tid < AMC_WI) {
+        if (tid == 0) next_w = atomicAdd(&p.wl_next[group], 1);
+        next_w = __shfl_sync(0xffffffffu, next_w, 0);
+        if (next_w < nwork) next_hdr = wl[(size_t)next_w * AMC_WI + tid];
+        if (tid == 0) s_w = next_w;
+    }
+    __syncthreads();
+    while (s_w < nwork) {
+        __syncthreads(); /* previous cell fully processed before S is reused; everyone has read s_w */
 #ifdef AMC_PHASE_CLOCK
         if (tid == 0) { S.t_last = clock64(); atomicAdd(&g_phase_clk[15], 1ull); }
 #endif
         if (tid < AMC_WI) {
             s_hdr[tid] = next_hdr;
-            int wn = w + gridDim.x;
-            if (wn < nwork) next_hdr = wl[(size_t)wn * AMC_WI + tid];
+            if (tid == 0) next_w = atomicAdd(&p.wl_next[group], 1);
+            next_w = __shfl_sync(0xffffffffu, next_w, 0);
+            if (next_w < nwork) next_hdr = wl[(size_t)next_w * AMC_WI + tid];
             __syncwarp();
             if (tid < 8) {
                 S.rbeg[tid] = s_hdr[4 + tid];
@@ -678,6 +689,9 @@ __global__ void __launch_bounds__(PAIR_THREADS, 8) k_pairs_group(const __grid_co
         }
         if (S.n >= 2) cell_process(p, S, group, cell);
         PHASE_MARK(7); /* resolution loop (cells with candidates) */
+        __syncthreads();
+        if (tid == 0) s_w = next_w;
+        __syncthreads();
     }
     __syncthreads();
     if (tid == 0) { /* one pair of global atomics per CTA instead of per cell */

@@ -3,7 +3,7 @@
 collision-resolved particle-steps/s at 1/2/4/8 B200 + fraction of the HBM roofline).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                  [--workload temp_pore|pore_ref] [--particles-per-gpu M]
+                  [--workload temp_pore|cube] [--particles-per-gpu M]
 
 One "step" = one whole timestep (drift, walls, recapture, cell sort, the 8-colour-group
 particle-particle pass, recapture, MFP / momentum bookkeeping) over all particles of the job.
@@ -100,6 +100,59 @@ def scaled_temp_config(total_particles):
     return cfg, scale
 
 
+def run_cube(args, world, rank, local, dev, barrier, max_over_ranks, sum_over_ranks):
+    """BASELINE config 4: --cube-particles (default 10 M) Maxwellian argon atoms in a cube with specular walls
+    at the reference density, colour-group pair schedule with ~21.4 nm cells, slab-decomposed along z
+    over the GPUs (strong scaling: the total is fixed)."""
+    import torch
+    import torch.distributed as dist
+    from argon_monte_carlo_b200 import amc, config, init_state, slab
+    n = args.cube_particles
+    base = config.cube_config()
+    scale = (n / base.num_molecules) ** (1.0 / 3.0)
+    n_sub = 2 * max(1, int(round(base.cube_x * scale / 21.43e-9 / 2)))
+    cfg = config.cube_config(scale=scale, n_sub=n_sub)
+    cfg.dt = cfg.tau / 1000                                           # SURVEY 8d: dt = tau/1000 for the synthetic configs
+    grid = config.Grid(nc=(n_sub,) * 3, c0=(0, 0, 0), d=(cfg.dx, cfg.dy, cfg.dz), band=(cfg.collision_range,) * 3)
+    state = init_state.synthetic_cube_state(cfg, n, seed=127)
+    if world == 1:
+        sim = amc.Simulation(cfg, kind=amc.KIND_CUBE, pp_mode=amc.PP_GROUPS, grid=grid, max_particles=n, device=local)
+        sim.set_state(*state)
+        sim.step_quiet(args.warmup)
+        barrier()
+        sim.step_quiet(args.steps)
+        ms = sim.last_timing()[0]
+        dev_ms, phases = ms[4], {"advect_walls": ms[0] / args.steps, "cell_sort": ms[1] / args.steps, "pairs": ms[2] / args.steps}
+        sim.close()
+    else:
+        cuts = slab.balanced_cuts(state[2], grid.edge[2], world)
+        layer = slab.owner_layer(state[2], grid.edge[2])
+        m = (layer >= cuts[rank]) & (layer < cuts[rank + 1])
+        sim = slab.SlabSimulation(cfg, world, state[2], transport=slab.DistTransport(), local_ranks=[rank], devices=[local],
+                                  cuts=cuts, kind=amc.KIND_CUBE, grid=grid, seed=127)
+        sim.set_local_state(np.nonzero(m)[0], *[a[m] for a in state], n_global=n)
+        sim.step(args.warmup, reduce=False)
+        barrier()
+        sim.step(args.steps, reduce=False, timing=True)
+        ms = sim.phase_ms
+        barrier()
+        dev_ms = max_over_ranks(float(ms.sum()))
+        phases = {"advect_walls": ms[0] / args.steps, "exchange_sort": ms[1] / args.steps,
+                  "pairs_and_handover": ms[2] / args.steps, "finish": ms[3] / args.steps}
+        sim.close()
+    out = {"metric": "collision-resolved particle-steps/s", "value": n * args.steps / (dev_ms * 1e-3), "unit": "particle-steps/s",
+           "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
+           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": "cube_%dM: Maxwellian argon in a %.0f nm cube, specular walls, colour-group pair schedule, "
+                                  "%d^3 cells, z slabs over %d GPU(s)" % (n // 1000000, cfg.cube_x * 1e9, n_sub, world),
+                      "particles_total": n, "l2": "inputs larger than L2"},
+           "phases_ms_per_step": phases}
+    if rank == 0:
+        emit(out)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -133,6 +186,8 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
+    if args.workload == "cube":
+        return run_cube(args, world, rank, local, dev, barrier, max_over_ranks, sum_over_ranks)
     if world > 1:
         return run_slabs(args, world, rank, local, dev, hbm_peak, peak_src, barrier, max_over_ranks, sum_over_ranks)
 
@@ -403,6 +458,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--particles-per-gpu", type=int, default=12_500_000)
+    ap.add_argument("--workload", default="temp_pore", choices=["temp_pore", "cube"],
+                    help="temp_pore (default, the headline workload) or cube (BASELINE config 4, secondary)")
+    ap.add_argument("--cube-particles", type=int, default=10_000_000)
     ap.add_argument("--no-also", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
