@@ -74,6 +74,7 @@ EXPORTS = ("amc_create", "amc_destroy", "amc_last_error", "amc_abi_version", "am
            "amc_num_particles", "amc_step", "amc_drift", "amc_walls", "amc_recapture", "amc_pairs", "amc_wall_case",
            "amc_wall_hits_pending", "amc_wall_apply_directions", "amc_get_histograms", "amc_get_pair_list",
            "amc_get_wall_bits", "amc_get_completed_paths", "amc_clear_taps", "amc_set_step_index", "amc_last_timing",
+           "amc_last_detect_ms",
            "amc_get_outputs_raw", "amc_set_outputs_raw", "amc_get_step_index",
            "amc_slab_enable", "amc_set_stream", "amc_set_ids", "amc_slab_advect", "amc_slab_sort", "amc_slab_pairs_begin",
            "amc_slab_group", "amc_slab_apply", "amc_slab_finish", "amc_slab_get_owned")
@@ -402,3 +403,9 @@ class Simulation:
         n = C.c_int64(0)
         self._check(self.lib.amc_last_timing(self.h, ms, C.byref(n)), "amc_last_timing")
         return list(ms), int(n.value)
+
+    def last_detect_ms(self):
+        """Device time (ms) of the detection kernel alone, summed over the steps of the last step() call."""
+        v = C.c_double(0.0)
+        self._check(self.lib.amc_last_detect_ms(self.h, C.byref(v)), "amc_last_detect_ms")
+        return float(v.value)

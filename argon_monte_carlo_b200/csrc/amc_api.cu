@@ -31,6 +31,7 @@ struct amc_handle {
     bool have_prior = false;
     int64_t step_index = 0;
     int pair_grid = 148 * 5;    // persistent CTAs of k_pairs_group: SMs x resident CTAs per SM
+    int det_grid = 148 * 4;     // persistent CTAs of k_detect
     // host-RNG parity mode: pending hits of the last amc_wall_hits_pending call
     int32_t *d_pend_count = nullptr, *d_pend_slot = nullptr, *d_pend_id = nullptr;
     double *d_pend_nrm = nullptr, *d_pend_colz = nullptr, *d_pend_dirs = nullptr, *d_pend_se = nullptr, *d_pend_dpz = nullptr, *d_pend_de = nullptr;
@@ -41,6 +42,9 @@ struct amc_handle {
     // timing
     std::vector<cudaEvent_t> events;
     double last_ms[5] = {0, 0, 0, 0, 0};
+    std::vector<cudaEvent_t> det_events; // two per step of the last amc_step chunk: around k_detect
+    int det_slot = -1;                   // step of the chunk run_pairs is recording for (-1: none)
+    double last_detect_ms = 0;
     int64_t last_launches = 0;
     std::string error;
 
@@ -144,6 +148,7 @@ extern "C" int amc_destroy(amc_handle *h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (void *q : h->allocs) cudaFree(q);
     for (cudaEvent_t e : h->events) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->det_events) cudaEventDestroy(e);
     if (h->h_stats) cudaFreeHost(h->h_stats);
     if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -239,10 +244,30 @@ static int create_impl(amc_handle *h, const amc_config *cfg, int device)
     {
         int64_t per_group = (int64_t)(cfg->nc[0] / 2 + 1) * (cfg->nc[1] / 2 + 1) * (cfg->nc[2] / 2 + 1);
         p.wl_stride = (int32_t)per_group;
-        ALLOC(p.wl, (size_t)per_group * 8 * AMC_WI); ALLOC(p.wl_count, 16); ALLOC(p.cell_active, per_group * 8);
+        ALLOC(p.wl, (size_t)per_group * 8 * AMC_WI); ALLOC(p.wl_count, AMC_WL_COUNTERS); ALLOC(p.cell_active, per_group * 8);
         p.wl_next = p.wl_count + 8;
-        CK(cudaMemset(p.wl_count, 0, 16 * sizeof(int32_t)));
+        p.dl_count = p.wl_count + 16;
+        ALLOC(p.dl, (size_t)cfg->nc[0] * cfg->nc[1] * cfg->nc[2] * AMC_WI); ALLOC(p.cell_n, per_group * 8);
+        CK(cudaMemset(p.wl_count, 0, AMC_WL_COUNTERS * sizeof(int32_t)));
         CK(cudaMemset(p.cell_active, 0, per_group * 8 * sizeof(int32_t)));
+        CK(cudaMemset(p.cell_n, 0, per_group * 8 * sizeof(int32_t)));
+        // fp32 filter of the detection pass.  Coordinates relative to the cell's low corner lie in (0, W) and are
+        // rounded to fp32 with an error <= 2^-24 W each; a coordinate difference is then off by e <= 3 * 2^-24 W
+        // (two roundings plus its own), the distance by <= sqrt(3) e, and the fused square sum by a relative
+        // 4 * 2^-24.  Every pair the exact test (Pore:173-174) accepts therefore has an fp32 squared distance
+        // below ((cr + sqrt(3) e)^2) (1 + 2^-21); the factors used here are twice as generous.
+        double wmax = 0.0;
+        p.det_own_is_member = 1;
+        for (int a = 0; a < 3; a++)
+            for (int k = 0; k < cfg->nc[a]; k++) {
+                wmax = std::max(wmax, cfg->edge[a][k + 1] - cfg->lo[a][k]);
+                if (!(cfg->lo[a][k] < cfg->edge[a][k])) p.det_own_is_member = 0;
+            }
+        double e_abs = 6.0 * std::ldexp(wmax, -24);
+        double r_f = std::sqrt(cfg->overlap_sq) * (1.0 + 1e-9) + 2.0 * e_abs;
+        double thr = r_f * r_f * (1.0 + std::ldexp(1.0, -20));
+        p.det_thr = std::nextafterf((float)thr, INFINITY);
+        p.det_w = std::nextafterf((float)(1.05 * std::sqrt((double)p.det_thr)), INFINITY);
     }
     p.esc_cap = (int32_t)std::min<int64_t>(std::max<int64_t>(h->cap / 64, 4096), 1 << 22);
     ALLOC(p.esc_count, 1); ALLOC(p.esc_slot, p.esc_cap); ALLOC(p.esc_cell, (size_t)p.esc_cap * 8);
@@ -265,6 +290,9 @@ static int create_impl(amc_handle *h, const amc_config *cfg, int device)
         CK(cudaFuncSetAttribute(k_pairs_group, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pairs_group, PAIR_THREADS, 0));
         h->pair_grid = std::max(1, sms * std::max(per_sm, 1));
+        CK(cudaFuncSetAttribute(k_detect, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_detect, DET_THREADS, 0));
+        h->det_grid = std::max(1, sms * std::max(per_sm, 1));
     }
     CK(cudaDeviceSynchronize());
     return AMC_OK;
@@ -370,12 +398,17 @@ static int run_pairs(amc_handle *h, int64_t *launches)
         if (launches) *launches += 1;
     } else {
         k_pp_begin<<<1, 256, 0, h->stream>>>(p);
-        CK(cudaMemsetAsync(p.wl_count, 0, 16 * sizeof(int32_t), h->stream));
+        CK(cudaMemsetAsync(p.wl_count, 0, AMC_WL_COUNTERS * sizeof(int32_t), h->stream));
         int ncell = p.nc[0] * p.nc[1] * p.nc[2];
+        CK(cudaMemsetAsync(p.cell_active, 0, (size_t)p.wl_stride * 8 * sizeof(int32_t), h->stream));
+        CK(cudaMemsetAsync(p.cell_n, 0, (size_t)p.wl_stride * 8 * sizeof(int32_t), h->stream));
         k_build_worklist<<<grid_for(ncell, ADVECT_THREADS), ADVECT_THREADS, 0, h->stream>>>(p);
+        if (h->det_slot >= 0) CK(cudaEventRecord(h->det_events[2 * h->det_slot], h->stream));
+        k_detect<<<h->det_grid, DET_THREADS, 0, h->stream>>>(p);
+        if (h->det_slot >= 0) CK(cudaEventRecord(h->det_events[2 * h->det_slot + 1], h->stream));
         unsigned grid = (unsigned)std::min<int64_t>((int64_t)h->pair_grid, std::max<int64_t>(ncell / 8, 1));
         for (int g = 0; g < 8; g++) k_pairs_group<<<grid, PAIR_THREADS, 0, h->stream>>>(p, g);
-        if (launches) *launches += 10;
+        if (launches) *launches += 11;
     }
     CK(cudaGetLastError());
     return AMC_OK;
@@ -402,6 +435,7 @@ extern "C" int amc_step(amc_handle *h, int32_t n_steps, amc_step_stats *stats)
     const bool sweep = p.pp_mode == AMC_PP_SWEEP;
     const bool has_recap = p.kind != AMC_KIND_CUBE;
     memset(h->last_ms, 0, sizeof(h->last_ms));
+    h->last_detect_ms = 0;
     h->last_launches = 0;
     int done = 0;
     if (sweep && h->n) { // the sweep kernel addresses particles by id: keep slot == id
@@ -412,6 +446,11 @@ extern "C" int amc_step(amc_handle *h, int32_t n_steps, amc_step_stats *stats)
         int chunk = std::min(n_steps - done, h->stats_cap);
         int rc = ensure_events(h, (size_t)chunk * 4 + 1);
         if (rc != AMC_OK) return rc;
+        while (h->det_events.size() < (size_t)chunk * 2) {
+            cudaEvent_t e;
+            CK(cudaEventCreate(&e));
+            h->det_events.push_back(e);
+        }
         CK(cudaMemsetAsync(h->d_stats, 0, chunk * sizeof(StatsDev), h->stream));
         CK(cudaEventRecord(h->events[0], h->stream));
         for (int s = 0; s < chunk; s++) {
@@ -431,7 +470,9 @@ extern "C" int amc_step(amc_handle *h, int32_t n_steps, amc_step_stats *stats)
                 CK(cudaEventRecord(h->events[4 * s + 1], h->stream));
                 if (!sweep) { rc = sort_scatter(h, &h->last_launches); if (rc != AMC_OK) return rc; }
                 CK(cudaEventRecord(h->events[4 * s + 2], h->stream));
+                h->det_slot = sweep ? -1 : s;
                 rc = run_pairs(h, &h->last_launches);
+                h->det_slot = -1;
                 if (rc != AMC_OK) return rc;
                 CK(cudaEventRecord(h->events[4 * s + 3], h->stream));
                 if (has_recap && s == chunk - 1) { // last step of the call: close it now
@@ -450,6 +491,10 @@ extern "C" int amc_step(amc_handle *h, int32_t n_steps, amc_step_stats *stats)
                 for (int k = 0; k < 4; k++) {
                     CK(cudaEventElapsedTime(&ms, h->events[4 * s + k], h->events[4 * s + k + 1]));
                     h->last_ms[k] += ms;
+                }
+                if (!sweep) {
+                    CK(cudaEventElapsedTime(&ms, h->det_events[2 * s], h->det_events[2 * s + 1]));
+                    h->last_detect_ms += ms;
                 }
             }
         for (int s = 0; s < chunk; s++) {
@@ -742,6 +787,13 @@ extern "C" int amc_last_timing(amc_handle *h, double ms[5], int64_t *launches)
     return AMC_OK;
 }
 
+extern "C" int amc_last_detect_ms(amc_handle *h, double *ms)
+{
+    if (!h || !ms) return AMC_E_INVALID;
+    *ms = h->last_detect_ms;
+    return AMC_OK;
+}
+
 // ---- slab decomposition (multi-GPU) ---------------------------------------------------------------
 extern "C" int amc_set_stream(amc_handle *h, void *cuda_stream)
 {
@@ -902,9 +954,12 @@ extern "C" int amc_slab_pairs_begin(amc_handle *h, int32_t pre_round)
     P &p = h->p;
     p.group_done = -1;
     k_pp_begin<<<1, 256, 0, h->stream>>>(p);
-    CK(cudaMemsetAsync(p.wl_count, 0, 16 * sizeof(int32_t), h->stream));
+    CK(cudaMemsetAsync(p.wl_count, 0, AMC_WL_COUNTERS * sizeof(int32_t), h->stream));
     int ncell = p.nc[0] * p.nc[1] * p.nc[2];
+    CK(cudaMemsetAsync(p.cell_active, 0, (size_t)p.wl_stride * 8 * sizeof(int32_t), h->stream));
+    CK(cudaMemsetAsync(p.cell_n, 0, (size_t)p.wl_stride * 8 * sizeof(int32_t), h->stream));
     k_build_worklist<<<grid_for(ncell, ADVECT_THREADS), ADVECT_THREADS, 0, h->stream>>>(p);
+    if (h->n) k_detect<<<h->det_grid, DET_THREADS, 0, h->stream>>>(p);
     if (pre_round) k_bnd_pack<<<2, ADVECT_THREADS, 0, h->stream>>>(p); // immigrants that landed in the top band; else they travel after group 0
     CK(cudaGetLastError());
     return AMC_OK;

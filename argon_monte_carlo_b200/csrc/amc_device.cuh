@@ -24,6 +24,7 @@
 #define AMC_MAX_MEMBERS 512  /* particles per reference cell incl. overlap band (reference: <= 308) */
 #define AMC_MAX_CAND 128     /* simultaneously overlapping pairs per cell visit */
 #define AMC_WI 32            /* ints per work item: cell, kx, ky, kz, beg[8], len[8], 6 doubles of bounds = 128 bytes */
+#define AMC_WL_COUNTERS 24 /* wl_count[8], wl_next[8], dl_count, padding */
 #define AMC_XBINS 64         /* slabs along x of the in-CTA neighbour search (multiple of 32) */
 #define AMC_SUB_MIN_N 48     /* below this many members the plain all-pairs scan is cheaper */
 
@@ -84,6 +85,12 @@ struct P {
     int32_t *wl;          /* [8][wl_stride][AMC_WI] work items: the cells of each colour group that can hold a pair */
     int32_t *wl_count;    /* [8] */
     int32_t *wl_next;     /* [8] ticket counters of the persistent pair kernel */
+    int32_t *dl;          /* [cells][AMC_WI] work items of the detection pass: every reference cell with >= 2 candidates */
+    int32_t *dl_count;    /* [1] */
+    int32_t *cell_n;      /* [8][wl_stride] members counted by the detection pass for cells it did not flag (0 otherwise) */
+    float det_thr;        /* fp32 squared distance below which the detection pass treats a pair as overlapping (conservative) */
+    float det_w;          /* minimal bin width of the detection pass: 1.05 * sqrt(det_thr) */
+    int32_t det_own_is_member; /* lo[k] < edge[k] everywhere: a particle of owner cell k is a member of reference cell k */
     int32_t *cell_active; /* [8][wl_stride] 1 = cell is in its group's worklist */
     int32_t wl_stride;    /* reference cells per colour group */
     int32_t nh[3];        /* reference cells per axis and parity class: (nc+1)/2 */

@@ -345,27 +345,67 @@ __device__ __forceinline__ void push_cand(CellShared &S, const P &p, int a, int 
     else atomicAdd(&p.stats->cand_overflow, 1ull);
 }
 
-// elastic exchange of one overlapping pair, executed by one thread (Pore:176-241).
+// elastic exchange of one overlapping pair (Pore:176-241), executed by all 32 lanes of warp 0.
 // m1 = member with the smaller global index (the reference's particle "1" = j), m2 the larger.
+// The arithmetic is evaluated redundantly (and identically) on every lane; what follows it is a set of
+// independent global-memory round trips -- state stores, histogram updates of the completed paths,
+// per-(particle, later colour group) cell activation -- which the lanes issue side by side instead of
+// one thread walking through them: the latency of a collision is what a launch of k_pairs_group waits for.
 __device__ __noinline__ void resolve_pair(const P &p, CellShared &S, int m1, int m2, int group, int cell)
 {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, w = lane & 1; /* even lanes hold particle 1's record, odd lanes particle 2's */
     const Arrays &A = p.a;
-    int s1 = S.slot[m1], s2 = S.slot[m2];
+    const int s1 = S.slot[m1], s2 = S.slot[m2];
+    const int so = w ? s2 : s1, mo = w ? m2 : m1;
+    const double ovx = A.vx[so], ovy = A.vy[so], ovz = A.vz[so], od = A.d[so], odx = A.dx[so], ody = A.dy[so], odz = A.dz[so];
+    uint32_t of = A.flag[so];
+    const double qvx = __shfl_xor_sync(FULL, ovx, 1), qvy = __shfl_xor_sync(FULL, ovy, 1), qvz = __shfl_xor_sync(FULL, ovz, 1);
     double x1 = S.x[m1], y1 = S.y[m1], z1 = S.z[m1], x2 = S.x[m2], y2 = S.y[m2], z2 = S.z[m2];
-    double vx1 = A.vx[s1], vy1 = A.vy[s1], vz1 = A.vz[s1], vx2 = A.vx[s2], vy2 = A.vy[s2], vz2 = A.vz[s2];
+    const double vx1 = w ? qvx : ovx, vy1 = w ? qvy : ovy, vz1 = w ? qvz : ovz;
+    const double vx2 = w ? ovx : qvx, vy2 = w ? ovy : qvy, vz2 = w ? ovz : qvz;
     double ddx = x2 - x1, ddy = y2 - y1, ddz = z2 - z1;
     double rx = -vx2 + vx1, ry = -vy2 + vy1, rz = -vz2 + vz1;
     double a = (rx * rx + ry * ry) + rz * rz;
     double b = 2 * ((ddx * rx + ddy * ry) + ddz * rz);
     double c = ((ddx * ddx + ddy * ddy) + ddz * ddz) - p.cr * p.cr;
     double disc = b * b - (4 * a) * c;
-    if (!(disc >= 0.0) || a == 0.0) { atomicAdd(&p.stats->errors, 1ull); return; }
+    if (!(disc >= 0.0) || a == 0.0) { if (lane == 0) atomicAdd(&p.stats->errors, 1ull); return; }
     double root = sqrt(disc);
     double t1 = (-b + root) / (2 * a), t2 = (-b - root) / (2 * a);
     double t = t1 > t2 ? t1 : t2;
-    uint32_t f1 = A.flag[s1], f2 = A.flag[s2];
-    mfp_record(p, A.d[s1], A.dx[s1], A.dy[s1], A.dz[s1], f1, vx1, vy1, vz1, t);
-    mfp_record(p, A.d[s2], A.dx[s2], A.dy[s2], A.dz[s2], f2, vx2, vy2, vz2, t);
+    // completed free paths (Pore:186-199): lanes 0-3 the four values of particle 1, lanes 4-7 of particle 2
+    {
+        const uint32_t qf = __shfl_xor_sync(FULL, of, 1);
+        const uint32_t f1 = w ? qf : of, f2 = w ? of : qf;
+        const int done1 = (f1 & AMC_FLAG_PATH) != 0, done2 = (f2 & AMC_FLAG_PATH) != 0;
+        // value `which` of the own particle, then routed to the lane that records it
+        double mine[4];
+        mine[0] = fabs(od - fabs(sqrt((ovx * ovx + ovy * ovy) + ovz * ovz) * t));
+        mine[1] = fabs(odx - fabs(ovx * t)); mine[2] = fabs(ody - fabs(ovy * t)); mine[3] = fabs(odz - fabs(ovz * t));
+        double val = 0.0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            double v = __shfl_sync(FULL, mine[k], (lane >> 2) & 1); /* lane 0 holds particle 1, lane 1 particle 2 */
+            if ((lane & 3) == k) val = v;
+        }
+        unsigned long long base = 0;
+        if (p.tap_path_count && lane == 0 && done1 + done2) base = atomicAdd(p.tap_path_count, (unsigned long long)(done1 + done2));
+        base = __shfl_sync(FULL, base, 0);
+        if (lane < 8) {
+            const int pw = lane >> 2, which = lane & 3;
+            if (pw ? done2 : done1) {
+                hist_add(p, which, val);
+                acc_add(p.path_sums + 2 * which, val, SC_L1, SC_L1I, SC_L2);
+                if (which == 0) { atomicAdd(p.path_count, 1ull); atomicAdd(&p.stats->paths, 1ull); }
+                if (p.tap_path_count) {
+                    unsigned long long k = base + (pw ? (unsigned long long)done1 : 0ull);
+                    if ((int64_t)k < p.path_cap) p.tap_paths[which][k] = val;
+                }
+            }
+        }
+        of |= AMC_FLAG_PATH;
+    }
     double nx1 = x1 - vx1 * t, ny1 = y1 - vy1 * t, nz1 = z1 - vz1 * t;
     double nx2 = x2 - vx2 * t, ny2 = y2 - vy2 * t, nz2 = z2 - vz2 * t;
     double n0 = (nx2 - nx1) / p.cr, n1 = (ny2 - ny1) / p.cr, n2 = (nz2 - nz1) / p.cr;
@@ -375,79 +415,81 @@ __device__ __noinline__ void resolve_pair(const P &p, CellShared &S, int m1, int
     double wx2 = vx2 + pm * n0, wy2 = vy2 + pm * n1, wz2 = vz2 + pm * n2;
     x1 = nx1 + wx1 * t; y1 = ny1 + wy1 * t; z1 = nz1 + wz1 * t;
     x2 = nx2 + wx2 * t; y2 = ny2 + wy2 * t; z2 = nz2 + wz2 * t;
-    S.x[m1] = x1; S.y[m1] = y1; S.z[m1] = z1; S.x[m2] = x2; S.y[m2] = y2; S.z[m2] = z2;
-    A.x[s1] = x1; A.y[s1] = y1; A.z[s1] = z1; A.x[s2] = x2; A.y[s2] = y2; A.z[s2] = z2;
-    A.vx[s1] = wx1; A.vy[s1] = wy1; A.vz[s1] = wz1; A.vx[s2] = wx2; A.vy[s2] = wy2; A.vz[s2] = wz2;
-    A.d[s2] = fabs(sqrt((wx2 * wx2 + wy2 * wy2) + wz2 * wz2) * t);
-    A.d[s1] = fabs(sqrt((wx1 * wx1 + wy1 * wy1) + wz1 * wz1) * t);
-    A.dx[s2] = fabs(wx2 * t); A.dy[s2] = fabs(wy2 * t); A.dz[s2] = fabs(wz2 * t);
-    A.dx[s1] = fabs(wx1 * t); A.dy[s1] = fabs(wy1 * t); A.dz[s1] = fabs(wz1 * t);
-    atomicAdd(&p.stats->pp, 1ull);
-    if (p.pair_count) {
-        unsigned long long k = atomicAdd(p.pair_count, 1ull);
-        if ((int64_t)k < p.pair_cap) { p.pair_hi[k] = S.id[m2]; p.pair_lo[k] = S.id[m1]; p.pair_group[k] = group; p.pair_cell[k] = cell; }
+    const double x = w ? x2 : x1, y = w ? y2 : y1, z = w ? z2 : z1; /* the own particle after the collision */
+    if (lane < 2) {
+        const double wx = w ? wx2 : wx1, wy = w ? wy2 : wy1, wz = w ? wz2 : wz1;
+        S.x[mo] = x; S.y[mo] = y; S.z[mo] = z;
+        A.x[so] = x; A.y[so] = y; A.z[so] = z;
+        A.vx[so] = wx; A.vy[so] = wy; A.vz[so] = wz;
+        A.d[so] = fabs(sqrt((wx * wx + wy * wy) + wz * wz) * t);
+        A.dx[so] = fabs(wx * t); A.dy[so] = fabs(wy * t); A.dz[so] = fabs(wz * t);
     }
-    if (p.slab) {
+    if (lane == 0) {
+        atomicAdd(&p.stats->pp, 1ull);
+        if (p.pair_count) {
+            unsigned long long k = atomicAdd(p.pair_count, 1ull);
+            if ((int64_t)k < p.pair_cap) { p.pair_hi[k] = S.id[m2]; p.pair_lo[k] = S.id[m1]; p.pair_group[k] = group; p.pair_cell[k] = cell; }
+        }
+    }
+    if (p.slab && lane < 2) {
         // slab decomposition: a moved particle that a neighbouring rank holds a copy of (or now
         // needs, because it entered the band at a cut / crossed it) is queued for the boundary
         // exchange that follows this colour group
-        for (int w = 0; w < 2; w++) {
-            int s = w ? s2 : s1;
-            double z = w ? z2 : z1;
-            uint32_t &f = w ? f2 : f1;
-            bool up = (f & AMC_FLAG_REL_UP) || z > p.up_thr, down = (f & AMC_FLAG_REL_DOWN) || z < p.down_thr;
-            if ((up && !(f & AMC_FLAG_REL_UP)) || (down && !(f & AMC_FLAG_REL_DOWN))) {
-                if (!(f & (AMC_FLAG_REL_UP | AMC_FLAG_REL_DOWN | AMC_FLAG_GHOST))) {
-                    rel_insert(p, S.id[w ? m2 : m1], s);
-                }
-                f |= (up ? AMC_FLAG_REL_UP : 0u) | (down ? AMC_FLAG_REL_DOWN : 0u);
-            }
-            for (int dir = 0; dir < 2; dir++) {
-                unsigned bit = dir == 0 ? AMC_FLAG_DIRTY_UP : AMC_FLAG_DIRTY_DOWN;
-                if ((dir == 0 ? up : down) && !(f & bit)) { /* once per group and direction */
-                    f |= bit;
-                    int j = atomicAdd(&p.bnd_n[dir], 1);
-                    if (j < p.bnd_cap) p.bnd_dirty[dir][j] = s; else atomicAdd(p.slab_overflow + 2, 1ull);
-                }
+        uint32_t &f = of;
+        bool up = (f & AMC_FLAG_REL_UP) || z > p.up_thr, down = (f & AMC_FLAG_REL_DOWN) || z < p.down_thr;
+        if ((up && !(f & AMC_FLAG_REL_UP)) || (down && !(f & AMC_FLAG_REL_DOWN))) {
+            if (!(f & (AMC_FLAG_REL_UP | AMC_FLAG_REL_DOWN | AMC_FLAG_GHOST))) rel_insert(p, S.id[mo], so);
+            f |= (up ? AMC_FLAG_REL_UP : 0u) | (down ? AMC_FLAG_REL_DOWN : 0u);
+        }
+        for (int dir = 0; dir < 2; dir++) {
+            unsigned bit = dir == 0 ? AMC_FLAG_DIRTY_UP : AMC_FLAG_DIRTY_DOWN;
+            if ((dir == 0 ? up : down) && !(f & bit)) { /* once per group and direction */
+                f |= bit;
+                int j = atomicAdd(&p.bnd_n[dir], 1);
+                if (j < p.bnd_cap) p.bnd_dirty[dir][j] = so; else atomicAdd(p.slab_overflow + 2, 1ull);
             }
         }
     }
     if (p.pp_mode == AMC_PP_GROUPS) {
-        // A moved particle whose owner cell changed can no longer be found through the sorted
-        // layout: publish its member cell for every later colour group in the escaped list.
-        for (int w = 0; w < 2; w++) {
-            int m = w ? m2 : m1, s = w ? s2 : s1;
-            double x = w ? x2 : x1, y = w ? y2 : y1, z = w ? z2 : z1;
-            uint32_t &f = w ? f2 : f1;
-            int o[3];
+        // Every cell of a later colour group that contains a moved particle has to be visited (k_detect
+        // only listed the cells that held an overlapping pair before the pass).  A moved particle whose
+        // owner cell changed can, in addition, no longer be found through the sorted layout: its member
+        // cell for every later group is published in the escaped list.
+        int o[3] = {0, 0, 0}, e = -1, findable = 0, ok = 0;
+        if (lane < 2) {
             int32_t k = owner_key(p, x, y, z, o);
-            int e = S.src[m];
+            e = S.src[mo];
+            ok = 1;
             if (e < 0) { /* found through the sorted layout: src = -1 - (low-side neighbour code) */
                 int nb = -1 - e;
                 int oc = ((S.kx + 1 - (nb >> 2)) * p.pnc[1] + (S.ky + 1 - ((nb >> 1) & 1))) * p.pnc[2] + (S.kz + 1 - (nb & 1));
                 /* still findable through the sorted layout: same owner cell, and either it sits in the
                    band prefix of that cell or it is (still) outside every band */
-                if (k == oc && (s < p.cell_start[oc] + p.band_count[oc] || !any_band(p, x, y, z, o))) continue;
-            }
-            if (e < 0) {
-                e = atomicAdd(p.esc_count, 1);
-                if (e >= p.esc_cap) { atomicAdd(&p.stats->esc_overflow, 1ull); continue; }
-                p.esc_slot[e] = s;
-                S.src[m] = e;
-                f |= AMC_FLAG_ESC;
-            }
-            for (int g2 = group + 1; g2 < 8; g2++) {
-                int cx = member_axis(p.edge[0], p.lo[0], p.nc[0], o[0], (g2 >> 2) & 1, x);
-                int cy = member_axis(p.edge[1], p.lo[1], p.nc[1], o[1], (g2 >> 1) & 1, y);
-                int cz = member_axis(p.edge[2], p.lo[2], p.nc[2], o[2], (g2 ^ p.zoff) & 1, z);
-                int32_t cc = (cx < 0 || cy < 0 || cz < 0) ? -1 : ((cx >> 1) * p.nh[1] + (cy >> 1)) * p.nh[2] + (cz >> 1);
-                p.esc_cell[e * 8 + g2] = cc;
-                if (cc >= 0 && atomicExch(&p.cell_active[(size_t)g2 * p.wl_stride + cc], 1) == 0) /* group g2 has not started yet */
-                    write_work_item(p, p.wl + ((size_t)g2 * p.wl_stride + atomicAdd(&p.wl_count[g2], 1)) * AMC_WI, cc, cx, cy, cz);
+                findable = k == oc && (so < p.cell_start[oc] + p.band_count[oc] || !any_band(p, x, y, z, o));
+                if (!findable) {
+                    e = atomicAdd(p.esc_count, 1);
+                    if (e >= p.esc_cap) { atomicAdd(&p.stats->esc_overflow, 1ull); ok = 0; }
+                    else { p.esc_slot[e] = so; S.src[mo] = e; of |= AMC_FLAG_ESC; }
+                }
             }
         }
+        // lane 8 * particle + g2 activates the particle's member cell of colour group g2
+        const int pw = (lane >> 3) & 1, g2 = lane & 7;
+        const int o0 = __shfl_sync(FULL, o[0], pw), o1 = __shfl_sync(FULL, o[1], pw), o2 = __shfl_sync(FULL, o[2], pw);
+        const int ee = __shfl_sync(FULL, e, pw), fnd = __shfl_sync(FULL, findable, pw), okk = __shfl_sync(FULL, ok, pw);
+        if (lane < 16 && g2 > group && okk) {
+            const double px = pw ? x2 : x1, py = pw ? y2 : y1, pz = pw ? z2 : z1;
+            int cx = member_axis(p.edge[0], p.lo[0], p.nc[0], o0, (g2 >> 2) & 1, px);
+            int cy = member_axis(p.edge[1], p.lo[1], p.nc[1], o1, (g2 >> 1) & 1, py);
+            int cz = member_axis(p.edge[2], p.lo[2], p.nc[2], o2, (g2 ^ p.zoff) & 1, pz);
+            int32_t cc = (cx < 0 || cy < 0 || cz < 0) ? -1 : ((cx >> 1) * p.nh[1] + (cy >> 1)) * p.nh[2] + (cz >> 1);
+            if (!fnd) p.esc_cell[ee * 8 + g2] = cc;
+            if (cc >= 0 && atomicExch(&p.cell_active[(size_t)g2 * p.wl_stride + cc], 1) == 0) /* group g2 has not started yet */
+                write_work_item(p, p.wl + ((size_t)g2 * p.wl_stride + atomicAdd(&p.wl_count[g2], 1)) * AMC_WI, cc, cx, cy, cz);
+        }
     }
-    A.flag[s1] = (uint8_t)f1; A.flag[s2] = (uint8_t)f2;
+    if (lane < 2) A.flag[so] = (uint8_t)of;
+    __syncwarp();
 }
 
 // members are in S.{x,y,z,id,slot,src}[0..S.n); all threads of the block call this
@@ -529,24 +571,26 @@ __device__ void cell_process(const P &p, CellShared &S, int group, int cell)
     if (tid == 0) { S.cursor = 0; S.done = 0; if (S.ncand > AMC_MAX_CAND) S.ncand = AMC_MAX_CAND; }
     __syncthreads();
     while (true) {
-        if (tid == 0) {
+        if (warp == 0) { /* warp-uniform: every lane scans the (few) candidates itself */
             int best = -1;
             unsigned long long bk = ~0ull;
             for (int k = 0; k < S.ncand; k++)
                 if (S.cand_key[k] < bk) { bk = S.cand_key[k]; best = k; } /* all stored keys are above the cursor */
-            if (best < 0) S.done = 1;
+            if (best < 0) { if (lane == 0) S.done = 1; }
             else {
                 int a = S.cand_ab[best] & 0xffff, b = S.cand_ab[best] >> 16;
                 int m1 = S.id[a] < S.id[b] ? a : b, m2 = S.id[a] < S.id[b] ? b : a;
                 resolve_pair(p, S, m1, m2, group, cell);
-                S.cursor = bk; S.moved_a = a; S.moved_b = b;
-                int w = 0;
-                for (int k = 0; k < S.ncand; k++) {
-                    int ka = S.cand_ab[k] & 0xffff, kb = S.cand_ab[k] >> 16;
-                    if (ka == a || ka == b || kb == a || kb == b) continue;
-                    S.cand_key[w] = S.cand_key[k]; S.cand_ab[w] = S.cand_ab[k]; w++;
+                if (lane == 0) {
+                    S.cursor = bk; S.moved_a = a; S.moved_b = b;
+                    int w = 0;
+                    for (int k = 0; k < S.ncand; k++) {
+                        int ka = S.cand_ab[k] & 0xffff, kb = S.cand_ab[k] >> 16;
+                        if (ka == a || ka == b || kb == a || kb == b) continue;
+                        S.cand_key[w] = S.cand_key[k]; S.cand_ab[w] = S.cand_ab[k]; w++;
+                    }
+                    S.ncand = w;
                 }
-                S.ncand = w;
             }
         }
         __syncthreads();
@@ -569,9 +613,10 @@ __device__ void cell_process(const P &p, CellShared &S, int group, int cell)
     }
 }
 
-// worklist of one pair pass: every reference cell whose 8 candidate owner cells hold at least two
-// particles, per colour group.  Cells that later receive an escaped particle are appended by
-// resolve_pair.  One thread per reference cell.
+// Detection list of one pair pass: every reference cell whose 8 candidate owner cells hold at least two
+// particles (all colour groups together).  k_detect turns it into the per-group worklists of the cells
+// that can hold a collision; cells that later receive a moved particle are appended by resolve_pair /
+// k_bnd_apply.  One thread per reference cell.
 __global__ void __launch_bounds__(ADVECT_THREADS) k_build_worklist(const __grid_constant__ P p)
 {
     int cid = blockIdx.x * blockDim.x + threadIdx.x; /* linear over (kx, ky, kz), z fastest */
@@ -584,11 +629,219 @@ __global__ void __launch_bounds__(ADVECT_THREADS) k_build_worklist(const __grid_
         int oc = ((kx + 1 - (nb >> 2)) * p.pnc[1] + (ky + 1 - ((nb >> 1) & 1))) * p.pnc[2] + (kz + 1 - (nb & 1));
         total += nb == 0 ? p.cell_start[oc + 1] - p.cell_start[oc] : p.band_count[oc];
     }
-    int group = ((kx & 1) << 2) | ((ky & 1) << 1) | ((kz + p.zoff) & 1); /* colour group from the GLOBAL z parity */
-    int cell = ((kx >> 1) * p.nh[1] + (ky >> 1)) * p.nh[2] + (kz >> 1);
-    int active = total >= 2;
-    p.cell_active[(size_t)group * p.wl_stride + cell] = active;
-    if (active) write_work_item(p, p.wl + ((size_t)group * p.wl_stride + atomicAdd(&p.wl_count[group], 1)) * AMC_WI, cell, kx, ky, kz);
+    if (total >= 2) { /* one atomic per warp */
+        unsigned peers = __activemask();
+        int leader = __ffs(peers) - 1, lane = threadIdx.x & 31, base = 0;
+        if (lane == leader) base = atomicAdd(p.dl_count, __popc(peers));
+        base = __shfl_sync(peers, base, leader);
+        int cell = ((kx >> 1) * p.nh[1] + (ky >> 1)) * p.nh[2] + (kz >> 1);
+        write_work_item(p, p.dl + (size_t)(base + __popc(peers & ((1u << lane) - 1))) * AMC_WI, cell, kx, ky, kz);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Detection pass (the neighbour search proper): ONE launch over every reference cell of all 8 colour
+// groups, on the positions as they are before the first group runs.  A cell visit of the reference
+// (Pore:160-255) changes nothing unless two of its members overlap, and the members of a cell only
+// change when a collision moves one of them -- so the ordered resolution (k_pairs_group) has to visit
+//   (a) the cells in which this pass finds an overlapping pair, and
+//   (b) the cells of later groups that contain a particle moved by a collision (activated there).
+// Everything here is a conservative filter: cell membership is decided exactly (fp64, Pore:527-529),
+// distances are tested in fp32 on cell-relative coordinates against a threshold widened by the
+// rounding bound (det_thr, amc_api.cu), and anything unusual (more candidates than the CTA holds, a
+// full slab) flags the cell.  False positives cost one exact visit; misses are impossible.
+//
+// Per cell: candidates are streamed from HBM once (24 B each; the loads of the NEXT cell are in flight
+// while the current one is searched).  Members are hashed into a 2-D table of bins over (x, y), each
+// >= 1.05 filter radii wide: at gas density a bin holds 0.07 particles, so a member only looks at its own
+// bin and the four forward neighbours and almost never finds anything to test.  Table entries carry the
+// visit number in their upper half, so the table is never cleared.  Two barriers per cell.
+#define DET_THREADS 128
+#define DET_K 3     /* candidates per thread: cells with more than DET_K * DET_THREADS candidates are flagged */
+#define DET_CAND (DET_K * DET_THREADS)
+#define DET_NB 64   /* bins per axis, at most */
+#define DET_ROW (DET_NB + 2)                /* one empty bin on either side of a row */
+#define DET_TAB ((DET_NB + 1) * DET_ROW)    /* one empty row behind the last */
+
+struct DetShared {
+    unsigned int head[DET_TAB];      /* (visit tag << 16) | (candidate index + 1) of the last member hashed into the bin */
+    float4 tile[DET_CAND];           /* cell-relative fp32 position by candidate index */
+    unsigned short next[DET_CAND];   /* older member of the same bin (index + 1), 0 = none */
+    __align__(16) int hdr[2][AMC_WI];
+    int rbeg[2][8], rcum[2][9];
+    float inv_wx[2], inv_wy[2];
+    int nbx[2], nby[2];
+    int nmem[2];
+};
+
+// warp 0: make the work item `v` (one int per lane) the header in buffer `buf`
+__device__ __forceinline__ void det_publish(const P &p, DetShared &S, int buf, int v, int lane)
+{
+    S.hdr[buf][lane] = v;
+    __syncwarp();
+    if (lane < 8) {
+        S.rbeg[buf][lane] = S.hdr[buf][4 + lane];
+        int inc = S.hdr[buf][12 + lane];
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) { int t = __shfl_up_sync(0xffu, inc, o); if (lane >= o) inc += t; }
+        S.rcum[buf][lane + 1] = inc;
+        if (lane < 2) { /* lane 0: bins along x, lane 1: along y */
+            const double *d = reinterpret_cast<const double *>(&S.hdr[buf][20]);
+            float wd = (float)(d[2 * lane + 1] - d[2 * lane]);
+            int nb = (int)fminf((float)DET_NB, floorf(wd / p.det_w));
+            if (nb < 1) nb = 1;
+            if (lane == 0) { S.nbx[buf] = nb; S.inv_wx[buf] = (float)nb / wd; S.rcum[buf][0] = 0; }
+            else { S.nby[buf] = nb; S.inv_wy[buf] = (float)nb / wd; }
+        }
+    }
+}
+
+// slot of candidate t of the work item in buffer `buf`: the owner cell's own particles first, then the
+// band prefixes of the 7 low-side neighbours
+__device__ __forceinline__ int det_slot(const DetShared &S, int buf, int t)
+{
+    if (t < S.rcum[buf][1]) return S.rbeg[buf][0] + t;
+    int nb = 1;
+#pragma unroll
+    for (int r = 2; r < 8; r++) nb += t >= S.rcum[buf][r];
+    return S.rbeg[buf][nb] + (t - S.rcum[buf][nb]);
+}
+
+__global__ void __launch_bounds__(DET_THREADS, 8) k_detect(const __grid_constant__ P p)
+{
+    __shared__ DetShared S;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const Arrays &A = p.a;
+    const int nwork = *p.dl_count;
+    const int stride = gridDim.x;
+    int w = blockIdx.x;
+    if (w >= nwork) return;
+    for (int c = tid; c < DET_TAB; c += DET_THREADS) S.head[c] = 0;
+    if (tid < 2) S.nmem[tid] = 0;
+    int hn = 0; /* warp 0: the work item after the one published in the other buffer */
+    if (warp == 0) {
+        det_publish(p, S, 0, p.dl[(size_t)w * AMC_WI + lane], lane);
+        if (w + stride < nwork) hn = p.dl[(size_t)(w + stride) * AMC_WI + lane];
+    }
+    __syncthreads();
+    double cx[DET_K], cy[DET_K], cz[DET_K];
+#pragma unroll
+    for (int k = 0; k < DET_K; k++) {
+        int t = tid + k * DET_THREADS;
+        if (t < S.rcum[0][8]) {
+            int s = det_slot(S, 0, t);
+            cx[k] = A.x[s]; cy[k] = A.y[s]; cz[k] = A.z[s];
+        }
+    }
+    unsigned int tests = 0;
+    unsigned long long nref = 0; /* thread 0 */
+    const float thr = p.det_thr;
+    unsigned int tagw = 0;
+    for (int it = 0; w < nwork; it++, w += stride) {
+        const int cur = it & 1, nxt = cur ^ 1;
+        tagw += 0x10000u;
+        if (tagw == 0) { /* visit tags exhausted (65535 cells in this CTA): start over with a clean table */
+            __syncthreads();
+            for (int c = tid; c < DET_TAB; c += DET_THREADS) S.head[c] = 0;
+            tagw = 0x10000u;
+            __syncthreads();
+        }
+        // ---- hash the members of the current cell
+        const int total = S.rcum[cur][8];
+        bool hit = total > DET_CAND;
+        float fx[DET_K], fy[DET_K], fz[DET_K];
+        int bin[DET_K], older[DET_K];
+        {
+            const double *bd = reinterpret_cast<const double *>(&S.hdr[cur][20]);
+            const double lox = bd[0], hix = bd[1], loy = bd[2], hiy = bd[3], loz = bd[4], hiz = bd[5];
+            const float inv_wx = S.inv_wx[cur], inv_wy = S.inv_wy[cur];
+            const int nbx1 = S.nbx[cur] - 1, nby1 = S.nby[cur] - 1;
+            const int own = p.det_own_is_member ? S.rcum[cur][1] : 0; /* the owner cell's particles are members by construction */
+            int nm = 0;
+#pragma unroll
+            for (int k = 0; k < DET_K; k++) {
+                int t = tid + k * DET_THREADS;
+                bin[k] = -1;
+                if (t < total) {
+                    double x = cx[k], y = cy[k], z = cz[k];
+                    if (t < own || (lox < x && x < hix && loy < y && y < hiy && loz < z && z < hiz)) { /* Pore:527-530 */
+                        fx[k] = (float)(x - lox); fy[k] = (float)(y - loy); fz[k] = (float)(z - loz);
+                        int b = min(nbx1, (int)(fx[k] * inv_wx)) * DET_ROW + min(nby1, (int)(fy[k] * inv_wy)) + 1;
+                        S.tile[t] = make_float4(fx[k], fy[k], fz[k], 0.f);
+                        unsigned int prev = atomicExch(&S.head[b], tagw | (unsigned int)(t + 1)) ^ tagw;
+                        prev = prev < 0x10000u ? prev : 0u;
+                        S.next[t] = (unsigned short)prev;
+                        bin[k] = b; older[k] = (int)prev;
+                        nm++;
+                    }
+                }
+            }
+            nm = __reduce_add_sync(0xffffffffu, nm);
+            if (lane == 0 && nm) atomicAdd(&S.nmem[cur], nm);
+        }
+        const int wn = w + stride;
+        if (warp == 0 && wn < nwork) {
+            det_publish(p, S, nxt, hn, lane);
+            if (wn + stride < nwork) hn = p.dl[(size_t)(wn + stride) * AMC_WI + lane];
+        }
+        __syncthreads();
+        // ---- the next cell's candidates start their trip from HBM now
+        if (wn < nwork) {
+            const int ntot = S.rcum[nxt][8];
+#pragma unroll
+            for (int k = 0; k < DET_K; k++) {
+                int t = tid + k * DET_THREADS;
+                if (t < ntot) {
+                    int s = det_slot(S, nxt, t);
+                    cx[k] = A.x[s]; cy[k] = A.y[s]; cz[k] = A.z[s];
+                }
+            }
+        }
+        // ---- search: the older members of the own bin and everything in the four forward neighbour bins
+        float dmin = 3.0e38f;
+#pragma unroll
+        for (int k = 0; k < DET_K; k++) {
+            if (bin[k] < 0) continue;
+            const int b = bin[k];
+            unsigned int c[5];
+            c[0] = (unsigned int)older[k];
+            c[1] = S.head[b + 1] ^ tagw; c[2] = S.head[b + DET_ROW - 1] ^ tagw;
+            c[3] = S.head[b + DET_ROW] ^ tagw; c[4] = S.head[b + DET_ROW + 1] ^ tagw;
+            if (c[0] == 0 && min(min(c[1], c[2]), min(c[3], c[4])) >= 0x10000u) continue;
+            const float ax = fx[k], ay = fy[k], az = fz[k];
+#pragma unroll
+            for (int n = 0; n < 5; n++) {
+                for (unsigned int e = c[n] < 0x10000u ? c[n] : 0u; e; e = S.next[e - 1]) {
+                    float4 q = S.tile[e - 1];
+                    float ex = q.x - ax, ey = q.y - ay, ez = q.z - az;
+                    dmin = fminf(dmin, fmaf(ez, ez, fmaf(ey, ey, ex * ex)));
+                    tests++;
+                }
+            }
+        }
+        hit = hit || dmin < thr;
+        if (tid == DET_THREADS - 1) S.nmem[nxt] = 0;
+        const int any = __syncthreads_or(hit);
+        if (warp == 0) {
+            const int *h = S.hdr[cur];
+            const int cell = h[0], kx = h[1], ky = h[2], kz = h[3];
+            const int g = ((kx & 1) << 2) | ((ky & 1) << 1) | ((kz + p.zoff) & 1);
+            const size_t ci = (size_t)g * p.wl_stride + cell;
+            if (any) {
+                int idx = 0;
+                if (lane == 0) { p.cell_active[ci] = 1; idx = atomicAdd(&p.wl_count[g], 1); }
+                idx = __shfl_sync(0xffffffffu, idx, 0);
+                p.wl[((size_t)g * p.wl_stride + idx) * AMC_WI + lane] = h[lane];
+            } else if (lane == 0) {
+                const int nm = S.nmem[cur];
+                p.cell_n[ci] = nm;
+                nref += (unsigned long long)nm * (nm - 1) / 2;
+            }
+        }
+    }
+    tests = __reduce_add_sync(0xffffffffu, tests);
+    if (lane == 0 && tests) atomicAdd(&p.stats->checks_exec, (unsigned long long)tests);
+    if (tid == 0 && nref) atomicAdd(&p.stats->checks_ref, nref);
 }
 
 // one colour group (Pore:522-549): persistent CTAs walk the group's worklist
@@ -660,17 +913,27 @@ __global__ void __launch_bounds__(PAIR_THREADS, 8) k_pairs_group(const __grid_co
             // membership is decided on the live position (Pore:527-530); the 8 ranges are walked as one
             // flat index space so every thread has independent loads in flight
             const int total = S.rcum[8];
-            for (int t = tid; t < total; t += PAIR_THREADS) {
-                int nb = 0;
+            for (int t0 = tid; t0 < total; t0 += 3 * PAIR_THREADS) { /* three candidates per thread in flight: one round trip for most cells */
+                unsigned fl[3]; double x[3], y[3], z[3]; int id[3], sl[3], nbk[3];
 #pragma unroll
-                for (int r = 1; r < 8; r++) nb += t >= S.rcum[r];
-                int s = S.rbeg[nb] + (t - S.rcum[nb]);
-                unsigned fl = A.flag[s];
-                double x = A.x[s], y = A.y[s], z = A.z[s];
-                int id = A.id[s]; /* issued with the other loads: one round trip per iteration */
-                if (!(fl & AMC_FLAG_ESC) && lox < x && x < hix && loy < y && y < hiy && loz < z && z < hiz) {
-                    int k = atomicAdd(&S.n, 1);
-                    if (k < AMC_MAX_MEMBERS) { S.x[k] = x; S.y[k] = y; S.z[k] = z; S.id[k] = id; S.slot[k] = s; S.src[k] = -1 - nb; }
+                for (int k = 0; k < 3; k++) {
+                    int t = t0 + k * PAIR_THREADS;
+                    if (t < total) {
+                        int nb = 0;
+#pragma unroll
+                        for (int r = 1; r < 8; r++) nb += t >= S.rcum[r];
+                        int s = S.rbeg[nb] + (t - S.rcum[nb]);
+                        fl[k] = A.flag[s]; x[k] = A.x[s]; y[k] = A.y[s]; z[k] = A.z[s]; id[k] = A.id[s];
+                        sl[k] = s; nbk[k] = nb;
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    int t = t0 + k * PAIR_THREADS;
+                    if (t < total && !(fl[k] & AMC_FLAG_ESC) && lox < x[k] && x[k] < hix && loy < y[k] && y[k] < hiy && loz < z[k] && z[k] < hiz) {
+                        int m = atomicAdd(&S.n, 1);
+                        if (m < AMC_MAX_MEMBERS) { S.x[m] = x[k]; S.y[m] = y[k]; S.z[m] = z[k]; S.id[m] = id[k]; S.slot[m] = sl[k]; S.src[m] = -1 - nbk[k]; }
+                    }
                 }
             }
             for (int e = tid; e < s_ne; e += PAIR_THREADS) { /* particles that left their sorted owner cell earlier in this pass */
@@ -686,6 +949,10 @@ __global__ void __launch_bounds__(PAIR_THREADS, 8) k_pairs_group(const __grid_co
             __syncthreads();
             if (tid == 0) { atomicAdd(&p.stats->cell_overflow, 1ull); S.n = AMC_MAX_MEMBERS; }
             __syncthreads();
+        }
+        if (tid == 0) { /* the detection pass already counted this cell if it saw it without an overlapping pair */
+            int nA = p.cell_n[(size_t)group * p.wl_stride + cell];
+            S.nref -= (unsigned long long)nA * (nA - 1) / 2;
         }
         if (S.n >= 2) cell_process(p, S, group, cell);
         PHASE_MARK(7); /* resolution loop (cells with candidates) */
@@ -948,24 +1215,23 @@ __global__ void __launch_bounds__(128) k_bnd_apply(const __grid_constant__ P p)
     if (e < 0) {
         int32_t sk = p.skey[s];
         findable = sk >= 0 && k == sk && (s < p.cell_start[sk] + p.band_count[sk] || !any_band(p, x, y, z, o));
-    }
-    if (!findable) {
-        if (e < 0) {
+        if (!findable) {
             e = atomicAdd(p.esc_count, 1);
             if (e >= p.esc_cap) { atomicAdd(&p.stats->esc_overflow, 1ull); e = -1; }
             else { p.esc_slot[e] = s; nf |= AMC_FLAG_ESC; }
         }
-        if (e >= 0)
-            for (int g2 = p.group_done + 1; g2 < 8; g2++) {
-                int cx = member_axis(p.edge[0], p.lo[0], p.nc[0], o[0], (g2 >> 2) & 1, x);
-                int cy = member_axis(p.edge[1], p.lo[1], p.nc[1], o[1], (g2 >> 1) & 1, y);
-                int cz = member_axis(p.edge[2], p.lo[2], p.nc[2], o[2], (g2 ^ p.zoff) & 1, z);
-                int32_t cc = (cx < 0 || cy < 0 || cz < 0) ? -1 : ((cx >> 1) * p.nh[1] + (cy >> 1)) * p.nh[2] + (cz >> 1);
-                p.esc_cell[e * 8 + g2] = cc;
-                if (cc >= 0 && atomicExch(&p.cell_active[(size_t)g2 * p.wl_stride + cc], 1) == 0)
-                    write_work_item(p, p.wl + ((size_t)g2 * p.wl_stride + atomicAdd(&p.wl_count[g2], 1)) * AMC_WI, cc, cx, cy, cz);
-            }
     }
+    // the cells of the remaining groups that hold this particle must be visited (k_detect did not see this position)
+    if (findable || e >= 0)
+        for (int g2 = p.group_done + 1; g2 < 8; g2++) {
+            int cx = member_axis(p.edge[0], p.lo[0], p.nc[0], o[0], (g2 >> 2) & 1, x);
+            int cy = member_axis(p.edge[1], p.lo[1], p.nc[1], o[1], (g2 >> 1) & 1, y);
+            int cz = member_axis(p.edge[2], p.lo[2], p.nc[2], o[2], (g2 ^ p.zoff) & 1, z);
+            int32_t cc = (cx < 0 || cy < 0 || cz < 0) ? -1 : ((cx >> 1) * p.nh[1] + (cy >> 1)) * p.nh[2] + (cz >> 1);
+            if (!findable) p.esc_cell[e * 8 + g2] = cc;
+            if (cc >= 0 && atomicExch(&p.cell_active[(size_t)g2 * p.wl_stride + cc], 1) == 0)
+                write_work_item(p, p.wl + ((size_t)g2 * p.wl_stride + atomicAdd(&p.wl_count[g2], 1)) * AMC_WI, cc, cx, cy, cz);
+        }
     A.flag[s] = (uint8_t)nf;
     }
 }

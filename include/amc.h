@@ -187,6 +187,10 @@ int amc_set_step_index(amc_handle *h, int64_t step);
  * launches: number of kernel launches in that call. */
 int amc_last_timing(amc_handle *h, double ms[5], int64_t *launches);
 
+/* device time (ms, summed over the steps of the last amc_step call) of the detection kernel alone (k_detect: the
+ * neighbour search over every reference cell, Pore:168-174); the rest of [2] above is the ordered resolution. */
+int amc_last_detect_ms(amc_handle *h, double *ms);
+
 /* ------------------------------------------------------------------------------------------------
  * Slab decomposition along z over several GPUs (one handle = one rank = the reference cells of the
  * global z layers [cuts[rank], cuts[rank+1]); no counterpart in the reference, results are identical

@@ -16,5 +16,5 @@ sim.set_state(*state)
 for k in range(steps):
     st = sim.step(1)[0]
 ms, launches = sim.last_timing()
-print(kind, len(state[0]), "last step ms", ms, "collisions", st["collisions"], "checks exec/ref", st["pair_checks_exec"], st["pair_checks_ref"])
+print(kind, len(state[0]), "detect ms", sim.last_detect_ms(), "last step ms", ms, "collisions", st["collisions"], "checks exec/ref", st["pair_checks_exec"], st["pair_checks_ref"])
 sim.close()
