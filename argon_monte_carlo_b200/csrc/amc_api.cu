@@ -270,7 +270,7 @@ static int create_impl(amc_handle *h, const amc_config *cfg, int device)
         p.det_w = std::nextafterf((float)(1.05 * std::sqrt((double)p.det_thr)), INFINITY);
     }
     p.esc_cap = (int32_t)std::min<int64_t>(std::max<int64_t>(h->cap / 64, 4096), 1 << 22);
-    ALLOC(p.esc_count, 1); ALLOC(p.esc_slot, p.esc_cap); ALLOC(p.esc_cell, (size_t)p.esc_cap * 8);
+    ALLOC(p.esc_count, 1); ALLOC(p.esc_slot, p.esc_cap); ALLOC(p.esc_cell, (size_t)p.esc_cap * 8); ALLOC(p.esc_next, (size_t)p.esc_cap * 8);
     CK(cudaMemset(p.esc_count, 0, sizeof(int32_t)));
     CK(cudaMemset(p.esc_cell, 0xff, (size_t)p.esc_cap * 8 * sizeof(int32_t)));
     h->stats_cap = 256;
@@ -460,15 +460,25 @@ extern "C" int amc_step(amc_handle *h, int32_t n_steps, amc_step_stats *stats)
                 // the recapture that closes step s-1's pair pass rides along in step s's advect kernel
                 const bool fuse_prev = has_recap && s > 0;
                 p.stats_prev = fuse_prev ? h->d_stats + (s - 1) : h->d_stats + s;
-                int phase = PH_DRIFT | PH_WALLS | (has_recap ? PH_RECAP : 0) | (sweep ? 0 : PH_KEYS) | (fuse_prev ? PH_RECAP_POST : 0);
-                if (!sweep) {
+                int phase = PH_DRIFT | PH_WALLS | (has_recap ? PH_RECAP : 0) | (fuse_prev ? PH_RECAP_POST : 0);
+                if (sweep) {
+                    k_advect<<<grid_for(h->n, ADVECT_THREADS), ADVECT_THREADS, 0, h->stream>>>(p, phase);
+                    h->last_launches += 1;
+                    CK(cudaEventRecord(h->events[4 * s + 1], h->stream));
+                } else { // fused: keys of the post-step positions, then the step itself on the way to the sorted slot
                     CK(cudaMemsetAsync(p.band_count, 0, (h->n_buckets + 1) * sizeof(int32_t), h->stream));
                     CK(cudaMemsetAsync(p.rest_count, 0, (h->n_buckets + 1) * sizeof(int32_t), h->stream));
+                    k_keys<<<grid_for(h->n, ADVECT_THREADS), ADVECT_THREADS, 0, h->stream>>>(p, phase);
+                    CK(cudaEventRecord(h->events[4 * s + 1], h->stream));
+                    int m = h->n_buckets, ntiles = (m + SCAN_TILE - 1) / SCAN_TILE;
+                    k_scan_tiles<<<ntiles, SCAN_THREADS, 0, h->stream>>>(p.band_count, p.rest_count, p.cell_start, h->d_tile_sums, m);
+                    k_scan_sums<<<1, SCAN_THREADS, 0, h->stream>>>(h->d_tile_sums, ntiles);
+                    k_scan_add<<<ntiles, SCAN_THREADS, 0, h->stream>>>(p.cell_start, h->d_tile_sums, m, (int32_t)h->n);
+                    k_scatter_advect<<<grid_for(h->n, ADVECT_THREADS), ADVECT_THREADS, 0, h->stream>>>(p, phase);
+                    CK(cudaGetLastError());
+                    std::swap(p.a, p.b);
+                    h->last_launches += 5;
                 }
-                k_advect<<<grid_for(h->n, ADVECT_THREADS), ADVECT_THREADS, 0, h->stream>>>(p, phase);
-                h->last_launches += 1;
-                CK(cudaEventRecord(h->events[4 * s + 1], h->stream));
-                if (!sweep) { rc = sort_scatter(h, &h->last_launches); if (rc != AMC_OK) return rc; }
                 CK(cudaEventRecord(h->events[4 * s + 2], h->stream));
                 h->det_slot = sweep ? -1 : s;
                 rc = run_pairs(h, &h->last_launches);

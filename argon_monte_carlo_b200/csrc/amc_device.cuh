@@ -22,7 +22,7 @@
 #define AMC_REC 12            /* doubles per exchanged particle record: 10 state, id, flags */
 
 #define AMC_MAX_MEMBERS 512  /* particles per reference cell incl. overlap band (reference: <= 308) */
-#define AMC_MAX_CAND 128     /* simultaneously overlapping pairs per cell visit */
+#define AMC_MAX_CAND 64     /* simultaneously overlapping pairs per cell visit */
 #define AMC_WI 32            /* ints per work item: cell, kx, ky, kz, beg[8], len[8], 6 doubles of bounds = 128 bytes */
 #define AMC_WL_COUNTERS 24 /* wl_count[8], wl_next[8], dl_count, padding */
 #define AMC_XBINS 64         /* slabs along x of the in-CTA neighbour search (multiple of 32) */
@@ -91,7 +91,7 @@ struct P {
     float det_thr;        /* fp32 squared distance below which the detection pass treats a pair as overlapping (conservative) */
     float det_w;          /* minimal bin width of the detection pass: 1.05 * sqrt(det_thr) */
     int32_t det_own_is_member; /* lo[k] < edge[k] everywhere: a particle of owner cell k is a member of reference cell k */
-    int32_t *cell_active; /* [8][wl_stride] 1 = cell is in its group's worklist */
+    int32_t *cell_active; /* [8][wl_stride] 0: not on its group's worklist, 1: on it, e + 2: on it and escaped entry e heads its list (esc_link) */
     int32_t wl_stride;    /* reference cells per colour group */
     int32_t nh[3];        /* reference cells per axis and parity class: (nc+1)/2 */
     /* ---- slab decomposition along z (multi-GPU); slab == 0: single domain */
@@ -125,6 +125,7 @@ struct P {
     int32_t *esc_count;
     int32_t *esc_slot;
     int32_t *esc_cell; /* [esc_cap][8] member cell per colour group, -1 = none */
+    int32_t *esc_next; /* [esc_cap][8] next entry (+ 2) on the list of that cell, < 2 = end */
     StatsDev *stats;
     StatsDev *stats_prev; /* counters of the previous step (recapture fused into the next step's k_advect) */
 };
@@ -191,9 +192,11 @@ struct Part {
 
 // MFP bookkeeping shared by walls and pair collisions (Pore:274-284, 324-335, 186-199): a particle
 // that already finished a first collision completes a path of |path - |speed*t||, else it is flagged.
+template <bool LIVE = true>
 __device__ __forceinline__ void mfp_record(const P &p, double d, double dx, double dy, double dz, uint32_t &flag,
                                            double vx, double vy, double vz, double t)
 {
+    if (!LIVE) return; /* dry run (k_keys): only the final position matters */
     if (flag & AMC_FLAG_PATH) {
         double sp = sqrt((vx * vx + vy * vy) + vz * vz);
         emit_path(p, fabs(d - fabs(sp * t)), fabs(dx - fabs(vx * t)), fabs(dy - fabs(vy * t)), fabs(dz - fabs(vz * t)));
@@ -228,22 +231,24 @@ __device__ __forceinline__ void reflect_xy(Part &q, double Rc, double t)
 }
 
 // hit_cylinder_side_wall, Pore:294-348
+template <bool LIVE = true>
 __device__ __forceinline__ void pore_side_wall(const P &p, Part &q, double Rc)
 {
     double t;
-    if (!side_quadratic(q.x, q.y, q.vx, q.vy, Rc, t)) { atomicAdd(&p.stats->errors, 1ull); return; }
+    if (!side_quadratic(q.x, q.y, q.vx, q.vy, Rc, t)) { if (LIVE) atomicAdd(&p.stats->errors, 1ull); return; }
     double vx = q.vx, vy = q.vy, vz = q.vz;
-    mfp_record(p, q.d, q.dx, q.dy, q.dz, q.flag, vx, vy, vz, t);
+    mfp_record<LIVE>(p, q.d, q.dx, q.dy, q.dz, q.flag, vx, vy, vz, t);
     reflect_xy(q, Rc, t);
     q.d = fabs(sqrt((q.vx * q.vx + q.vy * q.vy) + vz * vz) * t);
     q.dx = fabs(q.vx * t); q.dy = fabs(q.vy * t); q.dz = fabs(vz * t);
 }
 
 // hit_vertical_wall, Pore:257-292
+template <bool LIVE = true>
 __device__ __forceinline__ void pore_plane_wall(const P &p, Part &q, double zp)
 {
     double t = (q.z - zp) / q.vz;
-    mfp_record(p, q.d, q.dx, q.dy, q.dz, q.flag, q.vx, q.vy, q.vz, t);
+    mfp_record<LIVE>(p, q.d, q.dx, q.dy, q.dz, q.flag, q.vx, q.vy, q.vz, t);
     q.d = fabs(sqrt((q.vx * q.vx + q.vy * q.vy) + q.vz * q.vz) * t);
     q.dx = fabs(q.vx * t); q.dy = fabs(q.vy * t); q.dz = fabs(q.vz * t);
     q.vz = -q.vz;
@@ -252,22 +257,23 @@ __device__ __forceinline__ void pore_plane_wall(const P &p, Part &q, double zp)
 
 // Pore wall cases 1..6 against the progressively mutated particle (Pore:442-485); returns hit bits.
 // `np.sqrt(x**2 + y**2) > R` is evaluated as `x*x + y*y > gt_R` (exactly equivalent, see P).
+template <bool LIVE = true>
 __device__ __forceinline__ uint32_t pore_walls(const P &p, Part &q)
 {
     const amc_geom &g = p.g;
     uint32_t bits = 0;
-    if (q.x * q.x + q.y * q.y > p.gt_Roa) { bits |= 1u << 0; pore_side_wall(p, q, g.R_oa_c); }
-    if (q.z < 0) { bits |= 1u << 1; pore_plane_wall(p, q, 0.0); }
-    if (q.z > g.H) { bits |= 1u << 2; pore_plane_wall(p, q, g.H); }
-    if (q.pz > g.z_cold && q.z < g.z_cold && q.x * q.x + q.y * q.y > p.gt_Rp) { bits |= 1u << 3; pore_plane_wall(p, q, g.z_cold); }
-    if (q.pz < g.oah && q.z > g.oah && q.x * q.x + q.y * q.y > p.gt_Rp) { bits |= 1u << 4; pore_plane_wall(p, q, g.oah); }
+    if (q.x * q.x + q.y * q.y > p.gt_Roa) { bits |= 1u << 0; pore_side_wall<LIVE>(p, q, g.R_oa_c); }
+    if (q.z < 0) { bits |= 1u << 1; pore_plane_wall<LIVE>(p, q, 0.0); }
+    if (q.z > g.H) { bits |= 1u << 2; pore_plane_wall<LIVE>(p, q, g.H); }
+    if (q.pz > g.z_cold && q.z < g.z_cold && q.x * q.x + q.y * q.y > p.gt_Rp) { bits |= 1u << 3; pore_plane_wall<LIVE>(p, q, g.z_cold); }
+    if (q.pz < g.oah && q.z > g.oah && q.x * q.x + q.y * q.y > p.gt_Rp) { bits |= 1u << 4; pore_plane_wall<LIVE>(p, q, g.oah); }
     double pr2 = q.px * q.px + q.py * q.py;
     bool pz_in_gap = q.pz < g.z_gt_pore && q.pz > g.z_gb;
-    if (pz_in_gap && pr2 < p.lt_Rg && q.x * q.x + q.y * q.y > p.gt_Rg) { bits |= 1u << 5; pore_side_wall(p, q, g.R_g_c); }
-    if (pr2 > p.gt_Rp && q.z < g.z_gb && pz_in_gap) { bits |= 1u << 6; pore_plane_wall(p, q, g.z_gb); }
-    if (pr2 > p.gt_Rp && q.z > g.z_gt_pore && pz_in_gap) { bits |= 1u << 7; pore_plane_wall(p, q, g.z_gt_pore); }
+    if (pz_in_gap && pr2 < p.lt_Rg && q.x * q.x + q.y * q.y > p.gt_Rg) { bits |= 1u << 5; pore_side_wall<LIVE>(p, q, g.R_g_c); }
+    if (pr2 > p.gt_Rp && q.z < g.z_gb && pz_in_gap) { bits |= 1u << 6; pore_plane_wall<LIVE>(p, q, g.z_gb); }
+    if (pr2 > p.gt_Rp && q.z > g.z_gt_pore && pz_in_gap) { bits |= 1u << 7; pore_plane_wall<LIVE>(p, q, g.z_gt_pore); }
     if (pr2 < p.lt_Rp && q.x * q.x + q.y * q.y > p.gt_Rp &&
-        ((q.z < g.z_cold && q.z > g.z_gt_pore) || (q.z < g.z_gb && q.z > g.oah))) { bits |= 1u << 8; pore_side_wall(p, q, g.R_p_c); }
+        ((q.z < g.z_cold && q.z > g.z_gt_pore) || (q.z < g.z_gb && q.z > g.oah))) { bits |= 1u << 8; pore_side_wall<LIVE>(p, q, g.R_p_c); }
     return bits;
 }
 
@@ -340,6 +346,7 @@ __device__ __forceinline__ bool temp_contact(const amc_geom &g, int c, const Par
 
 // energy accommodation at an energized wall (Temp:377-389, 402-403); leaves the particle at the
 // contact point with paths reset (Temp:398-401)
+template <bool LIVE = true>
 __device__ __forceinline__ void temp_energized(const P &p, Part &q, double t, const double col[3], const double dir[3],
                                                double Es, double alpha, double &dpz, double &dE)
 {
@@ -353,18 +360,19 @@ __device__ __forceinline__ void temp_energized(const P &p, Part &q, double t, co
     dE = Enew - E;
     double nvx = dir[0] * new_mag, nvy = dir[1] * new_mag, nvz = dir[2] * new_mag;
     dpz = m * nvz - old_pz;
-    mfp_record(p, q.d, q.dx, q.dy, q.dz, q.flag, q.vx, q.vy, q.vz, t);
+    mfp_record<LIVE>(p, q.d, q.dx, q.dy, q.dz, q.flag, q.vx, q.vy, q.vz, t);
     q.d = 0; q.dx = 0; q.dy = 0; q.dz = 0;
     q.x = col[0]; q.y = col[1]; q.z = col[2];
     q.vx = nvx; q.vy = nvy; q.vz = nvz;
 }
 
 // specular Temp cases: no MFP bookkeeping (Temp:311-347)
+template <bool LIVE = true>
 __device__ __forceinline__ void temp_specular(const P &p, int c, Part &q)
 {
     if (c == AMC_CASE_1) {
         double t;
-        if (!side_quadratic(q.x, q.y, q.vx, q.vy, p.g.R_oa_c, t)) { atomicAdd(&p.stats->errors, 1ull); return; }
+        if (!side_quadratic(q.x, q.y, q.vx, q.vy, p.g.R_oa_c, t)) { if (LIVE) atomicAdd(&p.stats->errors, 1ull); return; }
         reflect_xy(q, p.g.R_oa_c, t);
     } else {
         double zp = temp_plane(p.g, c);
@@ -465,6 +473,7 @@ __device__ __forceinline__ bool temp_any_mask(const P &p, const Part &q)
 }
 
 // all ten Temp cases on one particle with device RNG (Temp:693-753)
+template <bool LIVE = true>
 __device__ __forceinline__ uint32_t temp_walls_device(const P &p, Part &q, int64_t id)
 {
     uint32_t bits = 0;
@@ -473,13 +482,14 @@ __device__ __forceinline__ uint32_t temp_walls_device(const P &p, Part &q, int64
     for (int c = 0; c < AMC_NUM_CASES; c++) {
         if (!temp_mask(p, c, q)) continue;
         bits |= 1u << c;
-        if (c <= AMC_CASE_2B) { temp_specular(p, c, q); continue; }
+        if (c <= AMC_CASE_2B) { temp_specular<LIVE>(p, c, q); continue; }
         double t, col[3], nrm[3], dir[3], dpz, dE;
-        if (!temp_contact(p.g, c, q, t, col, nrm)) { atomicAdd(&p.stats->errors, 1ull); continue; }
+        if (!temp_contact(p.g, c, q, t, col, nrm)) { if (LIVE) atomicAdd(&p.stats->errors, 1ull); continue; }
         philox_direction(p, id, c, nrm, dir);
         double Es = c == AMC_CASE_4 ? cheb_eval(p, col[2]) : (temp_is_cold(c) ? p.g.E_cold : p.g.E_hot);
         double alpha = c == AMC_CASE_4 ? p.g.alpha_g : p.g.alpha_c;
-        temp_energized(p, q, t, col, dir, Es, alpha, dpz, dE);
+        temp_energized<LIVE>(p, q, t, col, dir, Es, alpha, dpz, dE);
+        if (!LIVE) continue;
         acc_add(p.stats->dpz, dpz, SC_P1, SC_P1I, SC_P2);
         if (c != AMC_CASE_4) acc_add(temp_is_cold(c) ? p.stats->ecold : p.stats->ehot, dE, SC_E1, SC_E1I, SC_E2);
     }

@@ -10,6 +10,8 @@
 
 #define ADVECT_THREADS 256
 #define PAIR_THREADS 128
+#define WALK_K 3 /* chains a thread of cell_process walks side by side */
+#define PAIR_K 3 /* candidates a thread of k_pairs_group has in flight during the gather */
 #define SWEEP_THREADS 512
 
 __device__ __forceinline__ void load_part(const Arrays &a, int64_t s, Part &q)
@@ -142,6 +144,94 @@ __global__ void __launch_bounds__(ADVECT_THREADS, 4) k_advect(const __grid_const
         int r = warp_rank(band ? &p.band_count[k] : &p.rest_count[k], (k << 1) | (int)band);
         p.rank[s] = band ? r : ~r;
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// The fused timestep streams the state ONCE through the SM instead of twice: a light first pass finds out
+// where every particle will be after the step (k_keys: 52 B read, 8 B written), and the counting-sort
+// scatter then carries out the step itself on the way to the particle's new slot (k_scatter_advect:
+// 93 B read, 85 B written) -- 238 B per particle and step instead of the 352 B of k_advect + k_scatter.
+// advance_particle is the per-particle part of a timestep before the pair pass (closing recapture of
+// the previous step, drift, wall cases, recapture; same references as k_advect).  LIVE = false is a
+// dry run: same arithmetic and therefore bit-identical positions, but no counters, no completed paths,
+// no path-length bookkeeping -- none of which feeds back into the position.
+template <bool LIVE>
+__device__ __forceinline__ void advance_particle(const P &p, Part &q, const int32_t id, const int phase)
+{
+    if (phase & PH_RECAP_POST) { // recapture that closes the previous step's pair pass (Pore:550 / Temp:843-845)
+        int cnt = p.kind == AMC_KIND_TEMP ? temp_oob(p.g, q) : 0;
+        int moved = p.kind == AMC_KIND_TEMP ? temp_recapture(p.g, q) : pore_recapture(p.g, q);
+        if (p.kind != AMC_KIND_TEMP) cnt = moved;
+        if (LIVE && cnt) atomicAdd(&p.stats_prev->oob_pp, (unsigned long long)cnt);
+        if (LIVE && p.kind == AMC_KIND_TEMP && moved) {
+            int after = temp_oob(p.g, q);
+            if (after) atomicAdd(&p.stats_prev->oob_pp_after, (unsigned long long)after);
+        }
+    }
+    if (phase & PH_DRIFT) {
+        q.px = q.x; q.py = q.y; q.pz = q.z;
+        double ax = p.dt * q.vx, ay = p.dt * q.vy, az = p.dt * q.vz;
+        q.x += ax; q.y += ay; q.z += az;
+        if (LIVE) {
+            q.d += fabs(sqrt((ax * ax + ay * ay) + az * az));
+            q.dx += fabs(ax); q.dy += fabs(ay); q.dz += fabs(az);
+        }
+    }
+    if (phase & PH_WALLS) {
+        uint32_t bits = p.kind == AMC_KIND_PORE ? pore_walls<LIVE>(p, q) : (p.kind == AMC_KIND_TEMP ? temp_walls_device<LIVE>(p, q, id) : cube_walls(p, q));
+        if (LIVE) {
+            for (uint32_t b = bits; b; b &= b - 1) atomicAdd(&p.stats->wall_hits[__ffs(b) - 1], 1ull);
+            if (p.wall_bits) p.wall_bits[id] = (uint16_t)bits;
+        }
+    }
+    if (phase & PH_RECAP) {
+        if (p.kind == AMC_KIND_PORE) {
+            int cnt = pore_recapture(p.g, q);
+            if (LIVE && cnt) atomicAdd(&p.stats->oob_walls, (unsigned long long)cnt);
+        } else if (p.kind == AMC_KIND_TEMP) {
+            int cnt = temp_oob(p.g, q);
+            if (LIVE && cnt) atomicAdd(&p.stats->oob_walls, (unsigned long long)cnt);
+            if (temp_recapture(p.g, q) && LIVE) {
+                int after = temp_oob(p.g, q);
+                if (after) atomicAdd(&p.stats->oob_walls_after, (unsigned long long)after);
+            }
+        }
+    }
+}
+
+// pass 1 of the fused step: owner cell of the position each particle will have after the step, and its
+// rank inside that cell (band particles first, see k_advect)
+__global__ void __launch_bounds__(ADVECT_THREADS, 4) k_keys(const __grid_constant__ P p, const int phase)
+{
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= p.n) return;
+    Part q;
+    q.x = p.a.x[s]; q.y = p.a.y[s]; q.z = p.a.z[s]; q.vx = p.a.vx[s]; q.vy = p.a.vy[s]; q.vz = p.a.vz[s];
+    q.d = q.dx = q.dy = q.dz = 0.0; q.flag = 0;
+    const int32_t id = p.kind == AMC_KIND_TEMP ? p.a.id[s] : 0; /* keys the device RNG of the energized walls */
+    advance_particle<false>(p, q, id, phase);
+    int o[3];
+    int32_t k = owner_key(p, q.x, q.y, q.z, o);
+    p.key[s] = k;
+    bool band = k != p.ncell_pad && any_band(p, q.x, q.y, q.z, o);
+    int r = warp_rank(band ? &p.band_count[k] : &p.rest_count[k], (k << 1) | (int)band);
+    p.rank[s] = band ? r : ~r;
+}
+
+// pass 2: the timestep proper, written straight to the particle's slot in owner-cell order
+__global__ void __launch_bounds__(ADVECT_THREADS, 3) k_scatter_advect(const __grid_constant__ P p, const int phase)
+{
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= p.n) return;
+    Part q;
+    load_part(p.a, s, q);
+    q.flag &= AMC_FLAG_PATH;
+    const int32_t id = p.a.id[s];
+    const int32_t k = p.key[s], r = p.rank[s];
+    advance_particle<true>(p, q, id, phase);
+    const int64_t t = (int64_t)p.cell_start[k] + (r >= 0 ? r : p.band_count[k] + ~r);
+    store_part(p.b, t, q);
+    p.b.id[t] = id;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -317,15 +407,17 @@ struct CellShared {
     int moved_a, moved_b;
     int kx, ky, kz; /* 0-based cell indices of this visit (colour-group mode) */
     long long t_last;
-    /* neighbour search: members binned into slabs along x */
-    double lo[3], inv_s[3]; /* [0]: low bound and 1/slab width along x */
-    int sub_ok, nb;
+    double org[3];               /* low corner of the cell: origin of the fp32 coordinates below */
+    double hi[3];                /* upper bounds of the cell (membership: org < v < hi, Pore:527-529) */
+    float fx[AMC_MAX_MEMBERS], fy[AMC_MAX_MEMBERS], fz[AMC_MAX_MEMBERS]; /* filter copy of the member positions */
+    /* neighbour search: members chained per slab along x (>= 1.05 filter radii wide) */
+    int head[AMC_XBINS + 2];     /* last member hashed into the slab (index + 1), 0 = empty; zero on entry of cell_process */
+    uint16_t nxt[AMC_MAX_MEMBERS];
+    float inv_w;                 /* slabs per unit length */
+    int nb;                      /* slabs of this cell, 1..AMC_XBINS */
     unsigned int nexec;          /* distance tests executed by this CTA since the last flush */
     unsigned long long nref;      /* reference-equivalent tests, thread 0 only */
     int rbeg[8], rcum[9];         /* the 8 candidate owner-cell ranges of this visit */
-    uint16_t sub_of[AMC_MAX_MEMBERS], pos_of[AMC_MAX_MEMBERS], order[AMC_MAX_MEMBERS];
-    int sub_off[AMC_XBINS + 2];
-    int sub_cnt[AMC_XBINS];
 };
 
 __device__ __forceinline__ unsigned long long pair_key(int32_t ia, int32_t ib)
@@ -343,6 +435,28 @@ __device__ __forceinline__ void push_cand(CellShared &S, const P &p, int a, int 
     int k = atomicAdd(&S.ncand, 1);
     if (k < AMC_MAX_CAND) { S.cand_key[k] = pair_key(S.id[a], S.id[b]); S.cand_ab[k] = a | (b << 16); }
     else atomicAdd(&p.stats->cand_overflow, 1ull);
+    // the resolution will read the velocity / path records of both particles: start them on their way from HBM
+    for (int w = 0; w < 2; w++) {
+        int s = S.slot[w ? b : a];
+        const double *rec[7] = {p.a.vx + s, p.a.vy + s, p.a.vz + s, p.a.d + s, p.a.dx + s, p.a.dy + s, p.a.dz + s};
+#pragma unroll
+        for (int r = 0; r < 7; r++) asm volatile("prefetch.global.L2 [%0];" ::"l"(rec[r]));
+    }
+}
+
+// Make sure colour group g2 (which has not started yet) visits cell cc.  cell_active[g2][cc] is 0 while the cell
+// is not on the group's worklist, 1 when it is, and e + 2 when it is and escaped-list entry e heads the list of
+// the particles that can no longer be found through the sorted layout but are members of that cell (older
+// entries follow through esc_next).  e < 0: just activate.  An entry is linked at most once per group.
+__device__ __forceinline__ void esc_link(const P &p, int g2, int32_t cc, int cx, int cy, int cz, int e)
+{
+    if (e >= 0) p.esc_cell[e * 8 + g2] = cc;
+    if (cc < 0) return;
+    int32_t *slot = &p.cell_active[(size_t)g2 * p.wl_stride + cc];
+    int old;
+    if (e >= 0) { old = atomicExch(slot, e + 2); p.esc_next[e * 8 + g2] = old; }
+    else old = atomicCAS(slot, 0, 1);
+    if (old == 0) write_work_item(p, p.wl + ((size_t)g2 * p.wl_stride + atomicAdd(&p.wl_count[g2], 1)) * AMC_WI, cc, cx, cy, cz);
 }
 
 // elastic exchange of one overlapping pair (Pore:176-241), executed by all 32 lanes of warp 0.
@@ -351,13 +465,37 @@ __device__ __forceinline__ void push_cand(CellShared &S, const P &p, int a, int 
 // independent global-memory round trips -- state stores, histogram updates of the completed paths,
 // per-(particle, later colour group) cell activation -- which the lanes issue side by side instead of
 // one thread walking through them: the latency of a collision is what a launch of k_pairs_group waits for.
-__device__ __noinline__ void resolve_pair(const P &p, CellShared &S, int m1, int m2, int group, int cell)
+__device__ __forceinline__ void resolve_pair(const P &p, CellShared &S, int m1, int m2, int group, int cell)
 {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, w = lane & 1; /* even lanes hold particle 1's record, odd lanes particle 2's */
     const Arrays &A = p.a;
     const int s1 = S.slot[m1], s2 = S.slot[m2];
     const int so = w ? s2 : s1, mo = w ? m2 : m1;
+    // The tail of this function walks through small tables with dependent loads (owner cell of the new position,
+    // member cells of the later groups, histogram edges).  The collision moves a particle by a fraction of the
+    // collision range, so the entries it will need are the ones around the OLD position: touch them now, while
+    // the velocity records are on their way, and the dependent loads become L1 hits.
+    if (lane < 12) {
+        const int ax = (lane >> 1) % 3, tbl = lane / 6;
+        const double v = ax == 0 ? S.x[mo] : (ax == 1 ? S.y[mo] : S.z[mo]);
+        const int nc = p.nc[ax];
+        int o = (int)((v - p.e0[ax]) * p.inv_d[ax]);
+        o = max(0, min(nc - 1, o));
+        const double *t0 = (tbl ? p.lo[ax] : p.edge[ax]) + max(0, o - 1), *t1 = (tbl ? p.lo[ax] : p.edge[ax]) + min(nc - 1, o + 2);
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(t0));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(t1));
+    } else if (lane < 25) {
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(p.hist_edges + min(16 * (lane - 12), AMC_NUM_BINS)));
+    } else if (lane < 27 && p.pp_mode == AMC_PP_GROUPS) {
+        const int e = S.src[lane == 25 ? m1 : m2];
+        if (e < 0) {
+            const int nb = -1 - e;
+            const int oc = ((S.kx + 1 - (nb >> 2)) * p.pnc[1] + (S.ky + 1 - ((nb >> 1) & 1))) * p.pnc[2] + (S.kz + 1 - (nb & 1));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(p.cell_start + oc));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(p.band_count + oc));
+        }
+    }
     const double ovx = A.vx[so], ovy = A.vy[so], ovz = A.vz[so], od = A.d[so], odx = A.dx[so], ody = A.dy[so], odz = A.dz[so];
     uint32_t of = A.flag[so];
     const double qvx = __shfl_xor_sync(FULL, ovx, 1), qvy = __shfl_xor_sync(FULL, ovy, 1), qvz = __shfl_xor_sync(FULL, ovz, 1);
@@ -455,37 +593,37 @@ __device__ __noinline__ void resolve_pair(const P &p, CellShared &S, int m1, int
         // only listed the cells that held an overlapping pair before the pass).  A moved particle whose
         // owner cell changed can, in addition, no longer be found through the sorted layout: its member
         // cell for every later group is published in the escaped list.
-        int o[3] = {0, 0, 0}, e = -1, findable = 0, ok = 0;
+        int o[3] = {0, 0, 0}, e = -1, e_old = -1, findable = 0, ok = 0;
         if (lane < 2) {
             int32_t k = owner_key(p, x, y, z, o);
-            e = S.src[mo];
+            e_old = S.src[mo];
             ok = 1;
-            if (e < 0) { /* found through the sorted layout: src = -1 - (low-side neighbour code) */
-                int nb = -1 - e;
+            if (e_old < 0) { /* found through the sorted layout: src = -1 - (low-side neighbour code) */
+                int nb = -1 - e_old;
                 int oc = ((S.kx + 1 - (nb >> 2)) * p.pnc[1] + (S.ky + 1 - ((nb >> 1) & 1))) * p.pnc[2] + (S.kz + 1 - (nb & 1));
                 /* still findable through the sorted layout: same owner cell, and either it sits in the
                    band prefix of that cell or it is (still) outside every band */
                 findable = k == oc && (so < p.cell_start[oc] + p.band_count[oc] || !any_band(p, x, y, z, o));
-                if (!findable) {
-                    e = atomicAdd(p.esc_count, 1);
-                    if (e >= p.esc_cap) { atomicAdd(&p.stats->esc_overflow, 1ull); ok = 0; }
-                    else { p.esc_slot[e] = so; S.src[mo] = e; of |= AMC_FLAG_ESC; }
-                }
+            }
+            if (!findable) { /* entries are never re-linked: a particle that moves again gets a fresh one, the old one is retired below */
+                e = atomicAdd(p.esc_count, 1);
+                if (e >= p.esc_cap) { atomicAdd(&p.stats->esc_overflow, 1ull); ok = 0; }
+                else { p.esc_slot[e] = so; S.src[mo] = e; of |= AMC_FLAG_ESC; }
             }
         }
-        // lane 8 * particle + g2 activates the particle's member cell of colour group g2
+        // lane 8 * particle + g2 takes care of the particle's member cell in colour group g2
         const int pw = (lane >> 3) & 1, g2 = lane & 7;
         const int o0 = __shfl_sync(FULL, o[0], pw), o1 = __shfl_sync(FULL, o[1], pw), o2 = __shfl_sync(FULL, o[2], pw);
-        const int ee = __shfl_sync(FULL, e, pw), fnd = __shfl_sync(FULL, findable, pw), okk = __shfl_sync(FULL, ok, pw);
+        const int ee = __shfl_sync(FULL, e, pw), eo = __shfl_sync(FULL, e_old, pw);
+        const int fnd = __shfl_sync(FULL, findable, pw), okk = __shfl_sync(FULL, ok, pw);
         if (lane < 16 && g2 > group && okk) {
             const double px = pw ? x2 : x1, py = pw ? y2 : y1, pz = pw ? z2 : z1;
             int cx = member_axis(p.edge[0], p.lo[0], p.nc[0], o0, (g2 >> 2) & 1, px);
             int cy = member_axis(p.edge[1], p.lo[1], p.nc[1], o1, (g2 >> 1) & 1, py);
             int cz = member_axis(p.edge[2], p.lo[2], p.nc[2], o2, (g2 ^ p.zoff) & 1, pz);
             int32_t cc = (cx < 0 || cy < 0 || cz < 0) ? -1 : ((cx >> 1) * p.nh[1] + (cy >> 1)) * p.nh[2] + (cz >> 1);
-            if (!fnd) p.esc_cell[ee * 8 + g2] = cc;
-            if (cc >= 0 && atomicExch(&p.cell_active[(size_t)g2 * p.wl_stride + cc], 1) == 0) /* group g2 has not started yet */
-                write_work_item(p, p.wl + ((size_t)g2 * p.wl_stride + atomicAdd(&p.wl_count[g2], 1)) * AMC_WI, cc, cx, cy, cz);
+            if (eo >= 0) p.esc_cell[eo * 8 + g2] = -1;
+            esc_link(p, g2, cc, cx, cy, cz, fnd ? -1 : ee);
         }
     }
     if (lane < 2) A.flag[so] = (uint8_t)of;
@@ -493,79 +631,72 @@ __device__ __noinline__ void resolve_pair(const P &p, CellShared &S, int m1, int
 }
 
 // members are in S.{x,y,z,id,slot,src}[0..S.n); all threads of the block call this
-__device__ void cell_process(const P &p, CellShared &S, int group, int cell)
+__device__ __forceinline__ void cell_process(const P &p, CellShared &S, int group, int cell)
 {
     const int n = S.n, tid = threadIdx.x, nthreads = blockDim.x;
-    const int lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
+    const int lane = tid & 31, warp = tid >> 5;
     if (tid == 0) S.nref += (unsigned long long)n * (n - 1) / 2;
-    if (n < AMC_SUB_MIN_N || !S.sub_ok) {
-        // small cell: all unordered pairs, one warp per row
-        for (int a = warp; a < n - 1; a += nwarps) {
-            double xa = S.x[a], ya = S.y[a], za = S.z[a];
-            for (int b = a + 1 + lane; b < n; b += 32)
-                if (overlap(p, xa, ya, za, S.x[b], S.y[b], S.z[b])) push_cand(S, p, a, b);
-        }
-        if (tid == 0) atomicAdd(&S.nexec, (unsigned int)(n * (n - 1) / 2));
-    } else {
-        // Sweep along x: bin the members into S.nb slabs of width >= 1.05 collision ranges and order them
-        // by slab.  Two spheres closer than the collision range are in the same or in adjacent slabs, so
-        // testing every member against the members that follow it in slab order up to the end of the
-        // next slab visits each candidate pair exactly once -- one contiguous range per member.
-        // (S.sub_cnt is zero on entry: zeroed at kernel start and again by the scan below.)
-        const int nb = S.nb;
-        const double lo = S.lo[0], inv_w = S.inv_s[0];
+    // Only cells that the detection pass flagged (or that received a moved particle) get here, so what counts is
+    // the latency of one visit.  Members are chained per slab along x (one shared-memory exchange each, no scan,
+    // no reordering); after one barrier every member walks the older entries of its own slab and the whole next
+    // slab.  A pair goes through the fp32 filter of k_detect first (cell-relative coordinates, threshold det_thr)
+    // and only the few that pass are decided by the exact test (Pore:173-174).
+    {
+        const float inv_w = S.inv_w, thr = p.det_thr;
+        const int nb1 = S.nb - 1;
         for (int k = tid; k < n; k += nthreads) {
-            int c = min(nb - 1, max(0, (int)((S.x[k] - lo) * inv_w)));
-            S.sub_of[k] = (uint16_t)c;
-            S.pos_of[k] = (uint16_t)atomicAdd(&S.sub_cnt[c], 1);
+            float fx = (float)(S.x[k] - S.org[0]);
+            S.fx[k] = fx; S.fy[k] = (float)(S.y[k] - S.org[1]); S.fz[k] = (float)(S.z[k] - S.org[2]);
+            int b = min(nb1, max(0, (int)(fx * inv_w)));
+            S.nxt[k] = (uint16_t)atomicExch(&S.head[b], k + 1);
         }
+        PHASE_MARK(9); /* chain: own work */
         __syncthreads();
-        PHASE_MARK(2); /* bin */
-        if (warp == 0) { // exclusive scan of the slab counters by one warp
-            constexpr int PER = AMC_XBINS / 32;
-            int v[PER], sum = 0;
-#pragma unroll
-            for (int k = 0; k < PER; k++) { v[k] = S.sub_cnt[lane * PER + k]; sum += v[k]; }
-            int inc = sum;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-            int ex = inc - sum;
-#pragma unroll
-            for (int k = 0; k < PER; k++) { S.sub_off[lane * PER + k] = ex; ex += v[k]; S.sub_cnt[lane * PER + k] = 0; }
-            if (lane == 31) { S.sub_off[AMC_XBINS] = ex; S.sub_off[AMC_XBINS + 1] = ex; }
-        }
-        __syncthreads();
-        PHASE_MARK(3); /* scan */
-        for (int k = tid; k < n; k += nthreads) {
-            int pos = S.sub_off[S.sub_of[k]] + S.pos_of[k];
-            S.pos_of[k] = (uint16_t)pos;
-            S.order[pos] = (uint16_t)k;
-        }
-        __syncthreads();
-        PHASE_MARK(4); /* order */
+        PHASE_MARK(2); /* chain: barrier */
         unsigned int mine = 0;
-        for (int q0 = tid; q0 < n; q0 += nthreads) { // walk in slab order so neighbouring lanes have similar ranges
-            int a = S.order[q0];
-            int end = S.sub_off[S.sub_of[a] + 2];
-            double xa = S.x[a], ya = S.y[a], za = S.z[a];
-            mine += end - (q0 + 1);
-            int q = q0 + 1;
-            for (; q + 1 < end; q += 2) { // two independent tests in flight
-                int b2 = S.order[q], b3 = S.order[q + 1];
-                bool h2 = overlap(p, xa, ya, za, S.x[b2], S.y[b2], S.z[b2]);
-                bool h3 = overlap(p, xa, ya, za, S.x[b3], S.y[b3], S.z[b3]);
-                if (h2) push_cand(S, p, a, b2);
-                if (h3) push_cand(S, p, a, b3);
+        for (int k0 = tid; k0 < n; k0 += WALK_K * nthreads) {
+            // WALK_K members per thread walk their chains side by side: every round is one hop for each of them
+            float ax[WALK_K], ay[WALK_K], az[WALK_K];
+            int e[WALK_K], more[WALK_K];
+#pragma unroll
+            for (int u = 0; u < WALK_K; u++) {
+                const int k = k0 + u * nthreads;
+                e[u] = 0; more[u] = 0; ax[u] = ay[u] = az[u] = 0.f;
+                if (k < n) {
+                    ax[u] = S.fx[k]; ay[u] = S.fy[k]; az[u] = S.fz[k];
+                    const int b = min(nb1, max(0, (int)(ax[u] * inv_w)));
+                    e[u] = S.nxt[k]; more[u] = S.head[b + 1];
+                }
             }
-            if (q < end) {
-                int b2 = S.order[q];
-                if (overlap(p, xa, ya, za, S.x[b2], S.y[b2], S.z[b2])) push_cand(S, p, a, b2);
+            while (true) {
+                int live = 0;
+#pragma unroll
+                for (int u = 0; u < WALK_K; u++) {
+                    if (e[u] == 0) { e[u] = more[u]; more[u] = 0; }
+                    live |= e[u];
+                }
+                if (live == 0) break;
+#pragma unroll
+                for (int u = 0; u < WALK_K; u++) {
+                    const int q = max(e[u] - 1, 0); /* entry 0 stands in for a finished chain; its result is masked */
+                    const float ex = S.fx[q] - ax[u], ey = S.fy[q] - ay[u], ez = S.fz[q] - az[u];
+                    const int nx = S.nxt[q];
+                    const float d2 = fmaf(ez, ez, fmaf(ey, ey, ex * ex));
+                    if (e[u] != 0 && d2 < thr) { /* rare */
+                        const int k = k0 + u * nthreads;
+                        if (overlap(p, S.x[k], S.y[k], S.z[k], S.x[q], S.y[q], S.z[q])) push_cand(S, p, k, q);
+                    }
+                    mine += e[u] != 0;
+                    e[u] = e[u] != 0 ? nx : 0;
+                }
             }
         }
+        PHASE_MARK(10); /* walk: own work */
         mine = __reduce_add_sync(0xffffffffu, mine);
         if (lane == 0 && mine) atomicAdd(&S.nexec, mine);
     }
     __syncthreads();
+    for (int c = tid; c < AMC_XBINS + 2; c += nthreads) S.head[c] = 0; /* every walk is done; the barriers of the caller order this before the next cell */
     PHASE_MARK(5); /* search */
     if (S.ncand == 0) return;
     if (tid == 0) { S.cursor = 0; S.done = 0; if (S.ncand > AMC_MAX_CAND) S.ncand = AMC_MAX_CAND; }
@@ -580,7 +711,9 @@ __device__ void cell_process(const P &p, CellShared &S, int group, int cell)
             else {
                 int a = S.cand_ab[best] & 0xffff, b = S.cand_ab[best] >> 16;
                 int m1 = S.id[a] < S.id[b] ? a : b, m2 = S.id[a] < S.id[b] ? b : a;
+                PHASE_MARK(6); /* pick */
                 resolve_pair(p, S, m1, m2, group, cell);
+                PHASE_MARK(8); /* resolve_pair */
                 if (lane == 0) {
                     S.cursor = bk; S.moved_a = a; S.moved_b = b;
                     int w = 0;
@@ -619,23 +752,33 @@ __device__ void cell_process(const P &p, CellShared &S, int group, int cell)
 // k_bnd_apply.  One thread per reference cell.
 __global__ void __launch_bounds__(ADVECT_THREADS) k_build_worklist(const __grid_constant__ P p)
 {
+    __shared__ int s_cnt, s_base;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
     int cid = blockIdx.x * blockDim.x + threadIdx.x; /* linear over (kx, ky, kz), z fastest */
     int ncell = p.nc[0] * p.nc[1] * p.nc[2];
-    if (cid >= ncell) return;
-    int kz = cid % p.nc[2], ky = (cid / p.nc[2]) % p.nc[1], kx = cid / (p.nc[2] * p.nc[1]);
-    int total = 0; /* upper bound of the member count: own owner cell + band prefixes of the 7 lower neighbours */
+    int kz = 0, ky = 0, kx = 0, total = 0; /* upper bound of the member count: own owner cell + band prefixes of the 7 lower neighbours */
+    if (cid < ncell) {
+        kz = cid % p.nc[2]; ky = (cid / p.nc[2]) % p.nc[1]; kx = cid / (p.nc[2] * p.nc[1]);
 #pragma unroll
-    for (int nb = 0; nb < 8; nb++) {
-        int oc = ((kx + 1 - (nb >> 2)) * p.pnc[1] + (ky + 1 - ((nb >> 1) & 1))) * p.pnc[2] + (kz + 1 - (nb & 1));
-        total += nb == 0 ? p.cell_start[oc + 1] - p.cell_start[oc] : p.band_count[oc];
+        for (int nb = 0; nb < 8; nb++) {
+            int oc = ((kx + 1 - (nb >> 2)) * p.pnc[1] + (ky + 1 - ((nb >> 1) & 1))) * p.pnc[2] + (kz + 1 - (nb & 1));
+            total += nb == 0 ? p.cell_start[oc + 1] - p.cell_start[oc] : p.band_count[oc];
+        }
     }
-    if (total >= 2) { /* one atomic per warp */
-        unsigned peers = __activemask();
-        int leader = __ffs(peers) - 1, lane = threadIdx.x & 31, base = 0;
-        if (lane == leader) base = atomicAdd(p.dl_count, __popc(peers));
-        base = __shfl_sync(peers, base, leader);
+    // one global atomic per block: the list counter is a single address
+    const bool active = total >= 2;
+    const unsigned bal = __ballot_sync(0xffffffffu, active);
+    const int lane = threadIdx.x & 31;
+    int mine = 0;
+    if (lane == 0 && bal) mine = atomicAdd(&s_cnt, __popc(bal));
+    mine = __shfl_sync(0xffffffffu, mine, 0) + __popc(bal & ((1u << lane) - 1));
+    __syncthreads();
+    if (threadIdx.x == 0 && s_cnt) s_base = atomicAdd(p.dl_count, s_cnt);
+    __syncthreads();
+    if (active) {
         int cell = ((kx >> 1) * p.nh[1] + (ky >> 1)) * p.nh[2] + (kz >> 1);
-        write_work_item(p, p.dl + (size_t)(base + __popc(peers & ((1u << lane) - 1))) * AMC_WI, cell, kx, ky, kz);
+        write_work_item(p, p.dl + (size_t)(s_base + mine) * AMC_WI, cell, kx, ky, kz);
     }
 }
 
@@ -718,8 +861,10 @@ __global__ void __launch_bounds__(DET_THREADS, 8) k_detect(const __grid_constant
     if (w >= nwork) return;
     for (int c = tid; c < DET_TAB; c += DET_THREADS) S.head[c] = 0;
     if (tid < 2) S.nmem[tid] = 0;
-    int hn = 0; /* warp 0: the work item after the one published in the other buffer */
-    if (warp == 0) {
+    // the header bookkeeping rides on the last warp: it has the fewest candidates to handle (the tail of the list)
+    const bool hw = warp == DET_THREADS / 32 - 1;
+    int hn = 0; /* header warp: the work item after the one published in the other buffer */
+    if (hw) {
         det_publish(p, S, 0, p.dl[(size_t)w * AMC_WI + lane], lane);
         if (w + stride < nwork) hn = p.dl[(size_t)(w + stride) * AMC_WI + lane];
     }
@@ -734,7 +879,7 @@ __global__ void __launch_bounds__(DET_THREADS, 8) k_detect(const __grid_constant
         }
     }
     unsigned int tests = 0;
-    unsigned long long nref = 0; /* thread 0 */
+    unsigned long long nref = 0; /* header warp, lane 0 */
     const float thr = p.det_thr;
     unsigned int tagw = 0;
     for (int it = 0; w < nwork; it++, w += stride) {
@@ -780,7 +925,7 @@ __global__ void __launch_bounds__(DET_THREADS, 8) k_detect(const __grid_constant
             if (lane == 0 && nm) atomicAdd(&S.nmem[cur], nm);
         }
         const int wn = w + stride;
-        if (warp == 0 && wn < nwork) {
+        if (hw && wn < nwork) {
             det_publish(p, S, nxt, hn, lane);
             if (wn + stride < nwork) hn = p.dl[(size_t)(wn + stride) * AMC_WI + lane];
         }
@@ -808,21 +953,30 @@ __global__ void __launch_bounds__(DET_THREADS, 8) k_detect(const __grid_constant
             c[1] = S.head[b + 1] ^ tagw; c[2] = S.head[b + DET_ROW - 1] ^ tagw;
             c[3] = S.head[b + DET_ROW] ^ tagw; c[4] = S.head[b + DET_ROW + 1] ^ tagw;
             if (c[0] == 0 && min(min(c[1], c[2]), min(c[3], c[4])) >= 0x10000u) continue;
-            const float ax = fx[k], ay = fy[k], az = fz[k];
+            // the non-empty chains (indices < 512) are packed into one word and walked in a single loop
+            unsigned long long pend = c[0];
+            int sh = c[0] ? 9 : 0;
 #pragma unroll
-            for (int n = 0; n < 5; n++) {
-                for (unsigned int e = c[n] < 0x10000u ? c[n] : 0u; e; e = S.next[e - 1]) {
-                    float4 q = S.tile[e - 1];
-                    float ex = q.x - ax, ey = q.y - ay, ez = q.z - az;
-                    dmin = fminf(dmin, fmaf(ez, ez, fmaf(ey, ey, ex * ex)));
-                    tests++;
+            for (int n = 1; n < 5; n++)
+                if (c[n] < 0x10000u) { pend |= (unsigned long long)c[n] << sh; sh += 9; }
+            const float ax = fx[k], ay = fy[k], az = fz[k];
+            for (unsigned int e = 0;;) {
+                if (e == 0) {
+                    if (pend == 0) break;
+                    e = (unsigned int)pend & 511u;
+                    pend >>= 9;
                 }
+                float4 q = S.tile[e - 1];
+                float ex = q.x - ax, ey = q.y - ay, ez = q.z - az;
+                dmin = fminf(dmin, fmaf(ez, ez, fmaf(ey, ey, ex * ex)));
+                tests++;
+                e = S.next[e - 1];
             }
         }
         hit = hit || dmin < thr;
         if (tid == DET_THREADS - 1) S.nmem[nxt] = 0;
         const int any = __syncthreads_or(hit);
-        if (warp == 0) {
+        if (hw) {
             const int *h = S.hdr[cur];
             const int cell = h[0], kx = h[1], ky = h[2], kz = h[3];
             const int g = ((kx & 1) << 2) | ((ky & 1) << 1) | ((kz + p.zoff) & 1);
@@ -841,26 +995,79 @@ __global__ void __launch_bounds__(DET_THREADS, 8) k_detect(const __grid_constant
     }
     tests = __reduce_add_sync(0xffffffffu, tests);
     if (lane == 0 && tests) atomicAdd(&p.stats->checks_exec, (unsigned long long)tests);
-    if (tid == 0 && nref) atomicAdd(&p.stats->checks_ref, nref);
+    if (hw && lane == 0 && nref) atomicAdd(&p.stats->checks_ref, nref);
+}
+
+// members of one reference cell of a colour group -> S.{x,y,z,id,slot,src}[0..S.n): its own register budget
+__device__ __forceinline__ void gather_members(const P &p, CellShared &S, const int group, const int cell)
+{
+    const int tid = threadIdx.x;
+    const Arrays &A = p.a;
+    const double lox = S.org[0], hix = S.hi[0], loy = S.org[1], hiy = S.hi[1], loz = S.org[2], hiz = S.hi[2];
+    {
+            // membership is decided on the live position (Pore:527-530); the 8 ranges are walked as one
+            // flat index space so every thread has independent loads in flight
+            const int total = S.rcum[8];
+            // particles that left their sorted owner cell earlier in this pass and are members of this cell now hang
+            // on the cell's own list (head in cell_active, see esc_link): one load for nearly every cell
+            int esc_head = 0;
+            if (tid == PAIR_THREADS - 1) esc_head = p.cell_active[(size_t)group * p.wl_stride + cell];
+            for (int tb = 0; tb < total; tb += PAIR_K * PAIR_THREADS) { /* PAIR_K candidates per thread in flight: one round trip for most cells */
+                unsigned fl[PAIR_K]; double x[PAIR_K], y[PAIR_K], z[PAIR_K]; int id[PAIR_K];
+#pragma unroll
+                for (int k = 0; k < PAIR_K; k++) {
+                    int t = tb + tid + k * PAIR_THREADS;
+                    if (t < total) {
+                        int nb = 0;
+#pragma unroll
+                        for (int r = 1; r < 8; r++) nb += t >= S.rcum[r];
+                        int s = S.rbeg[nb] + (t - S.rcum[nb]);
+                        fl[k] = A.flag[s]; x[k] = A.x[s]; y[k] = A.y[s]; z[k] = A.z[s]; id[k] = A.id[s];
+                    }
+                }
+                PHASE_MARK(11); /* gather: loads issued */
+#pragma unroll
+                for (int k = 0; k < PAIR_K; k++) {
+                    int t = tb + tid + k * PAIR_THREADS;
+                    bool mem = t < total && !(fl[k] & AMC_FLAG_ESC) && lox < x[k] && x[k] < hix && loy < y[k] && y[k] < hiy && loz < z[k] && z[k] < hiz;
+                    unsigned bal = __ballot_sync(0xffffffffu, mem); /* one shared atomic per warp, not per member */
+                    int base = 0;
+                    if ((tid & 31) == 0 && bal) base = atomicAdd(&S.n, __popc(bal));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (mem) {
+                        int m = base + __popc(bal & ((1u << (tid & 31)) - 1));
+                        if (m < AMC_MAX_MEMBERS) {
+                            int nb = 0;
+#pragma unroll
+                            for (int r = 1; r < 8; r++) nb += t >= S.rcum[r];
+                            S.x[m] = x[k]; S.y[m] = y[k]; S.z[m] = z[k]; S.id[m] = id[k];
+                            S.slot[m] = S.rbeg[nb] + (t - S.rcum[nb]); S.src[m] = -1 - nb;
+                        }
+                    }
+                }
+            }
+            PHASE_MARK(12); /* gather: members stored */
+            for (int v = esc_head; v >= 2;) { /* thread PAIR_THREADS - 1 only */
+                const int e = v - 2;
+                v = p.esc_next[e * 8 + group];
+                if (p.esc_cell[e * 8 + group] != cell) continue; /* the particle moved on since it was linked here */
+                int s = p.esc_slot[e];
+                int k = atomicAdd(&S.n, 1);
+                if (k < AMC_MAX_MEMBERS) { S.x[k] = A.x[s]; S.y[k] = A.y[s]; S.z[k] = A.z[s]; S.id[k] = A.id[s]; S.slot[k] = s; S.src[k] = e; }
+            }
+        }
 }
 
 // one colour group (Pore:522-549): persistent CTAs walk the group's worklist
-__global__ void __launch_bounds__(PAIR_THREADS, 8) k_pairs_group(const __grid_constant__ P p, const int group)
+__global__ void __launch_bounds__(PAIR_THREADS, 6) k_pairs_group(const __grid_constant__ P p, const int group)
 {
     __shared__ CellShared S;
-    __shared__ double s_lo[3], s_hi[3];
-    __shared__ int s_ne;
     const int tid = threadIdx.x;
-    const Arrays &A = p.a;
     const int nwork = p.wl_count[group];
     const int32_t *wl = p.wl + (size_t)group * p.wl_stride * AMC_WI;
     __shared__ __align__(16) int s_hdr[AMC_WI];
-    if (tid == 0) {
-        S.nexec = 0; S.nref = 0;
-        int ne = *p.esc_count; /* entries appended while this group runs belong to later groups */
-        s_ne = ne > p.esc_cap ? p.esc_cap : ne;
-    }
-    for (int c = tid; c < AMC_XBINS; c += PAIR_THREADS) S.sub_cnt[c] = 0; /* kept zero by the scan */
+    if (tid == 0) { S.nexec = 0; S.nref = 0; }
+    for (int c = tid; c < AMC_XBINS + 2; c += PAIR_THREADS) S.head[c] = 0;
     // warp 0 fetches a work item with one coalesced 128-byte load and already has the next one in flight
     // while the CTA works on the current cell
     // Work items are handed out dynamically (one atomic per cell on a per-group ticket) so a CTA that
@@ -868,10 +1075,9 @@ __global__ void __launch_bounds__(PAIR_THREADS, 8) k_pairs_group(const __grid_co
     // current one is processed, which keeps its header load in flight.
     __shared__ int s_w;
     int next_hdr = 0, next_w = nwork;
-    if (tid < AMC_WI) {
-        if (tid == 0) next_w = atomicAdd(&p.wl_next[group], 1);
-        next_w = __shfl_sync(0xffffffffu, next_w, 0);
-        if (next_w < nwork) next_hdr = wl[(size_t)next_w * AMC_WI + tid];
+    if (tid < AMC_WI) { /* the first item is the CTA's own index; further ones are drawn from the ticket counter */
+        next_w = blockIdx.x;
+        next_hdr = wl[(size_t)next_w * AMC_WI + tid]; /* unconditional (the slot exists): in flight together with the count */
         if (tid == 0) s_w = next_w;
     }
     __syncthreads();
@@ -882,9 +1088,11 @@ __global__ void __launch_bounds__(PAIR_THREADS, 8) k_pairs_group(const __grid_co
 #endif
         if (tid < AMC_WI) {
             s_hdr[tid] = next_hdr;
-            if (tid == 0) next_w = atomicAdd(&p.wl_next[group], 1);
-            next_w = __shfl_sync(0xffffffffu, next_w, 0);
-            if (next_w < nwork) next_hdr = wl[(size_t)next_w * AMC_WI + tid];
+            if (nwork > (int)gridDim.x) { /* more items than CTAs: draw the next one */
+                if (tid == 0) next_w = (int)gridDim.x + atomicAdd(&p.wl_next[group], 1);
+                next_w = __shfl_sync(0xffffffffu, next_w, 0);
+                if (next_w < nwork) next_hdr = wl[(size_t)next_w * AMC_WI + tid];
+            } else next_w = nwork;
             __syncwarp();
             if (tid < 8) {
                 S.rbeg[tid] = s_hdr[4 + tid];
@@ -896,11 +1104,12 @@ __global__ void __launch_bounds__(PAIR_THREADS, 8) k_pairs_group(const __grid_co
             if (tid < 3) {
                 const double *d = reinterpret_cast<const double *>(s_hdr + 20);
                 double lo = d[2 * tid], hi = d[2 * tid + 1];
-                s_lo[tid] = lo; s_hi[tid] = hi;
-                if (tid == 0) { /* slabs along x, at least 1.05 collision ranges wide */
-                    int nb = (int)fmin((double)AMC_XBINS, floor((hi - lo) / (1.05 * p.cr)));
-                    S.nb = nb; S.sub_ok = nb >= 2;
-                    S.lo[0] = lo; S.inv_s[0] = (double)nb / (hi - lo);
+                S.org[tid] = lo; S.hi[tid] = hi;
+                if (tid == 0) { /* slabs along x, at least 1.05 filter radii wide */
+                    float wd = (float)(hi - lo);
+                    int nb = (int)fminf((float)AMC_XBINS, floorf(wd / p.det_w));
+                    if (nb < 1) nb = 1;
+                    S.nb = nb; S.inv_w = (float)nb / wd;
                     S.rcum[0] = 0; S.n = 0; S.ncand = 0; S.kx = s_hdr[1]; S.ky = s_hdr[2]; S.kz = s_hdr[3];
                 }
             }
@@ -908,41 +1117,7 @@ __global__ void __launch_bounds__(PAIR_THREADS, 8) k_pairs_group(const __grid_co
         __syncthreads();
         PHASE_MARK(0); /* header */
         const int cell = s_hdr[0];
-        const double lox = s_lo[0], hix = s_hi[0], loy = s_lo[1], hiy = s_hi[1], loz = s_lo[2], hiz = s_hi[2];
-        {
-            // membership is decided on the live position (Pore:527-530); the 8 ranges are walked as one
-            // flat index space so every thread has independent loads in flight
-            const int total = S.rcum[8];
-            for (int t0 = tid; t0 < total; t0 += 3 * PAIR_THREADS) { /* three candidates per thread in flight: one round trip for most cells */
-                unsigned fl[3]; double x[3], y[3], z[3]; int id[3], sl[3], nbk[3];
-#pragma unroll
-                for (int k = 0; k < 3; k++) {
-                    int t = t0 + k * PAIR_THREADS;
-                    if (t < total) {
-                        int nb = 0;
-#pragma unroll
-                        for (int r = 1; r < 8; r++) nb += t >= S.rcum[r];
-                        int s = S.rbeg[nb] + (t - S.rcum[nb]);
-                        fl[k] = A.flag[s]; x[k] = A.x[s]; y[k] = A.y[s]; z[k] = A.z[s]; id[k] = A.id[s];
-                        sl[k] = s; nbk[k] = nb;
-                    }
-                }
-#pragma unroll
-                for (int k = 0; k < 3; k++) {
-                    int t = t0 + k * PAIR_THREADS;
-                    if (t < total && !(fl[k] & AMC_FLAG_ESC) && lox < x[k] && x[k] < hix && loy < y[k] && y[k] < hiy && loz < z[k] && z[k] < hiz) {
-                        int m = atomicAdd(&S.n, 1);
-                        if (m < AMC_MAX_MEMBERS) { S.x[m] = x[k]; S.y[m] = y[k]; S.z[m] = z[k]; S.id[m] = id[k]; S.slot[m] = sl[k]; S.src[m] = -1 - nbk[k]; }
-                    }
-                }
-            }
-            for (int e = tid; e < s_ne; e += PAIR_THREADS) { /* particles that left their sorted owner cell earlier in this pass */
-                if (p.esc_cell[e * 8 + group] != cell) continue;
-                int s = p.esc_slot[e];
-                int k = atomicAdd(&S.n, 1);
-                if (k < AMC_MAX_MEMBERS) { S.x[k] = A.x[s]; S.y[k] = A.y[s]; S.z[k] = A.z[s]; S.id[k] = A.id[s]; S.slot[k] = s; S.src[k] = e; }
-            }
-        }
+        gather_members(p, S, group, cell);
         __syncthreads();
         PHASE_MARK(1); /* gather */
         if (S.n > AMC_MAX_MEMBERS) {
@@ -980,6 +1155,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_cube_sweep(const __grid_const
     const Arrays &A = p.a;
     int32_t *lx = p.key, *lxy = p.rank;
     if (tid == 0) { S.nexec = 0; S.nref = 0; }
+    for (int c = tid; c < AMC_XBINS + 2; c += SWEEP_THREADS) S.head[c] = 0;
     for (int xl = 0; xl < p.nc[0]; xl++) {
         if (tid == 0) nx = 0;
         __syncthreads();
@@ -1004,7 +1180,13 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_cube_sweep(const __grid_const
             }
             __syncthreads();
             for (int zl = 0; zl < p.nc[2]; zl++) {
-                if (tid == 0) { S.n = 0; S.ncand = 0; S.sub_ok = 0; }
+                if (tid == 0) {
+                    S.n = 0; S.ncand = 0; S.org[0] = p.lo[0][xl]; S.org[1] = p.lo[1][yl]; S.org[2] = p.lo[2][zl];
+                    float wd = (float)(p.edge[0][xl + 1] - p.lo[0][xl]);
+                    int nb = (int)fminf((float)AMC_XBINS, floorf(wd / p.det_w));
+                    if (nb < 1) nb = 1;
+                    S.nb = nb; S.inv_w = (float)nb / wd;
+                }
                 __syncthreads();
                 {
                     double lo = p.lo[2][zl], hi = p.edge[2][zl + 1];
@@ -1197,10 +1379,10 @@ __global__ void __launch_bounds__(128) k_bnd_apply(const __grid_constant__ P p)
     const int s = s_slot;
     if (s < 0) continue;
     const unsigned fl = A.flag[s];
-    if (fl & AMC_FLAG_ESC) { // already on the escaped list: find its entry
+    if (fl & AMC_FLAG_ESC) { // already on the escaped list: find its (latest) entry
         int ne = min(*p.esc_count, p.esc_cap);
         for (int e = tid; e < ne; e += blockDim.x)
-            if (p.esc_slot[e] == s) s_esc = e;
+            if (p.esc_slot[e] == s) atomicMax(&s_esc, e);
     }
     __syncthreads();
     if (tid != 0) continue;
@@ -1210,27 +1392,27 @@ __global__ void __launch_bounds__(128) k_bnd_apply(const __grid_constant__ P p)
     unsigned nf = (fl & ~AMC_FLAG_PATH) | ((unsigned)r[11] & AMC_FLAG_PATH);
     int o[3];
     int32_t k = owner_key(p, x, y, z, o);
-    int e = s_esc;
-    bool findable = false;
-    if (e < 0) {
+    const int e_old = s_esc;
+    int e = -1;
+    bool findable = false, ok = true;
+    if (e_old < 0) {
         int32_t sk = p.skey[s];
         findable = sk >= 0 && k == sk && (s < p.cell_start[sk] + p.band_count[sk] || !any_band(p, x, y, z, o));
-        if (!findable) {
-            e = atomicAdd(p.esc_count, 1);
-            if (e >= p.esc_cap) { atomicAdd(&p.stats->esc_overflow, 1ull); e = -1; }
-            else { p.esc_slot[e] = s; nf |= AMC_FLAG_ESC; }
-        }
+    }
+    if (!findable) {
+        e = atomicAdd(p.esc_count, 1);
+        if (e >= p.esc_cap) { atomicAdd(&p.stats->esc_overflow, 1ull); ok = false; }
+        else { p.esc_slot[e] = s; nf |= AMC_FLAG_ESC; }
     }
     // the cells of the remaining groups that hold this particle must be visited (k_detect did not see this position)
-    if (findable || e >= 0)
+    if (ok)
         for (int g2 = p.group_done + 1; g2 < 8; g2++) {
             int cx = member_axis(p.edge[0], p.lo[0], p.nc[0], o[0], (g2 >> 2) & 1, x);
             int cy = member_axis(p.edge[1], p.lo[1], p.nc[1], o[1], (g2 >> 1) & 1, y);
             int cz = member_axis(p.edge[2], p.lo[2], p.nc[2], o[2], (g2 ^ p.zoff) & 1, z);
             int32_t cc = (cx < 0 || cy < 0 || cz < 0) ? -1 : ((cx >> 1) * p.nh[1] + (cy >> 1)) * p.nh[2] + (cz >> 1);
-            if (!findable) p.esc_cell[e * 8 + g2] = cc;
-            if (cc >= 0 && atomicExch(&p.cell_active[(size_t)g2 * p.wl_stride + cc], 1) == 0)
-                write_work_item(p, p.wl + ((size_t)g2 * p.wl_stride + atomicAdd(&p.wl_count[g2], 1)) * AMC_WI, cc, cx, cy, cz);
+            if (e_old >= 0) p.esc_cell[e_old * 8 + g2] = -1;
+            esc_link(p, g2, cc, cx, cy, cz, findable ? -1 : e);
         }
     A.flag[s] = (uint8_t)nf;
     }

@@ -23,7 +23,7 @@ sim.lib.amc_debug_phase_clocks(out, 1)
 sim.step(4)
 sim.lib.amc_debug_phase_clocks(out, 0)
 ms, _ = sim.last_timing()
-names = ["header", "gather", "bin", "scan", "order", "search", "-", "resolve+tail"]
+names = ["header", "gather:barrier", "chain:barrier", "-", "-", "walk:barrier+zero", "pick", "retest+tail", "resolve_pair", "chain:own", "walk:own", "gather:issue", "gather:wait+store"]
 visits = out[15]
 print(kind, len(state[0]), "visits/step", visits / 4, "pairs ms/step", ms[2] / 4)
 tot = 0
