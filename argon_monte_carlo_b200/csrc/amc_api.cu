@@ -44,6 +44,7 @@ struct amc_handle {
     double last_ms[5] = {0, 0, 0, 0, 0};
     std::vector<cudaEvent_t> det_events; // two per step of the last amc_step chunk: around k_detect
     int det_slot = -1;                   // step of the chunk run_pairs is recording for (-1: none)
+    bool slab_det_pending = false;       // slab mode: events around k_detect recorded, not yet read
     double last_detect_ms = 0;
     int64_t last_launches = 0;
     std::string error;
@@ -969,7 +970,13 @@ extern "C" int amc_slab_pairs_begin(amc_handle *h, int32_t pre_round)
     CK(cudaMemsetAsync(p.cell_active, 0, (size_t)p.wl_stride * 8 * sizeof(int32_t), h->stream));
     CK(cudaMemsetAsync(p.cell_n, 0, (size_t)p.wl_stride * 8 * sizeof(int32_t), h->stream));
     k_build_worklist<<<grid_for(ncell, ADVECT_THREADS), ADVECT_THREADS, 0, h->stream>>>(p);
+    if (h->det_events.size() < 2) {
+        for (int k = 0; k < 2; k++) { cudaEvent_t e; CK(cudaEventCreate(&e)); h->det_events.push_back(e); }
+    }
+    CK(cudaEventRecord(h->det_events[0], h->stream));
     if (h->n) k_detect<<<h->det_grid, DET_THREADS, 0, h->stream>>>(p);
+    CK(cudaEventRecord(h->det_events[1], h->stream));
+    h->slab_det_pending = true;
     if (pre_round) k_bnd_pack<<<2, ADVECT_THREADS, 0, h->stream>>>(p); // immigrants that landed in the top band; else they travel after group 0
     CK(cudaGetLastError());
     return AMC_OK;
@@ -1012,6 +1019,12 @@ extern "C" int amc_slab_finish(amc_handle *h, amc_step_stats *stats)
     CK(cudaMemcpyAsync(ovf, h->d_slab_overflow, sizeof(ovf), cudaMemcpyDeviceToHost, h->stream));
     rc = phase_end(h, stats);
     if (rc != AMC_OK) return rc;
+    if (h->slab_det_pending) { /* slab mode: the detection time accumulates over steps (callers take differences) */
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, h->det_events[0], h->det_events[1]));
+        h->last_detect_ms += ms;
+        h->slab_det_pending = false;
+    }
     if ((rc = slab_overflow_error(h, ovf)) != AMC_OK) return rc;
     h->n += nf; // foreign copies appended behind the sorted particles; dropped by the next amc_slab_advect
     p.n = h->n;

@@ -201,7 +201,7 @@ __device__ __forceinline__ void advance_particle(const P &p, Part &q, const int3
 
 // pass 1 of the fused step: owner cell of the position each particle will have after the step, and its
 // rank inside that cell (band particles first, see k_advect)
-__global__ void __launch_bounds__(ADVECT_THREADS, 4) k_keys(const __grid_constant__ P p, const int phase)
+__global__ void __launch_bounds__(ADVECT_THREADS, 6) k_keys(const __grid_constant__ P p, const int phase)
 {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= p.n) return;
@@ -802,8 +802,13 @@ __global__ void __launch_bounds__(ADVECT_THREADS) k_build_worklist(const __grid_
 #define DET_THREADS 128
 #define DET_K 3     /* candidates per thread: cells with more than DET_K * DET_THREADS candidates are flagged */
 #define DET_CAND (DET_K * DET_THREADS)
-#define DET_NB 64   /* bins per axis, at most */
-#define DET_ROW (DET_NB + 2)                /* one empty bin on either side of a row */
+#define DET_NB 64   /* bins along x, at most */
+#ifndef DET_NBY
+#define DET_NBY 64  /* bins along y, at most */
+#define DET_YF 1.0f /* width of a y bin in units of the minimal bin width */
+#define DET_OCC 8   /* resident CTAs per SM the kernel is compiled for */
+#endif
+#define DET_ROW (DET_NBY + 2)               /* one empty bin on either side of a row */
 #define DET_TAB ((DET_NB + 1) * DET_ROW)    /* one empty row behind the last */
 
 struct DetShared {
@@ -831,7 +836,7 @@ __device__ __forceinline__ void det_publish(const P &p, DetShared &S, int buf, i
         if (lane < 2) { /* lane 0: bins along x, lane 1: along y */
             const double *d = reinterpret_cast<const double *>(&S.hdr[buf][20]);
             float wd = (float)(d[2 * lane + 1] - d[2 * lane]);
-            int nb = (int)fminf((float)DET_NB, floorf(wd / p.det_w));
+            int nb = lane == 0 ? (int)fminf((float)DET_NB, floorf(wd / p.det_w)) : (int)fminf((float)DET_NBY, floorf(wd / (DET_YF * p.det_w)));
             if (nb < 1) nb = 1;
             if (lane == 0) { S.nbx[buf] = nb; S.inv_wx[buf] = (float)nb / wd; S.rcum[buf][0] = 0; }
             else { S.nby[buf] = nb; S.inv_wy[buf] = (float)nb / wd; }
@@ -850,7 +855,7 @@ __device__ __forceinline__ int det_slot(const DetShared &S, int buf, int t)
     return S.rbeg[buf][nb] + (t - S.rcum[buf][nb]);
 }
 
-__global__ void __launch_bounds__(DET_THREADS, 8) k_detect(const __grid_constant__ P p)
+__global__ void __launch_bounds__(DET_THREADS, DET_OCC) k_detect(const __grid_constant__ P p)
 {
     __shared__ DetShared S;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;

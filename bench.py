@@ -5,8 +5,8 @@ collision-resolved particle-steps/s at 1/2/4/8 B200 + fraction of the HBM roofli
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
                   [--workload temp_pore|cube] [--particles-per-gpu M]
 
-One "step" = one whole timestep (drift, walls, recapture, cell sort, the 8-colour-group
-particle-particle pass, recapture, MFP / momentum bookkeeping) over all particles of the job.
+One "step" = one whole timestep (drift, walls, recapture, cell sort, pair detection, the ordered
+8-colour-group resolution, recapture, MFP / momentum bookkeeping) over all particles of the job.
 
 Workload (config.workload): a synthetic Maxwellian argon gas in the energized thruster-pore
 geometry of Temperature_Pore_MC.py, every length scaled so that each GPU holds
@@ -37,6 +37,7 @@ sys.path.insert(0, ROOT)
 
 B_STEP = 162.0      # algorithmic bytes per particle-step, fp64 state read + written once
 B_PAIR = 32.0       # algorithmic bytes per particle for the pair kernel: 3 x f64 position + cell header
+NCU_DETECT_TRAFFIC = 314.3e6   # dram__bytes_read.sum + dram__bytes_write.sum of one k_detect launch at 12,499,989 particles
 
 
 def measured_peaks():
@@ -122,7 +123,8 @@ def run_cube(args, world, rank, local, dev, barrier, max_over_ranks, sum_over_ra
         barrier()
         sim.step_quiet(args.steps)
         ms = sim.last_timing()[0]
-        dev_ms, phases = ms[4], {"advect_walls": ms[0] / args.steps, "cell_sort": ms[1] / args.steps, "pairs": ms[2] / args.steps}
+        dev_ms, phases = ms[4], {"keys": ms[0] / args.steps, "scan_scatter_advect": ms[1] / args.steps, "pairs": ms[2] / args.steps,
+                                 "pair_detect": sim.last_detect_ms() / args.steps}
         sim.close()
     else:
         cuts = slab.balanced_cuts(state[2], grid.edge[2], world)
@@ -214,15 +216,20 @@ def run_ours(args):
     total_particles = sum_over_ranks(float(n))
     value = total_particles * args.steps / (dev_ms * 1e-3)
     pair_ms = ms[2] / args.steps
+    det_ms = sim.last_detect_ms() / args.steps
     checks_ref = float(np.mean([s["pair_checks_ref"] for s in stats]))
+    checks_exec = float(np.mean([s["pair_checks_exec"] for s in stats]))
     collisions = float(np.mean([s["collisions"] for s in stats]))
-    # per launch: algorithmic bytes = 32 B x particles / 8 colour groups, duration = pair time / 8; traffic from the
-    # ncu --set full capture of this workload (profiles/r1_v5_ncu_full_summary.csv: 87.3 MB read + 3.6 MB written)
-    roofline = {"bound": "hbm", "kernel": "k_pairs_group (8 launches per step)",
-                "achieved": B_PAIR * n / (pair_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                "peak_source": peak_src, "algorithmic_bytes_per_launch": B_PAIR * n / 8,
-                "avg_launch_ms": pair_ms / 8,
-                "traffic": 90.9e6 * n / 12499989 if abs(n - 12499989) < 1e5 else None}
+    # dominant pair kernel: k_detect, ONE launch per step over every reference cell (the neighbour search; the
+    # ordered resolution that follows only visits the ~0.05 % of cells it flags).  Per launch: algorithmic bytes =
+    # 32 B x particles (3 x f64 position + cell header), duration = CUDA events around the launch on the
+    # handle's stream; traffic = dram read + write of one launch from the ncu --set full capture of this workload
+    # (profiles/r1_v7_ncu_full_summary.csv)
+    roofline = {"bound": "hbm", "kernel": "k_detect (pair detection, 1 launch per step)",
+                "achieved": B_PAIR * n / (det_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": B_PAIR * n,
+                "avg_launch_ms": det_ms,
+                "traffic": NCU_DETECT_TRAFFIC * n / 12499989 if abs(n - 12499989) < 1e5 else None}
     roofline["frac"] = roofline["achieved"] / hbm_peak
     whole = {"achieved": B_STEP * n * args.steps / (ms[4] * 1e-3) / 1e9, "unit": "GB/s"}
     whole["frac"] = whole["achieved"] / hbm_peak
@@ -259,9 +266,10 @@ def run_ours(args):
                    "l2": "inputs larger than L2"},
         "clocks": clk, "e2e": e2e, "gpu_launches": launches,
         "roofline": roofline, "roofline_whole_step": whole,
-        "phases_ms_per_step": {"advect_walls": ms[0] / args.steps, "cell_sort": ms[1] / args.steps,
-                               "pairs": ms[2] / args.steps, "recapture": ms[3] / args.steps},
-        "collision_checks_per_s": {"reference_equivalent": checks_ref * world / (dev_ms / args.steps * 1e-3)},
+        "phases_ms_per_step": {"keys": ms[0] / args.steps, "scan_scatter_advect": ms[1] / args.steps,
+                               "pair_detect": det_ms, "pair_resolve": pair_ms - det_ms, "recapture": ms[3] / args.steps},
+        "collision_checks_per_s": {"reference_equivalent": checks_ref * world / (dev_ms / args.steps * 1e-3),
+                                   "executed": checks_exec * world / (dev_ms / args.steps * 1e-3)},
         "collisions_per_step": collisions, "wall_s": wall,
     }
 
@@ -299,6 +307,7 @@ def run_slabs(args, world, rank, local, dev, hbm_peak, peak_src, barrier, max_ov
     clocks = ClockSampler(local)
     barrier()
     clocks.start()
+    det0 = sim.ranks[0].sim.last_detect_ms()
     t0 = time.perf_counter()
     stats = sim.step(args.steps, reduce=False, timing=True)
     wall = time.perf_counter() - t0
@@ -317,9 +326,10 @@ def run_slabs(args, world, rank, local, dev, hbm_peak, peak_src, barrier, max_ov
     checks_ref = sum_over_ranks(float(np.mean([s["pair_checks_ref"] for s in stats])))
     collisions = sum_over_ranks(float(np.mean([s["collisions"] for s in stats])))
     n_max = max_over_ranks(float(n))
-    roofline = {"bound": "hbm", "kernel": "k_pairs_group (8 launches per step, incl. the per-group boundary hand-over)",
-                "achieved": B_PAIR * n / (pair_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                "peak_source": peak_src, "traffic": None}
+    det_ms = max_over_ranks((sim.ranks[0].sim.last_detect_ms() - det0) / args.steps)
+    roofline = {"bound": "hbm", "kernel": "k_detect (pair detection, 1 launch per step and rank; slowest rank)",
+                "achieved": B_PAIR * n_max / (det_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                "peak_source": peak_src, "avg_launch_ms": det_ms, "traffic": None}
     roofline["frac"] = roofline["achieved"] / hbm_peak
     # e2e: host buffers in and out every step
     keys = ("x", "y", "z", "vx", "vy", "vz", "dist", "dist_x", "dist_y", "dist_z")
@@ -353,7 +363,8 @@ def run_slabs(args, world, rank, local, dev, hbm_peak, peak_src, barrier, max_ov
         "clocks": clk, "e2e": e2e, "gpu_launches": 54 * args.steps,
         "roofline": roofline,
         "phases_ms_per_step": {"advect_walls": ms[0] / args.steps, "exchange_sort": ms[1] / args.steps,
-                               "pairs_and_handover": ms[2] / args.steps, "finish": ms[3] / args.steps},
+                               "pairs_and_handover": ms[2] / args.steps, "pair_detect_slowest_rank": det_ms,
+                               "finish": ms[3] / args.steps},
         "collision_checks_per_s": {"reference_equivalent": checks_ref / (dev_ms / args.steps * 1e-3)},
         "collisions_per_step": collisions, "wall_s": wall, "resident_particles": int(n_now),
         "per_rank": {"columns": ["advect_walls_ms", "exchange_sort_ms", "pairs_and_handover_ms", "finish_ms", "particles"],
@@ -387,7 +398,7 @@ def bench_pore_ref(args, hbm_peak):
     sim.close()
     return {"workload": "pore_ref: Open_Air_Pore_MC.py, N=%d, seeds 17, L2 flushed between timed steps" % n,
             "value": n * k / (tot[4] * 1e-3), "unit": "particle-steps/s", "ms_per_step": tot[4] / k,
-            "phases_ms_per_step": {"advect_walls": tot[0] / k, "cell_sort": tot[1] / k, "pairs": tot[2] / k,
+            "phases_ms_per_step": {"keys": tot[0] / k, "scan_scatter_advect": tot[1] / k, "pairs": tot[2] / k,
                                    "recapture": tot[3] / k},
             "launches_per_step": launches, "steps": k}
 

@@ -188,7 +188,8 @@ int amc_set_step_index(amc_handle *h, int64_t step);
 int amc_last_timing(amc_handle *h, double ms[5], int64_t *launches);
 
 /* device time (ms, summed over the steps of the last amc_step call) of the detection kernel alone (k_detect: the
- * neighbour search over every reference cell, Pore:168-174); the rest of [2] above is the ordered resolution. */
+ * neighbour search over every reference cell, Pore:168-174); the rest of [2] above is the ordered resolution.
+ * Handles driven through the amc_slab_* entry points accumulate this time over steps instead. */
 int amc_last_detect_ms(amc_handle *h, double *ms);
 
 /* ------------------------------------------------------------------------------------------------
