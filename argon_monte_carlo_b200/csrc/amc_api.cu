@@ -44,6 +44,7 @@ struct amc_handle {
     double last_ms[5] = {0, 0, 0, 0, 0};
     std::vector<cudaEvent_t> det_events; // two per step of the last amc_step chunk: around k_detect
     int det_slot = -1;                   // step of the chunk run_pairs is recording for (-1: none)
+    int slab_phase = 0;                  // slab mode: PH_* bits of the step between amc_slab_advect and amc_slab_sort
     bool slab_det_pending = false;       // slab mode: events around k_detect recorded, not yet read
     double last_detect_ms = 0;
     int64_t last_launches = 0;
@@ -469,13 +470,13 @@ extern "C" int amc_step(amc_handle *h, int32_t n_steps, amc_step_stats *stats)
                 } else { // fused: keys of the post-step positions, then the step itself on the way to the sorted slot
                     CK(cudaMemsetAsync(p.band_count, 0, (h->n_buckets + 1) * sizeof(int32_t), h->stream));
                     CK(cudaMemsetAsync(p.rest_count, 0, (h->n_buckets + 1) * sizeof(int32_t), h->stream));
-                    k_keys<<<grid_for(h->n, ADVECT_THREADS), ADVECT_THREADS, 0, h->stream>>>(p, phase);
+                    k_keys<false><<<grid_for(h->n, ADVECT_THREADS), ADVECT_THREADS, 0, h->stream>>>(p, phase);
                     CK(cudaEventRecord(h->events[4 * s + 1], h->stream));
                     int m = h->n_buckets, ntiles = (m + SCAN_TILE - 1) / SCAN_TILE;
                     k_scan_tiles<<<ntiles, SCAN_THREADS, 0, h->stream>>>(p.band_count, p.rest_count, p.cell_start, h->d_tile_sums, m);
                     k_scan_sums<<<1, SCAN_THREADS, 0, h->stream>>>(h->d_tile_sums, ntiles);
                     k_scan_add<<<ntiles, SCAN_THREADS, 0, h->stream>>>(p.cell_start, h->d_tile_sums, m, (int32_t)h->n);
-                    k_scatter_advect<<<grid_for(h->n, ADVECT_THREADS), ADVECT_THREADS, 0, h->stream>>>(p, phase);
+                    k_scatter_advect<false><<<grid_for(h->n, ADVECT_THREADS), ADVECT_THREADS, 0, h->stream>>>(p, phase);
                     CK(cudaGetLastError());
                     std::swap(p.a, p.b);
                     h->last_launches += 5;
@@ -881,7 +882,7 @@ extern "C" int amc_slab_enable(amc_handle *h, const amc_slab_config *c)
     p.xf_count = h->d_counters; p.n_in = h->d_counters + c->nranks; p.bnd_n = h->d_counters + c->nranks + 1;
     p.rel_count = h->d_counters + c->nranks + 3; p.n_foreign = h->d_counters + c->nranks + 4;
     ALLOC(p.bnd_dirty[0], p.bnd_cap); ALLOC(p.bnd_dirty[1], p.bnd_cap);
-    ALLOC(p.rel_id, p.rel_cap); ALLOC(p.rel_slot, p.rel_cap); ALLOC(p.skey, h->cap);
+    ALLOC(p.rel_id, p.rel_cap); ALLOC(p.rel_slot, p.rel_cap); ALLOC(p.skey, h->cap); ALLOC(p.aux, h->cap);
     ALLOC(h->d_slab_overflow, 4);
     CK(cudaMemset(h->d_slab_overflow, 0, 4 * sizeof(unsigned long long)));
     p.slab_overflow = h->d_slab_overflow;
@@ -920,8 +921,8 @@ extern "C" int amc_slab_advect(amc_handle *h)
     CK(cudaMemsetAsync(p.rel_id, 0xff, (size_t)p.rel_cap * sizeof(int32_t), h->stream));
     CK(cudaMemsetAsync(p.band_count, 0, (h->n_buckets + 1) * sizeof(int32_t), h->stream));
     CK(cudaMemsetAsync(p.rest_count, 0, (h->n_buckets + 1) * sizeof(int32_t), h->stream));
-    int phase = PH_DRIFT | PH_WALLS | (p.kind != AMC_KIND_CUBE ? PH_RECAP : 0) | PH_KEYS;
-    if (h->n) k_advect<<<grid_for(h->n, ADVECT_THREADS), ADVECT_THREADS, 0, h->stream>>>(p, phase);
+    h->slab_phase = PH_DRIFT | PH_WALLS | (p.kind != AMC_KIND_CUBE ? PH_RECAP : 0);
+    if (h->n) k_keys<true><<<grid_for(h->n, ADVECT_THREADS), ADVECT_THREADS, 0, h->stream>>>(p, h->slab_phase);
     k_xfer_headers<<<1, 32, 0, h->stream>>>(p);
     CK(cudaGetLastError());
     return AMC_OK;
@@ -941,7 +942,7 @@ extern "C" int amc_slab_sort(amc_handle *h, int64_t *n_resident)
     k_scan_tiles<<<ntiles, SCAN_THREADS, 0, h->stream>>>(p.band_count, p.rest_count, p.cell_start, h->d_tile_sums, m);
     k_scan_sums<<<1, SCAN_THREADS, 0, h->stream>>>(h->d_tile_sums, ntiles);
     k_scan_add<<<ntiles, SCAN_THREADS, 0, h->stream>>>(p.cell_start, h->d_tile_sums, m, 0);
-    if (bound) k_scatter<<<grid_for(bound, ADVECT_THREADS), ADVECT_THREADS, 0, h->stream>>>(p);
+    if (bound) k_scatter_advect<true><<<grid_for(bound, ADVECT_THREADS), ADVECT_THREADS, 0, h->stream>>>(p, h->slab_phase);
     CK(cudaGetLastError());
     std::swap(p.a, p.b);
     int32_t counts[2] = {0, 0}; // resident = start of the GONE bucket; n_in for the capacity check

@@ -28,6 +28,10 @@
 #define AMC_XBINS 64         /* slabs along x of the in-CTA neighbour search (multiple of 32) */
 #define AMC_SUB_MIN_N 48     /* below this many members the plain all-pairs scan is cheaper */
 
+/* how much of a timestep's per-particle work a kernel carries out (advance_particle and the wall helpers):
+   DRY: only what decides the final position; LIVE: everything; QUIET: the full state update, but no counters,
+   completed paths or accumulators (the live run of the same particle records them) */
+enum { AMC_DRY = 0, AMC_LIVE = 1, AMC_QUIET = 2 };
 enum { PH_DRIFT = 1, PH_WALLS = 2, PH_RECAP = 4, PH_KEYS = 8, PH_SAVE_PRIOR = 16, PH_LOAD_PRIOR = 32, PH_RECAP_POST = 64 };
 
 struct Arrays {
@@ -117,6 +121,7 @@ struct P {
     int32_t *rel_id, *rel_slot, *rel_count; /* open-addressing hash: particles a neighbour may send updates for, id -> slot */
     int32_t rel_cap;          /* power of two; rel_id[] == -1: empty */
     int32_t *skey;            /* owner key each slot was sorted into (-1: appended foreign copy) */
+    uint8_t *aux;             /* per slot, k_keys -> k_scatter_advect: AUX_* bits of the slab protocol */
     int32_t *n_foreign;       /* foreign copies appended after the sort */
     int32_t foreign_cap;
     int32_t group_done;       /* last finished colour group (-1 before the first) */
@@ -192,11 +197,12 @@ struct Part {
 
 // MFP bookkeeping shared by walls and pair collisions (Pore:274-284, 324-335, 186-199): a particle
 // that already finished a first collision completes a path of |path - |speed*t||, else it is flagged.
-template <bool LIVE = true>
+template <int MODE = 1>
 __device__ __forceinline__ void mfp_record(const P &p, double d, double dx, double dy, double dz, uint32_t &flag,
                                            double vx, double vy, double vz, double t)
 {
-    if (!LIVE) return; /* dry run (k_keys): only the final position matters */
+    if (MODE == AMC_DRY) return;                             /* only the final position matters */
+    if (MODE == AMC_QUIET) { flag |= AMC_FLAG_PATH; return; } /* state as in the live run, nothing recorded */
     if (flag & AMC_FLAG_PATH) {
         double sp = sqrt((vx * vx + vy * vy) + vz * vz);
         emit_path(p, fabs(d - fabs(sp * t)), fabs(dx - fabs(vx * t)), fabs(dy - fabs(vy * t)), fabs(dz - fabs(vz * t)));
@@ -231,24 +237,24 @@ __device__ __forceinline__ void reflect_xy(Part &q, double Rc, double t)
 }
 
 // hit_cylinder_side_wall, Pore:294-348
-template <bool LIVE = true>
+template <int MODE = 1>
 __device__ __forceinline__ void pore_side_wall(const P &p, Part &q, double Rc)
 {
     double t;
-    if (!side_quadratic(q.x, q.y, q.vx, q.vy, Rc, t)) { if (LIVE) atomicAdd(&p.stats->errors, 1ull); return; }
+    if (!side_quadratic(q.x, q.y, q.vx, q.vy, Rc, t)) { if (MODE == AMC_LIVE) atomicAdd(&p.stats->errors, 1ull); return; }
     double vx = q.vx, vy = q.vy, vz = q.vz;
-    mfp_record<LIVE>(p, q.d, q.dx, q.dy, q.dz, q.flag, vx, vy, vz, t);
+    mfp_record<MODE>(p, q.d, q.dx, q.dy, q.dz, q.flag, vx, vy, vz, t);
     reflect_xy(q, Rc, t);
     q.d = fabs(sqrt((q.vx * q.vx + q.vy * q.vy) + vz * vz) * t);
     q.dx = fabs(q.vx * t); q.dy = fabs(q.vy * t); q.dz = fabs(vz * t);
 }
 
 // hit_vertical_wall, Pore:257-292
-template <bool LIVE = true>
+template <int MODE = 1>
 __device__ __forceinline__ void pore_plane_wall(const P &p, Part &q, double zp)
 {
     double t = (q.z - zp) / q.vz;
-    mfp_record<LIVE>(p, q.d, q.dx, q.dy, q.dz, q.flag, q.vx, q.vy, q.vz, t);
+    mfp_record<MODE>(p, q.d, q.dx, q.dy, q.dz, q.flag, q.vx, q.vy, q.vz, t);
     q.d = fabs(sqrt((q.vx * q.vx + q.vy * q.vy) + q.vz * q.vz) * t);
     q.dx = fabs(q.vx * t); q.dy = fabs(q.vy * t); q.dz = fabs(q.vz * t);
     q.vz = -q.vz;
@@ -257,23 +263,23 @@ __device__ __forceinline__ void pore_plane_wall(const P &p, Part &q, double zp)
 
 // Pore wall cases 1..6 against the progressively mutated particle (Pore:442-485); returns hit bits.
 // `np.sqrt(x**2 + y**2) > R` is evaluated as `x*x + y*y > gt_R` (exactly equivalent, see P).
-template <bool LIVE = true>
+template <int MODE = 1>
 __device__ __forceinline__ uint32_t pore_walls(const P &p, Part &q)
 {
     const amc_geom &g = p.g;
     uint32_t bits = 0;
-    if (q.x * q.x + q.y * q.y > p.gt_Roa) { bits |= 1u << 0; pore_side_wall<LIVE>(p, q, g.R_oa_c); }
-    if (q.z < 0) { bits |= 1u << 1; pore_plane_wall<LIVE>(p, q, 0.0); }
-    if (q.z > g.H) { bits |= 1u << 2; pore_plane_wall<LIVE>(p, q, g.H); }
-    if (q.pz > g.z_cold && q.z < g.z_cold && q.x * q.x + q.y * q.y > p.gt_Rp) { bits |= 1u << 3; pore_plane_wall<LIVE>(p, q, g.z_cold); }
-    if (q.pz < g.oah && q.z > g.oah && q.x * q.x + q.y * q.y > p.gt_Rp) { bits |= 1u << 4; pore_plane_wall<LIVE>(p, q, g.oah); }
+    if (q.x * q.x + q.y * q.y > p.gt_Roa) { bits |= 1u << 0; pore_side_wall<MODE>(p, q, g.R_oa_c); }
+    if (q.z < 0) { bits |= 1u << 1; pore_plane_wall<MODE>(p, q, 0.0); }
+    if (q.z > g.H) { bits |= 1u << 2; pore_plane_wall<MODE>(p, q, g.H); }
+    if (q.pz > g.z_cold && q.z < g.z_cold && q.x * q.x + q.y * q.y > p.gt_Rp) { bits |= 1u << 3; pore_plane_wall<MODE>(p, q, g.z_cold); }
+    if (q.pz < g.oah && q.z > g.oah && q.x * q.x + q.y * q.y > p.gt_Rp) { bits |= 1u << 4; pore_plane_wall<MODE>(p, q, g.oah); }
     double pr2 = q.px * q.px + q.py * q.py;
     bool pz_in_gap = q.pz < g.z_gt_pore && q.pz > g.z_gb;
-    if (pz_in_gap && pr2 < p.lt_Rg && q.x * q.x + q.y * q.y > p.gt_Rg) { bits |= 1u << 5; pore_side_wall<LIVE>(p, q, g.R_g_c); }
-    if (pr2 > p.gt_Rp && q.z < g.z_gb && pz_in_gap) { bits |= 1u << 6; pore_plane_wall<LIVE>(p, q, g.z_gb); }
-    if (pr2 > p.gt_Rp && q.z > g.z_gt_pore && pz_in_gap) { bits |= 1u << 7; pore_plane_wall<LIVE>(p, q, g.z_gt_pore); }
+    if (pz_in_gap && pr2 < p.lt_Rg && q.x * q.x + q.y * q.y > p.gt_Rg) { bits |= 1u << 5; pore_side_wall<MODE>(p, q, g.R_g_c); }
+    if (pr2 > p.gt_Rp && q.z < g.z_gb && pz_in_gap) { bits |= 1u << 6; pore_plane_wall<MODE>(p, q, g.z_gb); }
+    if (pr2 > p.gt_Rp && q.z > g.z_gt_pore && pz_in_gap) { bits |= 1u << 7; pore_plane_wall<MODE>(p, q, g.z_gt_pore); }
     if (pr2 < p.lt_Rp && q.x * q.x + q.y * q.y > p.gt_Rp &&
-        ((q.z < g.z_cold && q.z > g.z_gt_pore) || (q.z < g.z_gb && q.z > g.oah))) { bits |= 1u << 8; pore_side_wall<LIVE>(p, q, g.R_p_c); }
+        ((q.z < g.z_cold && q.z > g.z_gt_pore) || (q.z < g.z_gb && q.z > g.oah))) { bits |= 1u << 8; pore_side_wall<MODE>(p, q, g.R_p_c); }
     return bits;
 }
 
@@ -346,7 +352,7 @@ __device__ __forceinline__ bool temp_contact(const amc_geom &g, int c, const Par
 
 // energy accommodation at an energized wall (Temp:377-389, 402-403); leaves the particle at the
 // contact point with paths reset (Temp:398-401)
-template <bool LIVE = true>
+template <int MODE = 1>
 __device__ __forceinline__ void temp_energized(const P &p, Part &q, double t, const double col[3], const double dir[3],
                                                double Es, double alpha, double &dpz, double &dE)
 {
@@ -360,19 +366,19 @@ __device__ __forceinline__ void temp_energized(const P &p, Part &q, double t, co
     dE = Enew - E;
     double nvx = dir[0] * new_mag, nvy = dir[1] * new_mag, nvz = dir[2] * new_mag;
     dpz = m * nvz - old_pz;
-    mfp_record<LIVE>(p, q.d, q.dx, q.dy, q.dz, q.flag, q.vx, q.vy, q.vz, t);
+    mfp_record<MODE>(p, q.d, q.dx, q.dy, q.dz, q.flag, q.vx, q.vy, q.vz, t);
     q.d = 0; q.dx = 0; q.dy = 0; q.dz = 0;
     q.x = col[0]; q.y = col[1]; q.z = col[2];
     q.vx = nvx; q.vy = nvy; q.vz = nvz;
 }
 
 // specular Temp cases: no MFP bookkeeping (Temp:311-347)
-template <bool LIVE = true>
+template <int MODE = 1>
 __device__ __forceinline__ void temp_specular(const P &p, int c, Part &q)
 {
     if (c == AMC_CASE_1) {
         double t;
-        if (!side_quadratic(q.x, q.y, q.vx, q.vy, p.g.R_oa_c, t)) { if (LIVE) atomicAdd(&p.stats->errors, 1ull); return; }
+        if (!side_quadratic(q.x, q.y, q.vx, q.vy, p.g.R_oa_c, t)) { if (MODE == AMC_LIVE) atomicAdd(&p.stats->errors, 1ull); return; }
         reflect_xy(q, p.g.R_oa_c, t);
     } else {
         double zp = temp_plane(p.g, c);
@@ -473,7 +479,7 @@ __device__ __forceinline__ bool temp_any_mask(const P &p, const Part &q)
 }
 
 // all ten Temp cases on one particle with device RNG (Temp:693-753)
-template <bool LIVE = true>
+template <int MODE = 1>
 __device__ __forceinline__ uint32_t temp_walls_device(const P &p, Part &q, int64_t id)
 {
     uint32_t bits = 0;
@@ -482,14 +488,14 @@ __device__ __forceinline__ uint32_t temp_walls_device(const P &p, Part &q, int64
     for (int c = 0; c < AMC_NUM_CASES; c++) {
         if (!temp_mask(p, c, q)) continue;
         bits |= 1u << c;
-        if (c <= AMC_CASE_2B) { temp_specular<LIVE>(p, c, q); continue; }
+        if (c <= AMC_CASE_2B) { temp_specular<MODE>(p, c, q); continue; }
         double t, col[3], nrm[3], dir[3], dpz, dE;
-        if (!temp_contact(p.g, c, q, t, col, nrm)) { if (LIVE) atomicAdd(&p.stats->errors, 1ull); continue; }
+        if (!temp_contact(p.g, c, q, t, col, nrm)) { if (MODE == AMC_LIVE) atomicAdd(&p.stats->errors, 1ull); continue; }
         philox_direction(p, id, c, nrm, dir);
         double Es = c == AMC_CASE_4 ? cheb_eval(p, col[2]) : (temp_is_cold(c) ? p.g.E_cold : p.g.E_hot);
         double alpha = c == AMC_CASE_4 ? p.g.alpha_g : p.g.alpha_c;
-        temp_energized<LIVE>(p, q, t, col, dir, Es, alpha, dpz, dE);
-        if (!LIVE) continue;
+        temp_energized<MODE>(p, q, t, col, dir, Es, alpha, dpz, dE);
+        if (MODE != AMC_LIVE) continue;
         acc_add(p.stats->dpz, dpz, SC_P1, SC_P1I, SC_P2);
         if (c != AMC_CASE_4) acc_add(temp_is_cold(c) ? p.stats->ecold : p.stats->ehot, dE, SC_E1, SC_E1I, SC_E2);
     }
@@ -514,7 +520,7 @@ __device__ __forceinline__ uint32_t cube_walls(const P &p, Part &q)
 // Owner k: edge[k] <= v < edge[k+1].  Returns -1 below edge[0] (only the low band of cell 0 can
 // contain it) and nc for v >= edge[nc] or NaN (member of no cell).  The division is only an
 // estimate; the table comparisons decide.
-__device__ __forceinline__ int owner_axis(const double *edge, int nc, double e0, double inv_d, double v)
+__device__ __noinline__ int owner_axis_slow(const double *edge, int nc, double e0, double inv_d, double v)
 {
     if (!(v < edge[nc])) return nc;
     if (v < edge[0]) return -1;
@@ -524,6 +530,15 @@ __device__ __forceinline__ int owner_axis(const double *edge, int nc, double e0,
     while (v < edge[o]) --o;
     while (v >= edge[o + 1]) ++o;
     return o;
+}
+// the estimate is right for all but the particles within a rounding error of an edge: one pair of table
+// entries decides; everything else (outside the grid, NaN, off by one) takes the slow path
+__device__ __forceinline__ int owner_axis(const double *edge, int nc, double e0, double inv_d, double v)
+{
+    int o = __double2int_rd((v - e0) * inv_d);
+    o = min(max(o, 0), nc - 1);
+    if (edge[o] <= v && v < edge[o + 1]) return o;
+    return owner_axis_slow(edge, nc, e0, inv_d, v);
 }
 // padded owner key: each axis shifted by +1 so the virtual layer below edge[0] is index 0;
 // anything outside on the high side (or NaN) goes to the trailing OUT bucket ncell_pad

@@ -152,18 +152,18 @@ __global__ void __launch_bounds__(ADVECT_THREADS, 4) k_advect(const __grid_const
 // scatter then carries out the step itself on the way to the particle's new slot (k_scatter_advect:
 // 93 B read, 85 B written) -- 238 B per particle and step instead of the 352 B of k_advect + k_scatter.
 // advance_particle is the per-particle part of a timestep before the pair pass (closing recapture of
-// the previous step, drift, wall cases, recapture; same references as k_advect).  LIVE = false is a
+// the previous step, drift, wall cases, recapture; same references as k_advect).  MODE = AMC_DRY is a
 // dry run: same arithmetic and therefore bit-identical positions, but no counters, no completed paths,
 // no path-length bookkeeping -- none of which feeds back into the position.
-template <bool LIVE>
+template <int MODE>
 __device__ __forceinline__ void advance_particle(const P &p, Part &q, const int32_t id, const int phase)
 {
     if (phase & PH_RECAP_POST) { // recapture that closes the previous step's pair pass (Pore:550 / Temp:843-845)
         int cnt = p.kind == AMC_KIND_TEMP ? temp_oob(p.g, q) : 0;
         int moved = p.kind == AMC_KIND_TEMP ? temp_recapture(p.g, q) : pore_recapture(p.g, q);
         if (p.kind != AMC_KIND_TEMP) cnt = moved;
-        if (LIVE && cnt) atomicAdd(&p.stats_prev->oob_pp, (unsigned long long)cnt);
-        if (LIVE && p.kind == AMC_KIND_TEMP && moved) {
+        if (MODE == AMC_LIVE && cnt) atomicAdd(&p.stats_prev->oob_pp, (unsigned long long)cnt);
+        if (MODE == AMC_LIVE && p.kind == AMC_KIND_TEMP && moved) {
             int after = temp_oob(p.g, q);
             if (after) atomicAdd(&p.stats_prev->oob_pp_after, (unsigned long long)after);
         }
@@ -172,14 +172,14 @@ __device__ __forceinline__ void advance_particle(const P &p, Part &q, const int3
         q.px = q.x; q.py = q.y; q.pz = q.z;
         double ax = p.dt * q.vx, ay = p.dt * q.vy, az = p.dt * q.vz;
         q.x += ax; q.y += ay; q.z += az;
-        if (LIVE) {
+        if (MODE != AMC_DRY) {
             q.d += fabs(sqrt((ax * ax + ay * ay) + az * az));
             q.dx += fabs(ax); q.dy += fabs(ay); q.dz += fabs(az);
         }
     }
     if (phase & PH_WALLS) {
-        uint32_t bits = p.kind == AMC_KIND_PORE ? pore_walls<LIVE>(p, q) : (p.kind == AMC_KIND_TEMP ? temp_walls_device<LIVE>(p, q, id) : cube_walls(p, q));
-        if (LIVE) {
+        uint32_t bits = p.kind == AMC_KIND_PORE ? pore_walls<MODE>(p, q) : (p.kind == AMC_KIND_TEMP ? temp_walls_device<MODE>(p, q, id) : cube_walls(p, q));
+        if (MODE == AMC_LIVE) {
             for (uint32_t b = bits; b; b &= b - 1) atomicAdd(&p.stats->wall_hits[__ffs(b) - 1], 1ull);
             if (p.wall_bits) p.wall_bits[id] = (uint16_t)bits;
         }
@@ -187,11 +187,11 @@ __device__ __forceinline__ void advance_particle(const P &p, Part &q, const int3
     if (phase & PH_RECAP) {
         if (p.kind == AMC_KIND_PORE) {
             int cnt = pore_recapture(p.g, q);
-            if (LIVE && cnt) atomicAdd(&p.stats->oob_walls, (unsigned long long)cnt);
+            if (MODE == AMC_LIVE && cnt) atomicAdd(&p.stats->oob_walls, (unsigned long long)cnt);
         } else if (p.kind == AMC_KIND_TEMP) {
             int cnt = temp_oob(p.g, q);
-            if (LIVE && cnt) atomicAdd(&p.stats->oob_walls, (unsigned long long)cnt);
-            if (temp_recapture(p.g, q) && LIVE) {
+            if (MODE == AMC_LIVE && cnt) atomicAdd(&p.stats->oob_walls, (unsigned long long)cnt);
+            if (temp_recapture(p.g, q) && MODE == AMC_LIVE) {
                 int after = temp_oob(p.g, q);
                 if (after) atomicAdd(&p.stats->oob_walls_after, (unsigned long long)after);
             }
@@ -199,17 +199,57 @@ __device__ __forceinline__ void advance_particle(const P &p, Part &q, const int3
     }
 }
 
+// slab decomposition: the full post-step record of a particle that leaves for / is copied to another rank.
+// Rare (the particles next to a cut), so it has its own register budget; QUIET because the live run of
+// the same particle in k_scatter_advect does the recording.
+__device__ __noinline__ void slab_pack(const P &p, const int64_t s, const int32_t id, const int phase, const int to, const unsigned extra)
+{
+    int j = atomicAdd(&p.xf_count[to], 1);
+    if (j >= p.xf_capv[to]) { atomicAdd(p.slab_overflow + 0, 1ull); return; }
+    Part q;
+    load_part(p.a, s, q);
+    q.flag &= AMC_FLAG_PATH;
+    advance_particle<AMC_QUIET>(p, q, id, phase);
+    double *r = p.xf_send + ((size_t)p.xf_off[to] + 1 + j) * AMC_REC;
+    r[0] = q.x; r[1] = q.y; r[2] = q.z; r[3] = q.vx; r[4] = q.vy; r[5] = q.vz;
+    r[6] = q.d; r[7] = q.dx; r[8] = q.dy; r[9] = q.dz; r[10] = (double)id;
+    r[11] = (double)((q.flag & AMC_FLAG_PATH) | extra);
+}
+
 // pass 1 of the fused step: owner cell of the position each particle will have after the step, and its
-// rank inside that cell (band particles first, see k_advect)
-__global__ void __launch_bounds__(ADVECT_THREADS, 6) k_keys(const __grid_constant__ P p, const int phase)
+// rank inside that cell (band particles first, see k_advect).  Slab mode: also decides which rank owns
+// the particle after the step and packs the records that travel (see k_advect for the protocol).
+#define AUX_GHOST_UP 1u      /* kept, and copied to the rank above */
+#define AUX_STAY_AS_GHOST 2u /* owned by the rank below from now on, the local copy stays as its ghost */
+template <bool SLAB>
+__global__ void __launch_bounds__(ADVECT_THREADS, SLAB ? 4 : 6) k_keys(const __grid_constant__ P p, const int phase)
 {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= p.n) return;
+    if (SLAB && (p.a.flag[s] & AMC_FLAG_GHOST)) { // last step's copy of a neighbour's particle: drop it
+        p.key[s] = p.ncell_pad + 1; p.rank[s] = ~atomicAdd(&p.rest_count[p.ncell_pad + 1], 1);
+        return;
+    }
     Part q;
     q.x = p.a.x[s]; q.y = p.a.y[s]; q.z = p.a.z[s]; q.vx = p.a.vx[s]; q.vy = p.a.vy[s]; q.vz = p.a.vz[s];
     q.d = q.dx = q.dy = q.dz = 0.0; q.flag = 0;
-    const int32_t id = p.kind == AMC_KIND_TEMP ? p.a.id[s] : 0; /* keys the device RNG of the energized walls */
-    advance_particle<false>(p, q, id, phase);
+    const int32_t id = (p.kind == AMC_KIND_TEMP || SLAB) ? p.a.id[s] : 0; /* keys the device RNG of the energized walls */
+    advance_particle<AMC_DRY>(p, q, id, phase);
+    if (SLAB) {
+        int gz = owner_axis(p.gz_edge, p.gncz, p.g_e0z, p.g_inv_dz, q.z);
+        int layer = gz < 0 ? 0 : (gz >= p.gncz ? p.gncz - 1 : gz);
+        int dest = 0;
+        while (dest + 1 < p.nranks && layer >= p.cuts[dest + 1]) dest++;
+        const bool ghost_up = dest == p.srank && p.srank + 1 < p.nranks && q.z > p.up_thr;
+        const bool stay_as_ghost = dest == p.srank - 1 && q.z > p.down_band;
+        if (dest != p.srank) slab_pack(p, s, id, phase, dest, stay_as_ghost ? AMC_FLAG_REL_UP : 0u);
+        else if (ghost_up) slab_pack(p, s, id, phase, p.srank + 1, AMC_FLAG_GHOST | AMC_FLAG_REL_DOWN);
+        p.aux[s] = (uint8_t)((ghost_up ? AUX_GHOST_UP : 0u) | (stay_as_ghost ? AUX_STAY_AS_GHOST : 0u));
+        if (dest != p.srank && !stay_as_ghost) { // emigrant: leaves this rank's arrays at the coming sort
+            p.key[s] = p.ncell_pad + 1; p.rank[s] = ~atomicAdd(&p.rest_count[p.ncell_pad + 1], 1);
+            return;
+        }
+    }
     int o[3];
     int32_t k = owner_key(p, q.x, q.y, q.z, o);
     p.key[s] = k;
@@ -218,20 +258,40 @@ __global__ void __launch_bounds__(ADVECT_THREADS, 6) k_keys(const __grid_constan
     p.rank[s] = band ? r : ~r;
 }
 
-// pass 2: the timestep proper, written straight to the particle's slot in owner-cell order
+// pass 2: the timestep proper, written straight to the particle's slot in owner-cell order.  Slab mode: the
+// particles unpacked behind the resident ones (slots n .. n + n_in) arrive already advanced; ghosts of the last
+// step and emigrants go to the bucket behind the last cell and are dropped.
+template <bool SLAB>
 __global__ void __launch_bounds__(ADVECT_THREADS, 3) k_scatter_advect(const __grid_constant__ P p, const int phase)
 {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= p.n) return;
+    if (s >= p.n + (SLAB ? *p.n_in : 0)) return;
     Part q;
     load_part(p.a, s, q);
-    q.flag &= AMC_FLAG_PATH;
     const int32_t id = p.a.id[s];
     const int32_t k = p.key[s], r = p.rank[s];
-    advance_particle<true>(p, q, id, phase);
+    if (s < p.n && !(SLAB && (q.flag & AMC_FLAG_GHOST))) {
+        q.flag &= AMC_FLAG_PATH;
+        advance_particle<AMC_LIVE>(p, q, id, phase);
+        if (SLAB) {
+            const unsigned aux = p.aux[s];
+            if (aux & AUX_GHOST_UP) q.flag |= AMC_FLAG_REL_UP;
+            if (aux & AUX_STAY_AS_GHOST) q.flag = (q.flag & AMC_FLAG_PATH) | AMC_FLAG_GHOST | AMC_FLAG_REL_DOWN;
+        }
+    }
     const int64_t t = (int64_t)p.cell_start[k] + (r >= 0 ? r : p.band_count[k] + ~r);
+    const unsigned fl = q.flag;
+    q.flag = fl & (SLAB ? AMC_FLAG_KEEP : AMC_FLAG_PATH);
     store_part(p.b, t, q);
     p.b.id[t] = id;
+    if (SLAB) {
+        p.skey[t] = k;
+        if (k <= p.ncell_pad && (fl & (AMC_FLAG_GHOST | AMC_FLAG_REL_UP | AMC_FLAG_REL_DOWN))) rel_insert(p, id, (int32_t)t);
+        if (k <= p.ncell_pad && (fl & AMC_FLAG_LATE_UP)) {
+            int j = atomicAdd(&p.bnd_n[0], 1);
+            if (j < p.bnd_cap) p.bnd_dirty[0][j] = (int32_t)t; else atomicAdd(p.slab_overflow + 2, 1ull);
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
