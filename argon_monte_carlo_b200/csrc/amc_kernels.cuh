@@ -10,6 +10,7 @@
 
 #define ADVECT_THREADS 256
 #define PAIR_THREADS 128
+#define AMC_MV_CAP 32 /* particles one cell visit can move (reference scale: 2-6) */
 #define WALK_K 3 /* chains a thread of cell_process walks side by side */
 #define PAIR_K 3 /* candidates a thread of k_pairs_group has in flight during the gather */
 #define SWEEP_THREADS 512
@@ -222,7 +223,7 @@ __device__ __noinline__ void slab_pack(const P &p, const int64_t s, const int32_
 #define AUX_GHOST_UP 1u      /* kept, and copied to the rank above */
 #define AUX_STAY_AS_GHOST 2u /* owned by the rank below from now on, the local copy stays as its ghost */
 template <bool SLAB>
-__global__ void __launch_bounds__(ADVECT_THREADS, SLAB ? 4 : 6) k_keys(const __grid_constant__ P p, const int phase)
+__global__ void __launch_bounds__(ADVECT_THREADS, 6) k_keys(const __grid_constant__ P p, const int phase)
 {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= p.n) return;
@@ -473,6 +474,10 @@ struct CellShared {
     /* neighbour search: members chained per slab along x (>= 1.05 filter radii wide) */
     int head[AMC_XBINS + 2];     /* last member hashed into the slab (index + 1), 0 = empty; zero on entry of cell_process */
     uint16_t nxt[AMC_MAX_MEMBERS];
+    uint8_t mv[AMC_MAX_MEMBERS];      /* 0, or 1 + index of the member's pre-visit position in ox/oy/oz (moved by a collision of this visit) */
+    uint16_t mvlist[AMC_MAX_MEMBERS]; /* the moved members, compacted at the end of the visit */
+    double ox[AMC_MV_CAP], oy[AMC_MV_CAP], oz[AMC_MV_CAP];
+    int nmv, nold;
     float inv_w;                 /* slabs per unit length */
     int nb;                      /* slabs of this cell, 1..AMC_XBINS */
     unsigned int nexec;          /* distance tests executed by this CTA since the last flush */
@@ -562,6 +567,7 @@ __device__ __forceinline__ void resolve_pair(const P &p, CellShared &S, int m1, 
     double x1 = S.x[m1], y1 = S.y[m1], z1 = S.z[m1], x2 = S.x[m2], y2 = S.y[m2], z2 = S.z[m2];
     const double vx1 = w ? qvx : ovx, vy1 = w ? qvy : ovy, vz1 = w ? qvz : ovz;
     const double vx2 = w ? ovx : qvx, vy2 = w ? ovy : qvy, vz2 = w ? ovz : qvz;
+    const double oldx = w ? x2 : x1, oldy = w ? y2 : y1, oldz = w ? z2 : z1; /* the own particle before the collision */
     double ddx = x2 - x1, ddy = y2 - y1, ddz = z2 - z1;
     double rx = -vx2 + vx1, ry = -vy2 + vy1, rz = -vz2 + vz1;
     double a = (rx * rx + ry * ry) + rz * rz;
@@ -648,46 +654,81 @@ __device__ __forceinline__ void resolve_pair(const P &p, CellShared &S, int m1, 
             }
         }
     }
-    if (p.pp_mode == AMC_PP_GROUPS) {
-        // Every cell of a later colour group that contains a moved particle has to be visited (k_detect
-        // only listed the cells that held an overlapping pair before the pass).  A moved particle whose
-        // owner cell changed can, in addition, no longer be found through the sorted layout: its member
-        // cell for every later group is published in the escaped list.
-        int o[3] = {0, 0, 0}, e = -1, e_old = -1, findable = 0, ok = 0;
-        if (lane < 2) {
-            int32_t k = owner_key(p, x, y, z, o);
-            e_old = S.src[mo];
-            ok = 1;
-            if (e_old < 0) { /* found through the sorted layout: src = -1 - (low-side neighbour code) */
-                int nb = -1 - e_old;
-                int oc = ((S.kx + 1 - (nb >> 2)) * p.pnc[1] + (S.ky + 1 - ((nb >> 1) & 1))) * p.pnc[2] + (S.kz + 1 - (nb & 1));
-                /* still findable through the sorted layout: same owner cell, and either it sits in the
-                   band prefix of that cell or it is (still) outside every band */
-                findable = k == oc && (so < p.cell_start[oc] + p.band_count[oc] || !any_band(p, x, y, z, o));
-            }
-            if (!findable) { /* entries are never re-linked: a particle that moves again gets a fresh one, the old one is retired below */
-                e = atomicAdd(p.esc_count, 1);
-                if (e >= p.esc_cap) { atomicAdd(&p.stats->esc_overflow, 1ull); ok = 0; }
-                else { p.esc_slot[e] = so; S.src[mo] = e; of |= AMC_FLAG_ESC; }
-            }
-        }
-        // lane 8 * particle + g2 takes care of the particle's member cell in colour group g2
-        const int pw = (lane >> 3) & 1, g2 = lane & 7;
-        const int o0 = __shfl_sync(FULL, o[0], pw), o1 = __shfl_sync(FULL, o[1], pw), o2 = __shfl_sync(FULL, o[2], pw);
-        const int ee = __shfl_sync(FULL, e, pw), eo = __shfl_sync(FULL, e_old, pw);
-        const int fnd = __shfl_sync(FULL, findable, pw), okk = __shfl_sync(FULL, ok, pw);
-        if (lane < 16 && g2 > group && okk) {
-            const double px = pw ? x2 : x1, py = pw ? y2 : y1, pz = pw ? z2 : z1;
-            int cx = member_axis(p.edge[0], p.lo[0], p.nc[0], o0, (g2 >> 2) & 1, px);
-            int cy = member_axis(p.edge[1], p.lo[1], p.nc[1], o1, (g2 >> 1) & 1, py);
-            int cz = member_axis(p.edge[2], p.lo[2], p.nc[2], o2, (g2 ^ p.zoff) & 1, pz);
-            int32_t cc = (cx < 0 || cy < 0 || cz < 0) ? -1 : ((cx >> 1) * p.nh[1] + (cy >> 1)) * p.nh[2] + (cz >> 1);
-            if (eo >= 0) p.esc_cell[eo * 8 + g2] = -1;
-            esc_link(p, g2, cc, cx, cy, cz, fnd ? -1 : ee);
-        }
+    if (lane < 2 && S.mv[mo] == 0) { /* the later colour groups learn about the move when the visit is over (activate_moved) */
+        int i = atomicAdd(&S.nold, 1);
+        if (i < AMC_MV_CAP) { S.ox[i] = oldx; S.oy[i] = oldy; S.oz[i] = oldz; S.mv[mo] = (uint8_t)(i + 1); }
+        else atomicAdd(&p.stats->cand_overflow, 1ull);
     }
     if (lane < 2) A.flag[so] = (uint8_t)of;
     __syncwarp();
+}
+
+// End of a cell visit in colour-group mode: every cell of a LATER colour group that contains a particle moved in
+// this visit has to be visited too (k_detect only listed the cells that held an overlapping pair before the
+// pass).  A moved particle whose owner cell changed can, in addition, no longer be found through the sorted
+// layout: its member cell for every later group is published in the escaped list (esc_link).  Done once per
+// moved particle with its final position, all warps side by side: two particles per warp and round, lane
+// 8 * particle + g2 takes care of colour group g2.
+__device__ __forceinline__ void activate_moved(const P &p, CellShared &S, const int group)
+{
+    const unsigned FULL = 0xffffffffu;
+    const int tid = threadIdx.x, nthreads = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
+    const int n = S.n;
+    for (int k = tid; k < n; k += nthreads)
+        if (S.mv[k]) S.mvlist[atomicAdd(&S.nmv, 1)] = (uint16_t)k;
+    __syncthreads();
+    const int nmv = S.nmv;
+    const Arrays &A = p.a;
+    for (int base = 2 * warp; base < nmv; base += 2 * nwarps) {
+        const int pw = (lane >> 3) & 1, g2 = lane & 7;
+        int o[3] = {0, 0, 0}, q[3] = {0, 0, 0}, e = -1, e_old = -1, findable = 0, ok = 0;
+        double x = 0, y = 0, z = 0, ux = 0, uy = 0, uz = 0;
+        if (base + pw < nmv) {
+            const int m = S.mvlist[base + pw];
+            x = S.x[m]; y = S.y[m]; z = S.z[m];
+            const int io = S.mv[m] - 1;
+            ux = S.ox[io]; uy = S.oy[io]; uz = S.oz[io];
+            if ((lane & 7) == 0 && lane < 16) { /* lanes 0 and 8: one per particle */
+                const int so = S.slot[m];
+                int32_t k = owner_key(p, x, y, z, o);
+                owner_key(p, ux, uy, uz, q);
+                e_old = S.src[m];
+                ok = 1;
+                if (e_old < 0) { /* found through the sorted layout: src = -1 - (low-side neighbour code) */
+                    int nb = -1 - e_old;
+                    int oc = ((S.kx + 1 - (nb >> 2)) * p.pnc[1] + (S.ky + 1 - ((nb >> 1) & 1))) * p.pnc[2] + (S.kz + 1 - (nb & 1));
+                    /* still findable through the sorted layout: same owner cell, and either it sits in the
+                       band prefix of that cell or it is (still) outside every band */
+                    findable = k == oc && (so < p.cell_start[oc] + p.band_count[oc] || !any_band(p, x, y, z, o));
+                }
+                if (!findable) { /* entries are never re-linked: a particle that moves again in a later visit gets a fresh one */
+                    e = atomicAdd(p.esc_count, 1);
+                    if (e >= p.esc_cap) { atomicAdd(&p.stats->esc_overflow, 1ull); ok = 0; }
+                    else { p.esc_slot[e] = so; A.flag[so] |= AMC_FLAG_ESC; }
+                }
+            }
+        }
+        const int src = pw * 8;
+        const int o0 = __shfl_sync(FULL, o[0], src), o1 = __shfl_sync(FULL, o[1], src), o2 = __shfl_sync(FULL, o[2], src);
+        const int q0 = __shfl_sync(FULL, q[0], src), q1 = __shfl_sync(FULL, q[1], src), q2 = __shfl_sync(FULL, q[2], src);
+        const int ee = __shfl_sync(FULL, e, src), eo = __shfl_sync(FULL, e_old, src);
+        const int fnd = __shfl_sync(FULL, findable, src), okk = __shfl_sync(FULL, ok, src);
+        if (lane < 16 && g2 > group && okk) {
+            int cx = member_axis(p.edge[0], p.lo[0], p.nc[0], o0, (g2 >> 2) & 1, x);
+            int cy = member_axis(p.edge[1], p.lo[1], p.nc[1], o1, (g2 >> 1) & 1, y);
+            int cz = member_axis(p.edge[2], p.lo[2], p.nc[2], o2, (g2 ^ p.zoff) & 1, z);
+            int32_t cc = (cx < 0 || cy < 0 || cz < 0) ? -1 : ((cx >> 1) * p.nh[1] + (cy >> 1)) * p.nh[2] + (cz >> 1);
+            if (eo >= 0) p.esc_cell[eo * 8 + g2] = -1; /* retire the entry the particle came in through */
+            esc_link(p, g2, cc, cx, cy, cz, fnd ? -1 : ee);
+            // the cell the particle was a member of before the visit loses it: its member count changed, so the
+            // reference-equivalent test counter needs the visit even though no new overlap can arise there
+            int dx = member_axis(p.edge[0], p.lo[0], p.nc[0], q0, (g2 >> 2) & 1, ux);
+            int dy = member_axis(p.edge[1], p.lo[1], p.nc[1], q1, (g2 >> 1) & 1, uy);
+            int dz = member_axis(p.edge[2], p.lo[2], p.nc[2], q2, (g2 ^ p.zoff) & 1, uz);
+            int32_t dc = (dx < 0 || dy < 0 || dz < 0) ? -1 : ((dx >> 1) * p.nh[1] + (dy >> 1)) * p.nh[2] + (dz >> 1);
+            if (dc >= 0 && dc != cc) esc_link(p, g2, dc, dx, dy, dz, -1);
+        }
+    }
 }
 
 // members are in S.{x,y,z,id,slot,src}[0..S.n); all threads of the block call this
@@ -709,7 +750,9 @@ __device__ __forceinline__ void cell_process(const P &p, CellShared &S, int grou
             S.fx[k] = fx; S.fy[k] = (float)(S.y[k] - S.org[1]); S.fz[k] = (float)(S.z[k] - S.org[2]);
             int b = min(nb1, max(0, (int)(fx * inv_w)));
             S.nxt[k] = (uint16_t)atomicExch(&S.head[b], k + 1);
+            S.mv[k] = 0;
         }
+        if (tid == 0) { S.nmv = 0; S.nold = 0; }
         PHASE_MARK(9); /* chain: own work */
         __syncthreads();
         PHASE_MARK(2); /* chain: barrier */
@@ -804,6 +847,7 @@ __device__ __forceinline__ void cell_process(const P &p, CellShared &S, int grou
         if (tid == 0 && S.ncand > AMC_MAX_CAND) S.ncand = AMC_MAX_CAND;
         __syncthreads();
     }
+    if (p.pp_mode == AMC_PP_GROUPS) activate_moved(p, S, group);
 }
 
 // Detection list of one pair pass: every reference cell whose 8 candidate owner cells hold at least two
@@ -1450,36 +1494,52 @@ __global__ void __launch_bounds__(128) k_bnd_apply(const __grid_constant__ P p)
             if (p.esc_slot[e] == s) atomicMax(&s_esc, e);
     }
     __syncthreads();
-    if (tid != 0) continue;
-    double x = r[0], y = r[1], z = r[2];
-    A.x[s] = x; A.y[s] = y; A.z[s] = z; A.vx[s] = r[3]; A.vy[s] = r[4]; A.vz[s] = r[5];
-    A.d[s] = r[6]; A.dx[s] = r[7]; A.dy[s] = r[8]; A.dz[s] = r[9];
+    if (tid >= 32) continue; /* warp 0: lane 0 places the record, lanes 0-7 take one colour group each */
+    const double x = r[0], y = r[1], z = r[2];
     unsigned nf = (fl & ~AMC_FLAG_PATH) | ((unsigned)r[11] & AMC_FLAG_PATH);
-    int o[3];
-    int32_t k = owner_key(p, x, y, z, o);
+    int o[3] = {0, 0, 0};
     const int e_old = s_esc;
-    int e = -1;
-    bool findable = false, ok = true;
-    if (e_old < 0) {
-        int32_t sk = p.skey[s];
-        findable = sk >= 0 && k == sk && (s < p.cell_start[sk] + p.band_count[sk] || !any_band(p, x, y, z, o));
-    }
-    if (!findable) {
-        e = atomicAdd(p.esc_count, 1);
-        if (e >= p.esc_cap) { atomicAdd(&p.stats->esc_overflow, 1ull); ok = false; }
-        else { p.esc_slot[e] = s; nf |= AMC_FLAG_ESC; }
-    }
-    // the cells of the remaining groups that hold this particle must be visited (k_detect did not see this position)
-    if (ok)
-        for (int g2 = p.group_done + 1; g2 < 8; g2++) {
-            int cx = member_axis(p.edge[0], p.lo[0], p.nc[0], o[0], (g2 >> 2) & 1, x);
-            int cy = member_axis(p.edge[1], p.lo[1], p.nc[1], o[1], (g2 >> 1) & 1, y);
-            int cz = member_axis(p.edge[2], p.lo[2], p.nc[2], o[2], (g2 ^ p.zoff) & 1, z);
-            int32_t cc = (cx < 0 || cy < 0 || cz < 0) ? -1 : ((cx >> 1) * p.nh[1] + (cy >> 1)) * p.nh[2] + (cz >> 1);
-            if (e_old >= 0) p.esc_cell[e_old * 8 + g2] = -1;
-            esc_link(p, g2, cc, cx, cy, cz, findable ? -1 : e);
+    int e = -1, findable = 0, ok = 1;
+    int q[3] = {0, 0, 0};
+    double ux = x, uy = y, uz = z; /* where this rank had the particle so far (new foreign copy: nowhere else) */
+    if (tid == 0) {
+        if (p.skey[s] != -1 || (fl & AMC_FLAG_ESC)) { ux = A.x[s]; uy = A.y[s]; uz = A.z[s]; }
+        owner_key(p, ux, uy, uz, q);
+        A.x[s] = x; A.y[s] = y; A.z[s] = z; A.vx[s] = r[3]; A.vy[s] = r[4]; A.vz[s] = r[5];
+        A.d[s] = r[6]; A.dx[s] = r[7]; A.dy[s] = r[8]; A.dz[s] = r[9];
+        int32_t k = owner_key(p, x, y, z, o);
+        if (e_old < 0) {
+            int32_t sk = p.skey[s];
+            findable = sk >= 0 && k == sk && (s < p.cell_start[sk] + p.band_count[sk] || !any_band(p, x, y, z, o));
         }
-    A.flag[s] = (uint8_t)nf;
+        if (!findable) {
+            e = atomicAdd(p.esc_count, 1);
+            if (e >= p.esc_cap) { atomicAdd(&p.stats->esc_overflow, 1ull); ok = 0; }
+            else { p.esc_slot[e] = s; nf |= AMC_FLAG_ESC; }
+        }
+        A.flag[s] = (uint8_t)nf;
+    }
+    const unsigned FULL = 0xffffffffu;
+    const int o0 = __shfl_sync(FULL, o[0], 0), o1 = __shfl_sync(FULL, o[1], 0), o2 = __shfl_sync(FULL, o[2], 0);
+    e = __shfl_sync(FULL, e, 0); findable = __shfl_sync(FULL, findable, 0); ok = __shfl_sync(FULL, ok, 0);
+    const int q0 = __shfl_sync(FULL, q[0], 0), q1 = __shfl_sync(FULL, q[1], 0), q2 = __shfl_sync(FULL, q[2], 0);
+    const double vx_ = __shfl_sync(FULL, ux, 0), vy_ = __shfl_sync(FULL, uy, 0), vz_ = __shfl_sync(FULL, uz, 0);
+    // the cells of the remaining groups that hold this particle must be visited (k_detect did not see this position)
+    const int g2 = tid;
+    if (ok && g2 < 8 && g2 > p.group_done) {
+        int cx = member_axis(p.edge[0], p.lo[0], p.nc[0], o0, (g2 >> 2) & 1, x);
+        int cy = member_axis(p.edge[1], p.lo[1], p.nc[1], o1, (g2 >> 1) & 1, y);
+        int cz = member_axis(p.edge[2], p.lo[2], p.nc[2], o2, (g2 ^ p.zoff) & 1, z);
+        int32_t cc = (cx < 0 || cy < 0 || cz < 0) ? -1 : ((cx >> 1) * p.nh[1] + (cy >> 1)) * p.nh[2] + (cz >> 1);
+        if (e_old >= 0) p.esc_cell[e_old * 8 + g2] = -1;
+        esc_link(p, g2, cc, cx, cy, cz, findable ? -1 : e);
+        // the cell that held the copy so far loses it (see activate_moved)
+        int dx = member_axis(p.edge[0], p.lo[0], p.nc[0], q0, (g2 >> 2) & 1, vx_);
+        int dy = member_axis(p.edge[1], p.lo[1], p.nc[1], q1, (g2 >> 1) & 1, vy_);
+        int dz = member_axis(p.edge[2], p.lo[2], p.nc[2], q2, (g2 ^ p.zoff) & 1, vz_);
+        int32_t dc = (dx < 0 || dy < 0 || dz < 0) ? -1 : ((dx >> 1) * p.nh[1] + (dy >> 1)) * p.nh[2] + (dz >> 1);
+        if (dc >= 0 && dc != cc) esc_link(p, g2, dc, dx, dy, dz, -1);
+    }
     }
 }
 
