@@ -208,7 +208,12 @@ static int create_impl(amc_handle *h, const amc_config *cfg, int device)
     p.ncell_pad = (int32_t)ncell;
     for (int a = 0; a < 3; a++) p.nh[a] = (cfg->nc[a] + 1) / 2;
     h->n_buckets = (int)ncell + 2; /* padded owner cells + OUT + GONE (slab mode: emigrants and dropped ghosts) */
-    ALLOC(p.band_count, h->n_buckets + 1); ALLOC(p.rest_count, h->n_buckets + 1); ALLOC(p.cell_start, h->n_buckets + 1);
+    ALLOC(p.band_count, h->n_buckets + 2); ALLOC(p.rest_count, h->n_buckets + 1); ALLOC(p.cell_start, h->n_buckets + 1);
+    p.touched_n = p.band_count + (h->n_buckets + 1);
+    p.touched_cap = (int32_t)std::min<int64_t>(std::max<int64_t>(h->cap / 32, 8192), 1 << 22);
+    ALLOC(p.touched, p.touched_cap); ALLOC(p.touch_mark, h->cap);
+    CK(cudaMemset(p.touch_mark, 0, h->cap * sizeof(int32_t)));
+    CK(cudaMemset(p.band_count, 0, (h->n_buckets + 2) * sizeof(int32_t)));
     ALLOC(h->d_tile_sums, (h->n_buckets + SCAN_TILE - 1) / SCAN_TILE + 1);
     p.key0 = (uint32_t)cfg->seed; p.key1 = (uint32_t)(cfg->seed >> 32);
     if (cfg->cheb_coef && cfg->cheb_n > 0) {
@@ -468,7 +473,7 @@ extern "C" int amc_step(amc_handle *h, int32_t n_steps, amc_step_stats *stats)
                     h->last_launches += 1;
                     CK(cudaEventRecord(h->events[4 * s + 1], h->stream));
                 } else { // fused: keys of the post-step positions, then the step itself on the way to the sorted slot
-                    CK(cudaMemsetAsync(p.band_count, 0, (h->n_buckets + 1) * sizeof(int32_t), h->stream));
+                    CK(cudaMemsetAsync(p.band_count, 0, (h->n_buckets + 2) * sizeof(int32_t), h->stream));
                     CK(cudaMemsetAsync(p.rest_count, 0, (h->n_buckets + 1) * sizeof(int32_t), h->stream));
                     k_keys<false><<<grid_for(h->n, ADVECT_THREADS), ADVECT_THREADS, 0, h->stream>>>(p, phase);
                     CK(cudaEventRecord(h->events[4 * s + 1], h->stream));
@@ -488,7 +493,8 @@ extern "C" int amc_step(amc_handle *h, int32_t n_steps, amc_step_stats *stats)
                 if (rc != AMC_OK) return rc;
                 CK(cudaEventRecord(h->events[4 * s + 3], h->stream));
                 if (has_recap && s == chunk - 1) { // last step of the call: close it now
-                    k_recapture_post<<<grid_for(h->n, ADVECT_THREADS), ADVECT_THREADS, 0, h->stream>>>(p);
+                    if (sweep) k_recapture_post<<<grid_for(h->n, ADVECT_THREADS), ADVECT_THREADS, 0, h->stream>>>(p);
+                    else k_recapture_list<<<148, ADVECT_THREADS, 0, h->stream>>>(p);
                     h->last_launches += 1;
                 }
                 CK(cudaEventRecord(h->events[4 * s + 4], h->stream));
@@ -588,7 +594,7 @@ extern "C" int amc_pairs(amc_handle *h, amc_step_stats *stats)
         if (p.pp_mode == AMC_PP_SWEEP) {
             if ((rc = unsort(h)) != AMC_OK) return rc;
         } else {
-            CK(cudaMemsetAsync(p.band_count, 0, (h->n_buckets + 1) * sizeof(int32_t), h->stream));
+            CK(cudaMemsetAsync(p.band_count, 0, (h->n_buckets + 2) * sizeof(int32_t), h->stream));
             CK(cudaMemsetAsync(p.rest_count, 0, (h->n_buckets + 1) * sizeof(int32_t), h->stream));
             k_advect<<<grid_for(h->n, ADVECT_THREADS), ADVECT_THREADS, 0, h->stream>>>(p, PH_KEYS);
             if ((rc = sort_scatter(h, nullptr)) != AMC_OK) return rc;
@@ -788,6 +794,8 @@ extern "C" int amc_set_step_index(amc_handle *h, int64_t step)
 {
     if (!h) return AMC_E_INVALID;
     h->step_index = step;
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemsetAsync(h->p.touch_mark, 0, h->cap * sizeof(int32_t), h->stream)); /* the per-slot step tags of touch_slot */
     return AMC_OK;
 }
 
@@ -919,7 +927,7 @@ extern "C" int amc_slab_advect(amc_handle *h)
     CK(cudaMemsetAsync(h->d_stats, 0, sizeof(StatsDev), h->stream));
     CK(cudaMemsetAsync(h->d_counters, 0, (p.nranks + 8) * sizeof(int32_t), h->stream));
     CK(cudaMemsetAsync(p.rel_id, 0xff, (size_t)p.rel_cap * sizeof(int32_t), h->stream));
-    CK(cudaMemsetAsync(p.band_count, 0, (h->n_buckets + 1) * sizeof(int32_t), h->stream));
+    CK(cudaMemsetAsync(p.band_count, 0, (h->n_buckets + 2) * sizeof(int32_t), h->stream));
     CK(cudaMemsetAsync(p.rest_count, 0, (h->n_buckets + 1) * sizeof(int32_t), h->stream));
     h->slab_phase = PH_DRIFT | PH_WALLS | (p.kind != AMC_KIND_CUBE ? PH_RECAP : 0);
     if (h->n) k_keys<true><<<grid_for(h->n, ADVECT_THREADS), ADVECT_THREADS, 0, h->stream>>>(p, h->slab_phase);
@@ -1015,7 +1023,7 @@ extern "C" int amc_slab_finish(amc_handle *h, amc_step_stats *stats)
     P &p = h->p;
     int32_t nf = 0;
     CK(cudaMemcpyAsync(&nf, p.n_foreign, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
-    if (h->n && p.kind != AMC_KIND_CUBE) k_recapture_post<<<grid_for(h->n, ADVECT_THREADS), ADVECT_THREADS, 0, h->stream>>>(p);
+    if (h->n && p.kind != AMC_KIND_CUBE) k_recapture_list<<<148, ADVECT_THREADS, 0, h->stream>>>(p);
     unsigned long long ovf[4] = {0, 0, 0, 0};
     CK(cudaMemcpyAsync(ovf, h->d_slab_overflow, sizeof(ovf), cudaMemcpyDeviceToHost, h->stream));
     rc = phase_end(h, stats);

@@ -126,6 +126,10 @@ struct P {
     int32_t foreign_cap;
     int32_t group_done;       /* last finished colour group (-1 before the first) */
     unsigned long long *slab_overflow;
+    int32_t *touched;         /* slots the closing recapture of this step has to look at (touch_slot) */
+    int32_t *touched_n;       /* lives behind the last band counter: cleared with them at the start of a step */
+    int32_t *touch_mark;      /* [cap] step tag of the last listing of each slot */
+    int32_t touched_cap;
     int32_t esc_cap;
     int32_t *esc_count;
     int32_t *esc_slot;
@@ -611,4 +615,13 @@ __device__ __forceinline__ int32_t rel_find(const P &p, int32_t id)
         if (k == -1) return -1;
         h = (h + 1) & mask;
     }
+}
+
+// see k_recapture_list (amc_kernels.cuh)
+__device__ __forceinline__ void touch_slot(const P &p, const int32_t s)
+{
+    const int32_t tag = 1 + (int32_t)(p.step & 0x3fffffff); /* per-slot marker: listed in this step already */
+    if (atomicExch(&p.touch_mark[s], tag) == tag) return;
+    int i = atomicAdd(p.touched_n, 1);
+    if (i < p.touched_cap) p.touched[i] = s;
 }

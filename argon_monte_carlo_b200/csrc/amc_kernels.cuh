@@ -285,6 +285,11 @@ __global__ void __launch_bounds__(ADVECT_THREADS, 3) k_scatter_advect(const __gr
     q.flag = fl & (SLAB ? AMC_FLAG_KEEP : AMC_FLAG_PATH);
     store_part(p.b, t, q);
     p.b.id[t] = id;
+    if ((phase & PH_RECAP) && k <= p.ncell_pad) { // still out of bounds after this step's recapture: the closing one must see it
+        Part c = q;
+        bool again = p.kind == AMC_KIND_TEMP ? (temp_oob(p.g, c) != 0) | (temp_recapture(p.g, c) != 0) : (p.kind == AMC_KIND_PORE && pore_recapture(p.g, c) != 0);
+        if (again) touch_slot(p, (int32_t)t);
+    }
     if (SLAB) {
         p.skey[t] = k;
         if (k <= p.ncell_pad && (fl & (AMC_FLAG_GHOST | AMC_FLAG_REL_UP | AMC_FLAG_REL_DOWN))) rel_insert(p, id, (int32_t)t);
@@ -436,6 +441,40 @@ __global__ void __launch_bounds__(ADVECT_THREADS) k_recapture_post(const __grid_
     if (q.x != x0) p.a.x[s] = q.x;
     if (q.y != y0) p.a.y[s] = q.y;
     if (q.z != z0) p.a.z[s] = q.z;
+}
+
+// Only a particle that a collision moved (or that the walls + recapture of this step left out of bounds) can be
+// touched by the recapture that closes the pair pass, so the step keeps a list of those slots and the closing
+// recapture visits just them: same result as k_recapture_post over everything, a few microseconds instead of a
+// pass over all positions.  The list is de-duplicated through a per-slot step tag; an overflowing list makes the
+// kernel fall back to the full pass.
+__device__ __forceinline__ void recapture_slot(const P &p, const int64_t s)
+{
+    if (p.slab && (p.a.flag[s] & AMC_FLAG_GHOST)) return; /* the owning rank recaptures it */
+    Part q;
+    q.x = p.a.x[s]; q.y = p.a.y[s]; q.z = p.a.z[s];
+    double x0 = q.x, y0 = q.y, z0 = q.z;
+    int cnt = p.kind == AMC_KIND_TEMP ? temp_oob(p.g, q) : 0;
+    int moved = p.kind == AMC_KIND_TEMP ? temp_recapture(p.g, q) : pore_recapture(p.g, q);
+    if (p.kind != AMC_KIND_TEMP) cnt = moved;
+    if (cnt) atomicAdd(&p.stats->oob_pp, (unsigned long long)cnt);
+    if (p.kind == AMC_KIND_TEMP && moved) {
+        int after = temp_oob(p.g, q);
+        if (after) atomicAdd(&p.stats->oob_pp_after, (unsigned long long)after);
+    }
+    if (q.x != x0) p.a.x[s] = q.x;
+    if (q.y != y0) p.a.y[s] = q.y;
+    if (q.z != z0) p.a.z[s] = q.z;
+}
+__global__ void __launch_bounds__(ADVECT_THREADS) k_recapture_list(const __grid_constant__ P p)
+{
+    const int nt = *p.touched_n;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x, first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (nt > p.touched_cap) { /* list overflowed: everything */
+        for (int64_t s = first; s < p.n; s += stride) recapture_slot(p, s);
+    } else {
+        for (int64_t i = first; i < nt; i += stride) recapture_slot(p, p.touched[i]);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -675,7 +714,7 @@ __device__ __forceinline__ void activate_moved(const P &p, CellShared &S, const 
     const int tid = threadIdx.x, nthreads = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
     const int n = S.n;
     for (int k = tid; k < n; k += nthreads)
-        if (S.mv[k]) S.mvlist[atomicAdd(&S.nmv, 1)] = (uint16_t)k;
+        if (S.mv[k]) { S.mvlist[atomicAdd(&S.nmv, 1)] = (uint16_t)k; touch_slot(p, S.slot[k]); }
     __syncthreads();
     const int nmv = S.nmv;
     const Arrays &A = p.a;
@@ -1518,6 +1557,7 @@ __global__ void __launch_bounds__(128) k_bnd_apply(const __grid_constant__ P p)
             else { p.esc_slot[e] = s; nf |= AMC_FLAG_ESC; }
         }
         A.flag[s] = (uint8_t)nf;
+        touch_slot(p, s);
     }
     const unsigned FULL = 0xffffffffu;
     const int o0 = __shfl_sync(FULL, o[0], 0), o1 = __shfl_sync(FULL, o[1], 0), o2 = __shfl_sync(FULL, o[2], 0);

@@ -19,9 +19,12 @@ def test_pore_forty_steps_still_bit_identical(oracle, pore_cfg, pore_init):
     st = oracle.ParticleState(*pore_init)
     sim = amc.Simulation(pore_cfg)
     sim.set_state(*pore_init)
-    ref = [steps.pore_step(st, pore_cfg)["collisions"] for _ in range(40)]
-    got = [s["collisions"] for s in sim.step(40)]
-    assert got == ref
+    ref = [steps.pore_step(st, pore_cfg) for _ in range(40)]
+    got = sim.step(40)
+    assert [s["collisions"] for s in got] == [r["collisions"] for r in ref]
+    # the detection pass skips ~99 % of the cell visits; the reference-equivalent test counter must not notice
+    # (cells a moved particle enters or leaves are visited, the others are counted from the detection snapshot)
+    assert [s["pair_checks_ref"] for s in got] == [r["checks"] for r in ref]
     state = sim.get_state()
     for k in KEYS:
         assert np.array_equal(state[k], getattr(st, k)), k
