@@ -50,30 +50,60 @@ def owner_layer(z, edges):
     return np.clip(k, 0, len(edges) - 2)
 
 
-def balanced_cuts(z, edges, nranks, min_layers=2, prefer_odd=True):
-    """Cut indices (nranks+1) on z-cell boundaries with ~equal particle counts per slab."""
+def _greedy_cuts(cum, nranks, limit, min_layers, odd_only):
+    """Cuts such that no slab holds more than `limit` particles, each slab as thick as it can be; None if that takes
+    more than nranks slabs.  odd_only: interior cuts on odd layers."""
+    ncz = len(cum) - 1
+    cuts = [0]
+    for r in range(1, nranks + 1):
+        lo = cuts[-1] + min_layers
+        hi = ncz - (nranks - r) * min_layers
+        if r == nranks:
+            if cum[ncz] - cum[cuts[-1]] > limit:
+                return None
+            cuts.append(ncz)
+            break
+        k = int(np.searchsorted(cum, cum[cuts[-1]] + limit, side="right")) - 1   # thickest slab within the limit
+        k = min(k, hi)
+        if odd_only and k % 2 == 0:
+            k -= 1
+        if k < lo:
+            return None
+        cuts.append(k)
+    return cuts
+
+
+def balanced_cuts(z, edges, nranks, min_layers=2, prefer_odd=True, odd_tolerance=0.03):
+    """Cut indices (nranks+1) on z-cell boundaries that minimise the particle count of the fullest slab (bisection on
+    that count with a greedy feasibility test).  Odd cuts are preferred -- the cells just above an odd cut belong to
+    the odd z colour groups, so a ghost that has to be exported late (an immigrant that lands in the band below the
+    cut) is only needed from group 1 on and travels with the hand-over after group 0, no extra round before it --
+    unless they make the fullest slab more than odd_tolerance fuller than the unconstrained optimum."""
     ncz = len(edges) - 1
     if nranks * min_layers > ncz:
         raise ValueError("too many ranks for %d z layers" % ncz)
     hist = np.bincount(owner_layer(np.asarray(z), np.asarray(edges)), minlength=ncz).astype(np.float64)
     cum = np.concatenate([[0.0], np.cumsum(hist)])
-    cuts = [0]
-    for r in range(1, nranks):
-        target = cum[-1] * r / nranks
-        k = int(np.searchsorted(cum, target))
-        k = max(k, cuts[-1] + min_layers)
-        k = min(k, ncz - (nranks - r) * min_layers)
-        # prefer odd cuts: the cells just above an odd cut belong to the odd z colour groups, so a ghost
-        # that has to be exported late (an immigrant that lands in the band below the cut) is only needed
-        # from group 1 on and can travel with the hand-over after group 0 -- no extra round before it
-        if k % 2 == 0 and prefer_odd:
-            if k + 1 <= ncz - (nranks - r) * min_layers:
-                k += 1
-            elif k - 1 >= cuts[-1] + min_layers:
-                k -= 1
-        cuts.append(k)
-    cuts.append(ncz)
-    return np.array(cuts, dtype=np.int32)
+
+    def best(odd_only):
+        lo, hi = cum[-1] / nranks, cum[-1]
+        if _greedy_cuts(cum, nranks, hi, min_layers, odd_only) is None:
+            return None, np.inf
+        for _ in range(60):
+            mid = 0.5 * (lo + hi)
+            if _greedy_cuts(cum, nranks, mid, min_layers, odd_only) is None:
+                lo = mid
+            else:
+                hi = mid
+        cuts = _greedy_cuts(cum, nranks, hi, min_layers, odd_only)
+        return cuts, max(cum[b] - cum[a] for a, b in zip(cuts, cuts[1:]))
+
+    free, load_free = best(False)
+    if prefer_odd and nranks > 1:
+        odd, load_odd = best(True)
+        if odd is not None and load_odd <= load_free * (1.0 + odd_tolerance):
+            return np.array(odd, dtype=np.int32)
+    return np.array(free, dtype=np.int32)
 
 
 def local_grid(grid, z0, z1):
