@@ -63,6 +63,18 @@ class AmcStepStats(C.Structure):
         return d
 
 
+INIT_MAX_REGIONS = 8
+
+
+class AmcInitSpec(C.Structure):
+    """struct amc_init_spec (include/amc.h): synthetic Maxwellian state generated on the device."""
+    _fields_ = [("n_total", C.c_int64), ("seed", C.c_uint64), ("n_regions", C.c_int32), ("shape", C.c_int32),
+                ("cum_weight", C.c_double * INIT_MAX_REGIONS), ("radius", C.c_double * INIT_MAX_REGIONS),
+                ("bx", C.c_double * INIT_MAX_REGIONS), ("by", C.c_double * INIT_MAX_REGIONS),
+                ("z_lo", C.c_double * INIT_MAX_REGIONS), ("z_hi", C.c_double * INIT_MAX_REGIONS),
+                ("sigma", C.c_double), ("keep_z_lo", C.c_double), ("keep_z_hi", C.c_double)]
+
+
 class AmcError(RuntimeError):
     pass
 
@@ -74,7 +86,7 @@ EXPORTS = ("amc_create", "amc_destroy", "amc_last_error", "amc_abi_version", "am
            "amc_num_particles", "amc_step", "amc_drift", "amc_walls", "amc_recapture", "amc_pairs", "amc_wall_case",
            "amc_wall_hits_pending", "amc_wall_apply_directions", "amc_get_histograms", "amc_get_pair_list",
            "amc_get_wall_bits", "amc_get_completed_paths", "amc_clear_taps", "amc_set_step_index", "amc_last_timing",
-           "amc_last_detect_ms",
+           "amc_last_detect_ms", "amc_init_synthetic",
            "amc_get_outputs_raw", "amc_set_outputs_raw", "amc_get_step_index",
            "amc_slab_enable", "amc_set_stream", "amc_set_ids", "amc_slab_advect", "amc_slab_sort", "amc_slab_pairs_begin",
            "amc_slab_group", "amc_slab_apply", "amc_slab_finish", "amc_slab_get_owned")
@@ -208,6 +220,14 @@ class Simulation:
                                     fl.ctypes.data_as(c_uint8_p) if fl is not None else None)
         self._check(rc, "amc_set_state")
         self.n = n
+
+    def init_synthetic(self, spec):
+        """Generate the synthetic Maxwellian state described by an AmcInitSpec on the device (init_state.pore_spec /
+        cube_spec build one); returns the number of particles this handle holds afterwards."""
+        n = C.c_int64(0)
+        self._check(self.lib.amc_init_synthetic(self.h, C.byref(spec), C.byref(n)), "amc_init_synthetic")
+        self.n = int(n.value)
+        return self.n
 
     def get_state(self, out=None):
         """dict of the ten float64 arrays and the uint8 flag, original particle index order.

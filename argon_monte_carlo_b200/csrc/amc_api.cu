@@ -353,6 +353,32 @@ extern "C" int amc_set_state(amc_handle *h, int64_t n, const double *x, const do
     return AMC_OK;
 }
 
+extern "C" int amc_init_synthetic(amc_handle *h, const amc_init_spec *spec, int64_t *n_kept)
+{
+    if (!h || !spec) return AMC_E_INVALID;
+    if (spec->n_total < 0 || spec->n_total > 0x7fffffffLL) return h->fail(AMC_E_INVALID, "n_total out of range");
+    if (spec->n_regions < 1 || spec->n_regions > AMC_INIT_MAX_REGIONS) return h->fail(AMC_E_INVALID, "n_regions out of range");
+    if (spec->shape != 0 && spec->shape != 1) return h->fail(AMC_E_INVALID, "bad shape");
+    if (!(spec->sigma >= 0.0)) return h->fail(AMC_E_INVALID, "bad sigma");
+    const bool keep_all = std::isinf(spec->keep_z_lo) && spec->keep_z_lo < 0 && std::isinf(spec->keep_z_hi) && spec->keep_z_hi > 0;
+    if (keep_all && spec->n_total > h->cap) return h->fail(AMC_E_INVALID, "n_total exceeds max_particles");
+    CK(cudaSetDevice(h->device));
+    int32_t *cnt = h->p.wl_count + 20; /* spare counter of the pair-pass block */
+    CK(cudaMemsetAsync(cnt, 0, sizeof(int32_t), h->stream));
+    if (spec->n_total)
+        k_init_synthetic<<<148 * 8, ADVECT_THREADS, 0, h->stream>>>(h->p, *spec, keep_all ? 1 : 0, cnt, h->cap);
+    CK(cudaGetLastError());
+    int32_t c = 0;
+    CK(cudaMemcpyAsync(&c, cnt, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    int64_t n = keep_all ? spec->n_total : c;
+    if (n > h->cap) return h->fail(AMC_E_CAPACITY, "max_particles too small for the particles of this slab");
+    h->n = n;
+    h->p.n = n;
+    if (n_kept) *n_kept = n;
+    return AMC_OK;
+}
+
 // bring the state back to original index order (slot == id); b arrays are scratch between phases
 static int unsort(amc_handle *h)
 {

@@ -1420,6 +1420,49 @@ __global__ void __launch_bounds__(ADVECT_THREADS) k_case_apply(const __grid_cons
     out_dpz[k] = dpz; out_de[k] = c == AMC_CASE_4 ? 0.0 : dE;
     store_part(p.a, s, q);
 }
+// synthetic Maxwellian state (amc_init_synthetic): one thread per global particle index, grid-stride
+__global__ void __launch_bounds__(ADVECT_THREADS) k_init_synthetic(const __grid_constant__ P p, const __grid_constant__ amc_init_spec sp,
+                                                                   const int keep_all, int32_t *count, const int64_t cap)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const uint32_t k0 = (uint32_t)sp.seed, k1 = (uint32_t)(sp.seed >> 32);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < sp.n_total; i += stride) {
+        double u[8];
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            uint32_t r[4] = {(uint32_t)i, (uint32_t)((uint64_t)i >> 32), 0x1417u, (uint32_t)c};
+            philox4x32_10(r, k0, k1);
+            u[2 * c] = u53(r[0], r[1]); u[2 * c + 1] = u53(r[2], r[3]);
+        }
+        int reg = 0;
+        while (reg + 1 < sp.n_regions && u[0] >= sp.cum_weight[reg]) reg++;
+        double x, y;
+        if (sp.shape == 0) {
+            double rr = sp.radius[reg] * sqrt(u[1]), s, c;
+            sincos(6.283185307179586 * u[2], &s, &c);
+            x = rr * c; y = rr * s;
+        } else {
+            x = sp.bx[reg] * u[1]; y = sp.by[reg] * u[2];
+        }
+        const double z = sp.z_lo[reg] + (sp.z_hi[reg] - sp.z_lo[reg]) * u[3];
+        if (!keep_all && !(z >= sp.keep_z_lo && z < sp.keep_z_hi)) continue;
+        double s1, c1, s2, c2;
+        const double r1 = sp.sigma * sqrt(-2.0 * log(1.0 - u[4])), r2 = sp.sigma * sqrt(-2.0 * log(1.0 - u[6]));
+        sincos(6.283185307179586 * u[5], &s1, &c1);
+        sincos(6.283185307179586 * u[7], &s2, &c2);
+        int64_t t = i;
+        if (!keep_all) {
+            t = atomicAdd(count, 1);
+            if (t >= cap) continue; /* reported by the host from the final count */
+        }
+        p.a.x[t] = x; p.a.y[t] = y; p.a.z[t] = z;
+        p.a.vx[t] = r1 * c1; p.a.vy[t] = r1 * s1; p.a.vz[t] = r2 * c2;
+        p.a.d[t] = 0.0; p.a.dx[t] = 0.0; p.a.dy[t] = 0.0; p.a.dz[t] = 0.0;
+        p.a.flag[t] = 0;
+        p.a.id[t] = (int32_t)i;
+    }
+}
+
 __global__ void k_iota(int32_t *ids, int64_t n)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

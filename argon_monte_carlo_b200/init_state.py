@@ -187,3 +187,38 @@ def synthetic_pore_chunked(cfg, seed: int = 17, chunk_size: int = 1 << 22, keep=
             ids, arrs = ids[m], [a[m] for a in arrs]
         parts.append((ids, *arrs))
     return tuple(np.concatenate([p[i] for p in parts]) for i in range(7))
+
+
+# ---------------------------------------------------------------- device-side generation (amc_init_synthetic)
+def _spec(n_total, seed, shape, weights, radius, bx, by, z_lo, z_hi, sigma, keep_z=None):
+    from .amc import AmcInitSpec, INIT_MAX_REGIONS
+    sp = AmcInitSpec()
+    k = len(weights)
+    if not 1 <= k <= INIT_MAX_REGIONS:
+        raise ValueError("1..%d regions" % INIT_MAX_REGIONS)
+    cum = np.cumsum(np.asarray(weights, dtype=np.float64) / np.sum(weights))
+    cum[-1] = 1.0
+    sp.n_total, sp.seed, sp.n_regions, sp.shape, sp.sigma = int(n_total), int(seed), k, int(shape), float(sigma)
+    for r in range(k):
+        sp.cum_weight[r] = cum[r]
+        sp.radius[r], sp.bx[r], sp.by[r] = float(radius[r]), float(bx[r]), float(by[r])
+        sp.z_lo[r], sp.z_hi[r] = float(z_lo[r]), float(z_hi[r])
+    sp.keep_z_lo, sp.keep_z_hi = (-np.inf, np.inf) if keep_z is None else (float(keep_z[0]), float(keep_z[1]))
+    return sp
+
+
+def pore_spec(cfg, seed: int = 17, keep_z=None):
+    """The synthetic Maxwellian pore of synthetic_pore_chunk (same regions, weights and margins) as an
+    AmcInitSpec for Simulation.init_synthetic; keep_z = (z_lo, z_hi): only that slab."""
+    a, h = cfg.argon_radius, cfg.open_air_height
+    vols = [cfg.open_air_volume, cfg.hot_volume, cfg.gap_volume, cfg.cold_volume, cfg.open_air_volume]
+    radii = [cfg.open_air_radius - a, cfg.pore_coated_radius - a, cfg.gap_radius - a, cfg.pore_coated_radius - a,
+             cfg.open_air_radius - a]
+    zlo = [a, h, cfg.gap_bottom_height + a, cfg.gap_top_height, cfg.total_height - h + a]
+    zhi = [h - a, cfg.gap_bottom_height, cfg.gap_top_height - a, cfg.total_height - h, cfg.total_height - a]
+    return _spec(cfg.num_molecules, seed, 0, vols, radii, [0] * 5, [0] * 5, zlo, zhi, cfg.a_shape, keep_z)
+
+
+def cube_spec(cfg, n: int, seed: int = 127, keep_z=None):
+    """n particles uniform in the cube, Gaussian velocity components (config 4)."""
+    return _spec(n, seed, 1, [1.0], [0.0], [cfg.cube_x], [cfg.cube_y], [0.0], [cfg.cube_z], cfg.a_shape, keep_z)

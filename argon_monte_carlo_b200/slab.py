@@ -311,6 +311,20 @@ class SlabSimulation:
                             np.asarray(vz)[m], opt(dist, m), opt(dist_x, m), opt(dist_y, m), opt(dist_z, m), opt(flag, m))
             r.call("amc_set_ids", ids.ctypes.data_as(amc.c_int64_p))
 
+    def init_synthetic(self, make_spec):
+        """Generate the state on the devices (amc_init_synthetic): make_spec(keep_z) returns the AmcInitSpec of the
+        whole job restricted to a z range, e.g. lambda kz: init_state.pore_spec(cfg, 17, keep_z=kz).  Every local rank
+        keeps the particles of its own layers; particle i is the same whatever the number of ranks."""
+        edges = self.grid.edge[2]
+        n_global = 0
+        for r in self.ranks:
+            lo = -np.inf if r.rank == 0 else float(edges[self.cuts[r.rank]])
+            hi = np.inf if r.rank == len(self.cuts) - 2 else float(edges[self.cuts[r.rank + 1]])
+            spec = make_spec((lo, hi))
+            r.sim.init_synthetic(spec)
+            n_global = int(spec.n_total)
+        self.n_global = n_global
+
     def set_local_state(self, ids, x, y, z, vx, vy, vz, dist=None, dist_x=None, dist_y=None, dist_z=None, flag=None,
                         n_global=None):
         """Distributed use: this process's single rank receives exactly the particles it owns."""

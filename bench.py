@@ -196,10 +196,15 @@ def run_ours(args):
     # ---------------------------------------------------------------- main workload
     m = args.particles_per_gpu
     cfg, scale = scaled_temp_config(m)          # each rank: one domain of m particles (weak scaling)
-    state = init_state.synthetic_pore_state(cfg, seed=17 + rank)
-    n = len(state[0])
-    sim = amc.Simulation(cfg, seed=17 + rank, device=local, max_particles=n)
-    sim.set_state(*state)
+    if args.device_init:   # the same synthetic gas, generated by the device-side initialiser (amc_init_synthetic)
+        n = cfg.num_molecules
+        sim = amc.Simulation(cfg, seed=17 + rank, device=local, max_particles=n)
+        sim.init_synthetic(init_state.pore_spec(cfg, seed=17 + rank))
+    else:
+        state = init_state.synthetic_pore_state(cfg, seed=17 + rank)
+        n = len(state[0])
+        sim = amc.Simulation(cfg, seed=17 + rank, device=local, max_particles=n)
+        sim.set_state(*state)
     for _ in range(args.warmup):
         sim.step_quiet(1)
     clocks = ClockSampler(local)
@@ -472,6 +477,7 @@ def main():
     ap.add_argument("--workload", default="temp_pore", choices=["temp_pore", "cube"],
                     help="temp_pore (default, the headline workload) or cube (BASELINE config 4, secondary)")
     ap.add_argument("--cube-particles", type=int, default=10_000_000)
+    ap.add_argument("--device-init", action="store_true", help="1 GPU: generate the synthetic state on the device instead of on the host")
     ap.add_argument("--no-also", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -161,6 +161,28 @@ int amc_wall_hits_pending(amc_handle *h, int32_t case_id, int64_t cap, int64_t *
 int amc_wall_apply_directions(amc_handle *h, int32_t case_id, int64_t n_hits, const int64_t *idx, const double *dir3,
                               const double *surf_e, double *dpz, double *de, int64_t *errors);
 
+/* Synthetic Maxwellian initial state generated on the device (replaces init_positions / init_velocities,
+ * Pore:106-158, for the synthetic configurations of BASELINE.json: 10 M-particle cube, 100 M-particle pore, where
+ * the host-side generators take minutes).  Particle i depends only on (seed, i): Philox4x32-10 with counter
+ * (i, stream) gives its region (cumulative weights), a uniform position inside the region (cylinder about the z axis
+ * or box) and velocity components ~ N(0, sigma^2) (Box-Muller).  keep_z_lo <= z < keep_z_hi selects the particles
+ * that stay on this handle (one slab of a multi-GPU run; -inf / +inf: all of them, stored with slot == i);
+ * ids (amc_set_ids) are set to i.  Path accumulators and flags start at zero. */
+#define AMC_INIT_MAX_REGIONS 8
+typedef struct amc_init_spec {
+    int64_t n_total;                           /* particles of the whole job */
+    uint64_t seed;
+    int32_t n_regions;                         /* 1 .. AMC_INIT_MAX_REGIONS */
+    int32_t shape;                             /* 0: cylinders about the z axis (radius, z_lo, z_hi); 1: boxes [0,bx] x [0,by] x [z_lo,z_hi] */
+    double cum_weight[AMC_INIT_MAX_REGIONS];   /* cumulative region probabilities, last one 1.0 */
+    double radius[AMC_INIT_MAX_REGIONS];
+    double bx[AMC_INIT_MAX_REGIONS], by[AMC_INIT_MAX_REGIONS];
+    double z_lo[AMC_INIT_MAX_REGIONS], z_hi[AMC_INIT_MAX_REGIONS];
+    double sigma;                              /* sqrt(k_B T / m), Cube:56 */
+    double keep_z_lo, keep_z_hi;
+} amc_init_spec;
+int amc_init_synthetic(amc_handle *h, const amc_init_spec *spec, int64_t *n_kept);
+
 /* outputs: completed free paths (the four lists Pore:410-413) as device-side histograms with
  * np.histogram's uniform-bin rule (Pore:575-596), their count and sums (for the printed means
  * Pore:565-568).  counts: [4][AMC_NUM_BINS] in the order total, x, y, z. */
