@@ -192,6 +192,16 @@ static int create_impl(amc_handle *h, const amc_config *cfg, int device)
         p.gt_Roa = sq_threshold_gt(cfg->geom.R_oa); p.gt_Rp = sq_threshold_gt(cfg->geom.R_p); p.gt_Rg = sq_threshold_gt(cfg->geom.R_g);
         p.lt_Rp = sq_threshold_lt(cfg->geom.R_p); p.lt_Rg = sq_threshold_lt(cfg->geom.R_g);
     }
+    if (cfg->kind == AMC_KIND_TEMP) {
+        const amc_geom &g = cfg->geom;
+        const double zs[8] = {g.oah, g.zh3, g.z_gb, g.zgb_p, g.z_gt, g.zgt_m, g.z_cold, g.zc3};
+        double zA = g.H, zB = 0.0;
+        for (double v : zs) { zA = std::min(zA, v); zB = std::max(zB, v); }
+        p.calm_zA = zA; p.calm_zB = zB;
+        p.calm_rA = std::min(p.gt_Roa, g.R_oa_sq);
+        p.calm_rC = std::min(std::min(std::min(p.calm_rA, g.R_p_sq), std::min(g.R_g_c_sq, g.R_p_c_sq)), g.R_g_sq);
+        p.calm_ok = zA > 0.0 && zB < g.H && p.calm_rA > 0.0 && p.calm_rC > 0.0;
+    }
     int64_t ncell = 1;
     for (int a = 0; a < 3; a++) {
         p.nc[a] = cfg->nc[a]; p.pnc[a] = cfg->nc[a] + 1;

@@ -68,6 +68,11 @@ struct P {
     /* exact squared-radius thresholds: sqrt(v) > R <=> v > gt_*,  sqrt(v) < R <=> v < lt_* (sqrt is monotone and
        correctly rounded; the values are found on the host by stepping through neighbouring doubles) */
     double gt_Roa, gt_Rp, gt_Rg, lt_Rp, lt_Rg;
+    /* calm regions of the energized pore (advance_particle): below calm_zA / above calm_zB no z comparison of the wall
+       masks, the recapture or the out-of-bounds census can fire; inside calm_rA (squared) the open-air wall cannot,
+       inside calm_rC no radial comparison at all */
+    double calm_zA, calm_zB, calm_rA, calm_rC;
+    int32_t calm_ok;
     uint32_t key0, key1;
     int64_t step;
     const double *cheb;

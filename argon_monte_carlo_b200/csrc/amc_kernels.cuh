@@ -159,6 +159,29 @@ __global__ void __launch_bounds__(ADVECT_THREADS, 4) k_advect(const __grid_const
 template <int MODE>
 __device__ __forceinline__ void advance_particle(const P &p, Part &q, const int32_t id, const int phase)
 {
+    // Calm particles (energized pore, ~95 % of the gas): both the position before the drift and the one after it
+    // lie in one of three regions in which every wall mask (Temp:693-753), every recapture condition (Temp:594-616)
+    // and every out-of-bounds count (Temp:560-592) is false whatever the other coordinates are -- the interior of the
+    // bottom end cap (below every z threshold, inside the open-air radius), of the top end cap (above every z
+    // threshold) and the core of the pore (inside every radius, between the end plates); the bounds are the min / max
+    // of the geometry's thresholds, computed in amc_api.cu.  For them the whole step is the drift.
+    if (p.calm_ok && (phase & (PH_DRIFT | PH_WALLS | PH_RECAP)) == (PH_DRIFT | PH_WALLS | PH_RECAP)) {
+        const double ax = p.dt * q.vx, ay = p.dt * q.vy, az = p.dt * q.vz;
+        const double nx = q.x + ax, ny = q.y + ay, nz = q.z + az;
+        const double rmax = fmax(q.x * q.x + q.y * q.y, nx * nx + ny * ny), zmin = fmin(q.z, nz), zmax = fmax(q.z, nz);
+        const bool calm = (rmax <= p.calm_rA && ((zmin >= 0.0 && zmax < p.calm_zA) || (zmin > p.calm_zB && zmax <= p.g.H))) ||
+                          (rmax < p.calm_rC && zmin >= 0.0 && zmax <= p.g.H);
+        if (calm) {
+            q.px = q.x; q.py = q.y; q.pz = q.z;
+            q.x = nx; q.y = ny; q.z = nz;
+            if (MODE != AMC_DRY) {
+                q.d += fabs(sqrt((ax * ax + ay * ay) + az * az));
+                q.dx += fabs(ax); q.dy += fabs(ay); q.dz += fabs(az);
+            }
+            if (MODE == AMC_LIVE && p.wall_bits) p.wall_bits[id] = 0;
+            return;
+        }
+    }
     if (phase & PH_RECAP_POST) { // recapture that closes the previous step's pair pass (Pore:550 / Temp:843-845)
         int cnt = p.kind == AMC_KIND_TEMP ? temp_oob(p.g, q) : 0;
         int moved = p.kind == AMC_KIND_TEMP ? temp_recapture(p.g, q) : pore_recapture(p.g, q);
