@@ -265,6 +265,7 @@ static int create_impl(amc_handle *h, const amc_config *cfg, int device)
         p.wl_next = p.wl_count + 8;
         p.dl_count = p.wl_count + 16;
         ALLOC(p.dl, (size_t)cfg->nc[0] * cfg->nc[1] * cfg->nc[2] * AMC_WI); ALLOC(p.cell_n, per_group * 8);
+        ALLOC(p.wl_hit, (size_t)per_group * 8 * AMC_HIT_REC);
         CK(cudaMemset(p.wl_count, 0, AMC_WL_COUNTERS * sizeof(int32_t)));
         CK(cudaMemset(p.cell_active, 0, per_group * 8 * sizeof(int32_t)));
         CK(cudaMemset(p.cell_n, 0, per_group * 8 * sizeof(int32_t)));

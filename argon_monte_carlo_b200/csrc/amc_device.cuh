@@ -24,6 +24,9 @@
 #define AMC_MAX_MEMBERS 512  /* particles per reference cell incl. overlap band (reference: <= 308) */
 #define AMC_MAX_CAND 64     /* simultaneously overlapping pairs per cell visit */
 #define AMC_WI 32            /* ints per work item: cell, kx, ky, kz, beg[8], len[8], 6 doubles of bounds = 128 bytes */
+#define AMC_MAX_HITS 8      /* filter hits of one cell that k_detect hands to the resolution as a list */
+#define AMC_HIT_REC (1 + 2 * AMC_MAX_HITS) /* ints per work item in wl_hit: count (-1: search the cell), then slot pairs */
+#define AMC_CELL_DIRTY 0x40000000 /* bit of cell_n: a particle entered / left the cell after k_detect looked at it */
 #define AMC_WL_COUNTERS 24 /* wl_count[8], wl_next[8], dl_count, padding */
 #define AMC_XBINS 64         /* slabs along x of the in-CTA neighbour search (multiple of 32) */
 #define AMC_SUB_MIN_N 48     /* below this many members the plain all-pairs scan is cheaper */
@@ -94,6 +97,7 @@ struct P {
     int32_t *wl;          /* [8][wl_stride][AMC_WI] work items: the cells of each colour group that can hold a pair */
     int32_t *wl_count;    /* [8] */
     int32_t *wl_next;     /* [8] ticket counters of the persistent pair kernel */
+    int32_t *wl_hit;      /* [8][wl_stride][AMC_HIT_REC] per work item: the pairs k_detect found (as slots), see AMC_HIT_REC */
     int32_t *dl;          /* [cells][AMC_WI] work items of the detection pass: every reference cell with >= 2 candidates */
     int32_t *dl_count;    /* [1] */
     int32_t *cell_n;      /* [8][wl_stride] members counted by the detection pass for cells it did not flag (0 otherwise) */

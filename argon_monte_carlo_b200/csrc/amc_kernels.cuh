@@ -540,6 +540,9 @@ struct CellShared {
     uint16_t mvlist[AMC_MAX_MEMBERS]; /* the moved members, compacted at the end of the visit */
     double ox[AMC_MV_CAP], oy[AMC_MV_CAP], oz[AMC_MV_CAP];
     int nmv, nold;
+    int hits[AMC_HIT_REC];       /* this work item's record of wl_hit */
+    int hm[2 * AMC_MAX_HITS];    /* member index of each listed slot, -1 = not (or no longer) a member */
+    int use_hits;                /* the listed pairs are all there is to test (set after the gather) */
     float inv_w;                 /* slabs per unit length */
     int nb;                      /* slabs of this cell, 1..AMC_XBINS */
     unsigned int nexec;          /* distance tests executed by this CTA since the last flush */
@@ -579,11 +582,21 @@ __device__ __forceinline__ void esc_link(const P &p, int g2, int32_t cc, int cx,
 {
     if (e >= 0) p.esc_cell[e * 8 + g2] = cc;
     if (cc < 0) return;
+#pragma unroll
+    for (int nb = 0; nb < 8; nb++) { /* what write_work_item will read if the cell turns out to be new on the list */
+        const int oc = ((cx + 1 - (nb >> 2)) * p.pnc[1] + (cy + 1 - ((nb >> 1) & 1))) * p.pnc[2] + (cz + 1 - (nb & 1));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(p.cell_start + oc));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(p.band_count + oc));
+    }
     int32_t *slot = &p.cell_active[(size_t)g2 * p.wl_stride + cc];
     int old;
     if (e >= 0) { old = atomicExch(slot, e + 2); p.esc_next[e * 8 + g2] = old; }
     else old = atomicCAS(slot, 0, 1);
-    if (old == 0) write_work_item(p, p.wl + ((size_t)g2 * p.wl_stride + atomicAdd(&p.wl_count[g2], 1)) * AMC_WI, cc, cx, cy, cz);
+    if (old == 0) { /* new on the worklist: the resolution has to search it */
+        const size_t w = (size_t)g2 * p.wl_stride + atomicAdd(&p.wl_count[g2], 1);
+        write_work_item(p, p.wl + w * AMC_WI, cc, cx, cy, cz);
+        p.wl_hit[w * AMC_HIT_REC] = -1;
+    } else atomicOr(&p.cell_n[(size_t)g2 * p.wl_stride + cc], AMC_CELL_DIRTY); /* already listed by k_detect: its pair list is stale */
 }
 
 // elastic exchange of one overlapping pair (Pore:176-241), executed by all 32 lanes of warp 0.
@@ -799,69 +812,95 @@ __device__ __forceinline__ void cell_process(const P &p, CellShared &S, int grou
     const int n = S.n, tid = threadIdx.x, nthreads = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5;
     if (tid == 0) S.nref += (unsigned long long)n * (n - 1) / 2;
-    // Only cells that the detection pass flagged (or that received a moved particle) get here, so what counts is
-    // the latency of one visit.  Members are chained per slab along x (one shared-memory exchange each, no scan,
-    // no reordering); after one barrier every member walks the older entries of its own slab and the whole next
-    // slab.  A pair goes through the fp32 filter of k_detect first (cell-relative coordinates, threshold det_thr)
-    // and only the few that pass are decided by the exact test (Pore:173-174).
-    {
-        const float inv_w = S.inv_w, thr = p.det_thr;
-        const int nb1 = S.nb - 1;
+    // A cell that is here only because k_detect found overlapping-looking pairs in it, and that no particle has
+    // entered or left since, needs no search: the listed pairs (slots -> member indices) are all there is to test.
+    bool listed = false;
+    if (S.use_hits) { /* block-uniform */
+        const int nh2 = 2 * S.hits[0];
         for (int k = tid; k < n; k += nthreads) {
-            float fx = (float)(S.x[k] - S.org[0]);
-            S.fx[k] = fx; S.fy[k] = (float)(S.y[k] - S.org[1]); S.fz[k] = (float)(S.z[k] - S.org[2]);
-            int b = min(nb1, max(0, (int)(fx * inv_w)));
-            S.nxt[k] = (uint16_t)atomicExch(&S.head[b], k + 1);
             S.mv[k] = 0;
+            const int sl = S.slot[k];
+            for (int h = 0; h < nh2; h++)
+                if (S.hits[1 + h] == sl) S.hm[h] = k;
         }
         if (tid == 0) { S.nmv = 0; S.nold = 0; }
-        PHASE_MARK(9); /* chain: own work */
         __syncthreads();
-        PHASE_MARK(2); /* chain: barrier */
-        unsigned int mine = 0;
-        for (int k0 = tid; k0 < n; k0 += WALK_K * nthreads) {
-            // WALK_K members per thread walk their chains side by side: every round is one hop for each of them
-            float ax[WALK_K], ay[WALK_K], az[WALK_K];
-            int e[WALK_K], more[WALK_K];
-#pragma unroll
-            for (int u = 0; u < WALK_K; u++) {
-                const int k = k0 + u * nthreads;
-                e[u] = 0; more[u] = 0; ax[u] = ay[u] = az[u] = 0.f;
-                if (k < n) {
-                    ax[u] = S.fx[k]; ay[u] = S.fy[k]; az[u] = S.fz[k];
-                    const int b = min(nb1, max(0, (int)(ax[u] * inv_w)));
-                    e[u] = S.nxt[k]; more[u] = S.head[b + 1];
-                }
+        listed = true;
+        for (int h = 0; h < nh2; h++) listed = listed && S.hm[h] >= 0; /* all found (always, unless the state is inconsistent) */
+        if (listed) {
+            if (2 * tid < nh2) {
+                const int ma = S.hm[2 * tid], mb = S.hm[2 * tid + 1];
+                if (overlap(p, S.x[ma], S.y[ma], S.z[ma], S.x[mb], S.y[mb], S.z[mb])) push_cand(S, p, ma, mb);
             }
-            while (true) {
-                int live = 0;
-#pragma unroll
-                for (int u = 0; u < WALK_K; u++) {
-                    if (e[u] == 0) { e[u] = more[u]; more[u] = 0; }
-                    live |= e[u];
-                }
-                if (live == 0) break;
-#pragma unroll
-                for (int u = 0; u < WALK_K; u++) {
-                    const int q = max(e[u] - 1, 0); /* entry 0 stands in for a finished chain; its result is masked */
-                    const float ex = S.fx[q] - ax[u], ey = S.fy[q] - ay[u], ez = S.fz[q] - az[u];
-                    const int nx = S.nxt[q];
-                    const float d2 = fmaf(ez, ez, fmaf(ey, ey, ex * ex));
-                    if (e[u] != 0 && d2 < thr) { /* rare */
-                        const int k = k0 + u * nthreads;
-                        if (overlap(p, S.x[k], S.y[k], S.z[k], S.x[q], S.y[q], S.z[q])) push_cand(S, p, k, q);
-                    }
-                    mine += e[u] != 0;
-                    e[u] = e[u] != 0 ? nx : 0;
-                }
-            }
+            if (tid == 0) atomicAdd(&S.nexec, (unsigned int)(nh2 >> 1));
+            __syncthreads();
         }
-        PHASE_MARK(10); /* walk: own work */
-        mine = __reduce_add_sync(0xffffffffu, mine);
-        if (lane == 0 && mine) atomicAdd(&S.nexec, mine);
     }
-    __syncthreads();
-    for (int c = tid; c < AMC_XBINS + 2; c += nthreads) S.head[c] = 0; /* every walk is done; the barriers of the caller order this before the next cell */
+    if (!listed) {
+    // Only cells that the detection pass flagged (or that received a moved particle) get here, so what counts is
+        // the latency of one visit.  Members are chained per slab along x (one shared-memory exchange each, no scan,
+        // no reordering); after one barrier every member walks the older entries of its own slab and the whole next
+        // slab.  A pair goes through the fp32 filter of k_detect first (cell-relative coordinates, threshold det_thr)
+        // and only the few that pass are decided by the exact test (Pore:173-174).
+        {
+            const float inv_w = S.inv_w, thr = p.det_thr;
+            const int nb1 = S.nb - 1;
+            for (int k = tid; k < n; k += nthreads) {
+                float fx = (float)(S.x[k] - S.org[0]);
+                S.fx[k] = fx; S.fy[k] = (float)(S.y[k] - S.org[1]); S.fz[k] = (float)(S.z[k] - S.org[2]);
+                int b = min(nb1, max(0, (int)(fx * inv_w)));
+                S.nxt[k] = (uint16_t)atomicExch(&S.head[b], k + 1);
+                S.mv[k] = 0;
+            }
+            if (tid == 0) { S.nmv = 0; S.nold = 0; }
+            PHASE_MARK(9); /* chain: own work */
+            __syncthreads();
+            PHASE_MARK(2); /* chain: barrier */
+            unsigned int mine = 0;
+            for (int k0 = tid; k0 < n; k0 += WALK_K * nthreads) {
+                // WALK_K members per thread walk their chains side by side: every round is one hop for each of them
+                float ax[WALK_K], ay[WALK_K], az[WALK_K];
+                int e[WALK_K], more[WALK_K];
+#pragma unroll
+                for (int u = 0; u < WALK_K; u++) {
+                    const int k = k0 + u * nthreads;
+                    e[u] = 0; more[u] = 0; ax[u] = ay[u] = az[u] = 0.f;
+                    if (k < n) {
+                        ax[u] = S.fx[k]; ay[u] = S.fy[k]; az[u] = S.fz[k];
+                        const int b = min(nb1, max(0, (int)(ax[u] * inv_w)));
+                        e[u] = S.nxt[k]; more[u] = S.head[b + 1];
+                    }
+                }
+                while (true) {
+                    int live = 0;
+#pragma unroll
+                    for (int u = 0; u < WALK_K; u++) {
+                        if (e[u] == 0) { e[u] = more[u]; more[u] = 0; }
+                        live |= e[u];
+                    }
+                    if (live == 0) break;
+#pragma unroll
+                    for (int u = 0; u < WALK_K; u++) {
+                        const int q = max(e[u] - 1, 0); /* entry 0 stands in for a finished chain; its result is masked */
+                        const float ex = S.fx[q] - ax[u], ey = S.fy[q] - ay[u], ez = S.fz[q] - az[u];
+                        const int nx = S.nxt[q];
+                        const float d2 = fmaf(ez, ez, fmaf(ey, ey, ex * ex));
+                        if (e[u] != 0 && d2 < thr) { /* rare */
+                            const int k = k0 + u * nthreads;
+                            if (overlap(p, S.x[k], S.y[k], S.z[k], S.x[q], S.y[q], S.z[q])) push_cand(S, p, k, q);
+                        }
+                        mine += e[u] != 0;
+                        e[u] = e[u] != 0 ? nx : 0;
+                    }
+                }
+            }
+            PHASE_MARK(10); /* walk: own work */
+            mine = __reduce_add_sync(0xffffffffu, mine);
+            if (lane == 0 && mine) atomicAdd(&S.nexec, mine);
+        }
+        __syncthreads();
+        for (int c = tid; c < AMC_XBINS + 2; c += nthreads) S.head[c] = 0; /* every walk is done; the barriers of the caller order this before the next cell */
+    }
     PHASE_MARK(5); /* search */
     if (S.ncand == 0) return;
     if (tid == 0) { S.cursor = 0; S.done = 0; if (S.ncand > AMC_MAX_CAND) S.ncand = AMC_MAX_CAND; }
@@ -986,6 +1025,8 @@ struct DetShared {
     float inv_wx[2], inv_wy[2];
     int nbx[2], nby[2];
     int nmem[2];
+    int nhit[2];
+    unsigned int hit[2][AMC_MAX_HITS]; /* candidate indices of the pairs that passed the filter: (self << 16) | other */
 };
 
 // warp 0: make the work item `v` (one int per lane) the header in buffer `buf`
@@ -1031,7 +1072,7 @@ __global__ void __launch_bounds__(DET_THREADS, DET_OCC) k_detect(const __grid_co
     int w = blockIdx.x;
     if (w >= nwork) return;
     for (int c = tid; c < DET_TAB; c += DET_THREADS) S.head[c] = 0;
-    if (tid < 2) S.nmem[tid] = 0;
+    if (tid < 2) { S.nmem[tid] = 0; S.nhit[tid] = 0; }
     // the header bookkeeping rides on the last warp: it has the fewest candidates to handle (the tail of the list)
     const bool hw = warp == DET_THREADS / 32 - 1;
     int hn = 0; /* header warp: the work item after the one published in the other buffer */
@@ -1114,7 +1155,6 @@ __global__ void __launch_bounds__(DET_THREADS, DET_OCC) k_detect(const __grid_co
             }
         }
         // ---- search: the older members of the own bin and everything in the four forward neighbour bins
-        float dmin = 3.0e38f;
 #pragma unroll
         for (int k = 0; k < DET_K; k++) {
             if (bin[k] < 0) continue;
@@ -1130,7 +1170,9 @@ __global__ void __launch_bounds__(DET_THREADS, DET_OCC) k_detect(const __grid_co
 #pragma unroll
             for (int n = 1; n < 5; n++)
                 if (c[n] < 0x10000u) { pend |= (unsigned long long)c[n] << sh; sh += 9; }
+            const unsigned long long all = pend;
             const float ax = fx[k], ay = fy[k], az = fz[k];
+            float dmin = 3.0e38f;
             for (unsigned int e = 0;;) {
                 if (e == 0) {
                     if (pend == 0) break;
@@ -1143,9 +1185,26 @@ __global__ void __launch_bounds__(DET_THREADS, DET_OCC) k_detect(const __grid_co
                 tests++;
                 e = S.next[e - 1];
             }
+            if (dmin < thr) { /* rare: walk the chains once more and remember the pairs for the ordered resolution */
+                hit = true;
+                pend = all;
+                for (unsigned int e = 0;;) {
+                    if (e == 0) {
+                        if (pend == 0) break;
+                        e = (unsigned int)pend & 511u;
+                        pend >>= 9;
+                    }
+                    float4 q = S.tile[e - 1];
+                    float ex = q.x - ax, ey = q.y - ay, ez = q.z - az;
+                    if (fmaf(ez, ez, fmaf(ey, ey, ex * ex)) < thr) {
+                        const int hh = atomicAdd(&S.nhit[cur], 1);
+                        if (hh < AMC_MAX_HITS) S.hit[cur][hh] = ((unsigned int)(tid + k * DET_THREADS) << 16) | (e - 1);
+                    }
+                    e = S.next[e - 1];
+                }
+            }
         }
-        hit = hit || dmin < thr;
-        if (tid == DET_THREADS - 1) S.nmem[nxt] = 0;
+        if (tid == DET_THREADS - 1) { S.nmem[nxt] = 0; S.nhit[nxt] = 0; }
         const int any = __syncthreads_or(hit);
         if (hw) {
             const int *h = S.hdr[cur];
@@ -1157,6 +1216,16 @@ __global__ void __launch_bounds__(DET_THREADS, DET_OCC) k_detect(const __grid_co
                 if (lane == 0) { p.cell_active[ci] = 1; idx = atomicAdd(&p.wl_count[g], 1); }
                 idx = __shfl_sync(0xffffffffu, idx, 0);
                 p.wl[((size_t)g * p.wl_stride + idx) * AMC_WI + lane] = h[lane];
+                // the pairs that passed the filter, as slots: the resolution tests just these (exactly) instead of
+                // searching the cell again; -1 = search (cell flagged for another reason, or too many pairs)
+                const int nh = S.nhit[cur];
+                const bool listed = total <= DET_CAND && nh >= 1 && nh <= AMC_MAX_HITS;
+                int32_t *wh = p.wl_hit + ((size_t)g * p.wl_stride + idx) * AMC_HIT_REC;
+                if (lane == 0) wh[0] = listed ? nh : -1;
+                if (listed && lane < 2 * nh) {
+                    const unsigned int hv = S.hit[cur][lane >> 1];
+                    wh[1 + lane] = det_slot(S, cur, (lane & 1) ? (int)(hv & 0xffffu) : (int)(hv >> 16));
+                }
             } else if (lane == 0) {
                 const int nm = S.nmem[cur];
                 p.cell_n[ci] = nm;
@@ -1288,6 +1357,9 @@ __global__ void __launch_bounds__(PAIR_THREADS, 6) k_pairs_group(const __grid_co
         __syncthreads();
         PHASE_MARK(0); /* header */
         const int cell = s_hdr[0];
+        if (tid >= PAIR_THREADS - 32 && (tid & 31) < AMC_HIT_REC) /* last warp: this item's pair list from k_detect */
+            S.hits[tid & 31] = p.wl_hit[((size_t)group * p.wl_stride + s_w) * AMC_HIT_REC + (tid & 31)];
+        if (tid < 2 * AMC_MAX_HITS) S.hm[tid] = -1;
         gather_members(p, S, group, cell);
         __syncthreads();
         PHASE_MARK(1); /* gather */
@@ -1297,9 +1369,12 @@ __global__ void __launch_bounds__(PAIR_THREADS, 6) k_pairs_group(const __grid_co
             __syncthreads();
         }
         if (tid == 0) { /* the detection pass already counted this cell if it saw it without an overlapping pair */
-            int nA = p.cell_n[(size_t)group * p.wl_stride + cell];
+            const int raw = p.cell_n[(size_t)group * p.wl_stride + cell];
+            const int nA = raw & ~AMC_CELL_DIRTY;
             S.nref -= (unsigned long long)nA * (nA - 1) / 2;
+            S.use_hits = S.hits[0] >= 0 && !(raw & AMC_CELL_DIRTY);
         }
+        __syncthreads();
         if (S.n >= 2) cell_process(p, S, group, cell);
         PHASE_MARK(7); /* resolution loop (cells with candidates) */
         __syncthreads();
@@ -1352,7 +1427,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_cube_sweep(const __grid_const
             __syncthreads();
             for (int zl = 0; zl < p.nc[2]; zl++) {
                 if (tid == 0) {
-                    S.n = 0; S.ncand = 0; S.org[0] = p.lo[0][xl]; S.org[1] = p.lo[1][yl]; S.org[2] = p.lo[2][zl];
+                    S.n = 0; S.ncand = 0; S.use_hits = 0; S.org[0] = p.lo[0][xl]; S.org[1] = p.lo[1][yl]; S.org[2] = p.lo[2][zl];
                     float wd = (float)(p.edge[0][xl + 1] - p.lo[0][xl]);
                     int nb = (int)fminf((float)AMC_XBINS, floorf(wd / p.det_w));
                     if (nb < 1) nb = 1;

@@ -3,7 +3,7 @@ Launch count, median and total duration per kernel name, plus the kernels of the
 import csv, sys, statistics, collections
 lines = [l for l in open(sys.argv[1]) if not l.startswith("==")]
 rows = list(csv.DictReader(lines))
-names = [(r["Kernel Name"].split("(")[0], float(r["Metric Value"]) / 1000) for r in rows]
+names = [(r["Kernel Name"].split("(")[0].replace("void ", "").split("<")[0], float(r["Metric Value"]) / 1000) for r in rows]
 per = collections.OrderedDict()
 for n, v in names: per.setdefault(n, []).append(v)
 out = [("kernel", "launches", "median_us", "total_us")]
