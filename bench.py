@@ -37,7 +37,7 @@ sys.path.insert(0, ROOT)
 
 B_STEP = 162.0      # algorithmic bytes per particle-step, fp64 state read + written once
 B_PAIR = 32.0       # algorithmic bytes per particle for the pair kernel: 3 x f64 position + cell header
-NCU_DETECT_TRAFFIC = 314.3e6   # dram__bytes_read.sum + dram__bytes_write.sum of one k_detect launch at 12,499,989 particles
+NCU_DETECT_TRAFFIC = 317.8e6   # dram__bytes_read.sum + dram__bytes_write.sum of one k_detect launch at 12,499,989 particles
 
 
 def measured_peaks():
@@ -229,7 +229,7 @@ def run_ours(args):
     # ordered resolution that follows only visits the ~0.05 % of cells it flags).  Per launch: algorithmic bytes =
     # 32 B x particles (3 x f64 position + cell header), duration = CUDA events around the launch on the
     # handle's stream; traffic = dram read + write of one launch from the ncu --set full capture of this workload
-    # (profiles/r1_v7_ncu_full_summary.csv)
+    # (profiles/r1_v8_ncu_full_summary.csv)
     roofline = {"bound": "hbm", "kernel": "k_detect (pair detection, 1 launch per step)",
                 "achieved": B_PAIR * n / (det_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": B_PAIR * n,
