@@ -50,32 +50,40 @@ def owner_layer(z, edges):
     return np.clip(k, 0, len(edges) - 2)
 
 
-def _greedy_cuts(cum, nranks, limit, min_layers, odd_only):
-    """Cuts such that no slab holds more than `limit` particles, each slab as thick as it can be; None if that takes
-    more than nranks slabs.  odd_only: interior cuts on odd layers."""
+def _feasible_cuts(cum, nranks, limit, min_layers, odd_only):
+    """Cuts with at least min_layers layers and at most `limit` particles per slab, or None.  Dynamic programme over
+    (slab, end layer): slab r can end at layer k if slab r-1 can end at some j in [first j with cum[k]-cum[j] <= limit,
+    k - min_layers]; `last[k]` = largest reachable end <= k keeps the range test O(1).  odd_only: interior cuts on odd
+    layers."""
     ncz = len(cum) - 1
-    cuts = [0]
+    ks = np.arange(ncz + 1)
+    jmin = np.searchsorted(cum, cum - limit, side="left")           # smallest j with cum[j] >= cum[k] - limit
+    reach = np.zeros(ncz + 1, dtype=bool)
+    reach[0] = True
+    prev = []
     for r in range(1, nranks + 1):
-        lo = cuts[-1] + min_layers
-        hi = ncz - (nranks - r) * min_layers
-        if r == nranks:
-            if cum[ncz] - cum[cuts[-1]] > limit:
-                return None
-            cuts.append(ncz)
-            break
-        k = int(np.searchsorted(cum, cum[cuts[-1]] + limit, side="right")) - 1   # thickest slab within the limit
-        k = min(k, hi)
-        if odd_only and k % 2 == 0:
-            k -= 1
-        if k < lo:
-            return None
-        cuts.append(k)
-    return cuts
+        last = np.where(reach, ks, -1)
+        last = np.maximum.accumulate(last)                          # largest reachable end <= k
+        hi = ks - min_layers
+        cand = np.where(hi >= 0, last[np.maximum(hi, 0)], -1)       # best predecessor end for a slab ending at k
+        ok = cand >= jmin
+        if r < nranks:
+            if odd_only:
+                ok &= (ks % 2 == 1)
+            ok[ncz] = False
+        prev.append(np.where(ok, cand, -1))
+        reach = ok
+    if not reach[ncz]:
+        return None
+    cuts = [ncz]
+    for r in range(nranks - 1, -1, -1):
+        cuts.append(int(prev[r][cuts[-1]]))
+    return cuts[::-1]
 
 
 def balanced_cuts(z, edges, nranks, min_layers=2, prefer_odd=True, odd_tolerance=0.03):
     """Cut indices (nranks+1) on z-cell boundaries that minimise the particle count of the fullest slab (bisection on
-    that count with a greedy feasibility test).  Odd cuts are preferred -- the cells just above an odd cut belong to
+    that count with a dynamic-programming feasibility test).  Odd cuts are preferred -- the cells just above an odd cut belong to
     the odd z colour groups, so a ghost that has to be exported late (an immigrant that lands in the band below the
     cut) is only needed from group 1 on and travels with the hand-over after group 0, no extra round before it --
     unless they make the fullest slab more than odd_tolerance fuller than the unconstrained optimum."""
@@ -87,15 +95,15 @@ def balanced_cuts(z, edges, nranks, min_layers=2, prefer_odd=True, odd_tolerance
 
     def best(odd_only):
         lo, hi = cum[-1] / nranks, cum[-1]
-        if _greedy_cuts(cum, nranks, hi, min_layers, odd_only) is None:
+        if _feasible_cuts(cum, nranks, hi, min_layers, odd_only) is None:
             return None, np.inf
         for _ in range(60):
             mid = 0.5 * (lo + hi)
-            if _greedy_cuts(cum, nranks, mid, min_layers, odd_only) is None:
+            if _feasible_cuts(cum, nranks, mid, min_layers, odd_only) is None:
                 lo = mid
             else:
                 hi = mid
-        cuts = _greedy_cuts(cum, nranks, hi, min_layers, odd_only)
+        cuts = _feasible_cuts(cum, nranks, hi, min_layers, odd_only)
         return cuts, max(cum[b] - cum[a] for a, b in zip(cuts, cuts[1:]))
 
     free, load_free = best(False)

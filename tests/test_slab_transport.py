@@ -105,3 +105,58 @@ def test_dist_transport_gloo(world):
     [p.join(120) for p in procs]
     assert all(p.exitcode == 0 for p in procs)
     assert all(out.get(k) for k in range(world)), dict(out)
+
+
+def test_balanced_cuts_minimise_the_fullest_slab():
+    """Against brute force on small random layer histograms: no choice of cuts has a lighter fullest slab; odd cuts
+    are used when they cost less than the tolerance."""
+    import itertools
+    from argon_monte_carlo_b200 import slab
+    rng = np.random.default_rng(3)
+    for trial in range(30):
+        ncz = int(rng.integers(8, 15))
+        nranks = int(rng.integers(2, 4))
+        hist = rng.integers(1, 50, ncz) * np.where(rng.random(ncz) < 0.2, 20, 1)     # a few dense layers, as in the end caps
+        edges = np.arange(ncz + 1, dtype=np.float64)
+        z = np.repeat(np.arange(ncz) + 0.5, hist)
+        cum = np.concatenate([[0], np.cumsum(hist)])
+        load = lambda c: max(cum[b] - cum[a] for a, b in zip(c, c[1:]))
+        best = min(load((0,) + mid + (ncz,)) for mid in itertools.combinations(range(1, ncz), nranks - 1)
+                   if all(b - a >= 2 for a, b in zip((0,) + mid, mid + (ncz,))))
+        free = slab.balanced_cuts(z, edges, nranks, prefer_odd=False)
+        assert load(tuple(free)) == best, (hist, free)
+        odd = slab.balanced_cuts(z, edges, nranks, prefer_odd=True)
+        assert (np.diff(odd) >= 2).all() and load(tuple(odd)) <= best * 1.03 + 1e-9
+        if any(int(c) % 2 == 0 for c in odd[1:-1]):      # an even cut only where every all-odd choice is too heavy
+            odd_only = [load((0,) + mid + (ncz,)) for mid in itertools.combinations(range(1, ncz, 2), nranks - 1)
+                        if all(b - a >= 2 for a, b in zip((0,) + mid, mid + (ncz,)))]
+            assert not odd_only or min(odd_only) > best * 1.03
+
+
+def test_device_initialiser_restatement_and_spec():
+    """tests/synthetic_ref.py (the NumPy restatement the GPU test compares k_init_synthetic with) uses the same
+    Philox4x32-10 as the oracle's C implementation, and init_state.pore_spec describes the regions of Pore:79-83."""
+    import ctypes as C
+    from oracle import oracle as O
+    from argon_monte_carlo_b200 import config, init_state
+    from synthetic_ref import philox4x32_10, generate
+    L = O.lib()
+    rng = np.random.default_rng(1)
+    ctr = rng.integers(0, 2 ** 32, (50, 4), dtype=np.uint64)
+    key = rng.integers(0, 2 ** 32, (50, 2), dtype=np.uint64)
+    for c, k in zip(ctr, key):
+        out = (C.c_uint32 * 4)()
+        L.orc_philox4x32_10((C.c_uint32 * 4)(*[int(v) for v in c]), (C.c_uint32 * 2)(*[int(v) for v in k]), out)
+        got = philox4x32_10([np.array([v]) for v in c], int(k[0]), int(k[1]))
+        assert [int(g[0]) for g in got] == [int(v) for v in out]
+    cfg = config.pore_config(True)
+    spec = init_state.pore_spec(cfg, seed=9, keep_z=(1e-7, 2e-7))
+    cum = np.array(spec.cum_weight[:5])
+    assert spec.n_regions == 5 and spec.n_total == cfg.num_molecules and cum[-1] == 1.0 and (np.diff(cum) > 0).all()
+    assert (spec.keep_z_lo, spec.keep_z_hi) == (1e-7, 2e-7)
+    x, y, z, vx, vy, vz, reg = generate(spec, np.arange(200000))
+    frac = np.bincount(reg, minlength=5) / 200000.0
+    vols = np.array([cfg.open_air_volume, cfg.hot_volume, cfg.gap_volume, cfg.cold_volume, cfg.open_air_volume])
+    assert np.max(np.abs(frac - vols / vols.sum())) < 5e-3
+    assert z.min() >= cfg.argon_radius and z.max() <= cfg.total_height - cfg.argon_radius
+    assert abs(np.std(np.concatenate([vx, vy, vz])) / cfg.a_shape - 1) < 5e-3
