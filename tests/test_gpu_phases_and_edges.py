@@ -132,6 +132,41 @@ def test_cube_geometry_with_colour_groups(oracle):
     sim.close()
 
 
+def _cube_groups_run(oracle, scale, n_sub, n, seed, steps):
+    from argon_monte_carlo_b200 import amc, config, init_state
+    cfg = config.cube_config(scale=scale, n_sub=n_sub)
+    cfg.grid = config.Grid(nc=(n_sub,) * 3, c0=(0, 0, 0), d=(cfg.dx, cfg.dy, cfg.dz), band=(cfg.collision_range,) * 3)
+    init = init_state.synthetic_cube_state(cfg, n, seed=seed)
+    st = oracle.ParticleState(*init)
+    sim = amc.Simulation(cfg, kind=amc.KIND_CUBE, pp_mode=amc.PP_GROUPS, max_particles=n)
+    sim.set_state(*init)
+    total = 0
+    for _ in range(steps):
+        oracle.drift(st, cfg.dt, False)
+        oracle.cube_walls(st, cfg.cube_x, cfg.cube_y, cfg.cube_z)
+        ncol, checks, _ = oracle.pp_groups(st, cfg.grid, cfg.collision_range, cfg.argon_mass)
+        s = sim.step(1)[0]
+        assert s["pp_collisions"] == ncol and s["pair_checks_ref"] == checks
+        same(sim.get_state(), st)
+        total += ncol
+    sim.close()
+    return total
+
+
+def test_cells_with_more_candidates_than_the_detection_pass_holds(oracle):
+    """25 nm cells with ~400 members: more candidates than a CTA of k_detect takes (384), so every cell is flagged
+    unseen and the ordered kernel searches all of them itself -- the conservative fallback, end to end."""
+    assert _cube_groups_run(oracle, 2.0, 8, 204800, 11, 3) > 100
+
+
+def test_tiny_cells_dense_gas_many_chained_collisions(oracle):
+    """1 nm cells (3 collision ranges: 2-3 search bins per axis) and 25 x the gas density: overlapping pairs
+    everywhere, several collisions per cell visit, moved particles that change cell all the time.  The ordered
+    resolution, the escaped lists and the activation of the cells a particle enters or leaves have to reproduce the
+    reference sweep exactly."""
+    assert _cube_groups_run(oracle, 0.2, 20, 5000, 12, 6) > 300
+
+
 def test_checkpoint_resume_is_exact(temp_cfg, temp_init, tmp_path):
     """A run continued from a checkpoint in a fresh handle equals the uninterrupted run: state,
     histograms, free-path sums and the device-RNG stream (keyed by the step index)."""
