@@ -1,10 +1,16 @@
 // amc_kernels.cuh -- the kernels of libamc.so.
-//   k_advect        K1+K4: drift, wall cases, recapture, owner-cell key + in-cell rank   (HBM streaming)
-//   k_scan_*        exclusive scan of the owner-cell histogram                          (tiny)
-//   k_scatter       counting-sort scatter of the SoA state into owner-cell order        (HBM streaming)
-//   k_pairs_group   K2+K3: one CTA per reference cell of a colour group                 (fp64 / latency)
-//   k_cube_sweep    the serial lexicographic cell sweep of the cube stage               (latency)
-//   k_case_*        per-case wall kernels for the host-RNG parity mode
+//   k_keys            dry run of the timestep -> owner cell + in-cell rank of every particle     (issue / latency)
+//   k_scan_*          exclusive scan of the owner-cell histogram                                 (tiny)
+//   k_scatter_advect  the timestep itself on the way to the sorted slot                         (HBM streaming)
+//   k_build_worklist  reference cells with >= 2 candidates -> detection list                    (tiny)
+//   k_detect          neighbour search over every reference cell, all colour groups at once     (issue; 25 B/particle)
+//   k_pairs_group     ordered resolution of the flagged / activated cells of one colour group   (latency)
+//   k_recapture_list  closing recapture over the slots a collision touched                      (tiny)
+//   k_advect, k_scatter, k_recapture_post   the same step as separate in-place passes: phase-level parity entry points
+//   k_cube_sweep      the serial lexicographic cell sweep of the cube stage                     (latency)
+//   k_case_*          per-case wall kernels for the host-RNG parity mode
+//   k_init_synthetic  synthetic Maxwellian initial state
+//   k_xfer_*, k_bnd_* slab decomposition: migration / ghost copies, per-group hand-over
 #pragma once
 #include "amc_device.cuh"
 
@@ -501,7 +507,7 @@ __global__ void __launch_bounds__(ADVECT_THREADS) k_recapture_list(const __grid_
 }
 
 // ------------------------------------------------------------------------------------------------
-// K2 + K3: one reference cell.
+// K2 + K3: one reference cell (ordered resolution; the cells get here through k_detect / esc_link).
 //
 // The reference visits the members of a cell in ascending global index and tests (i, j<i) against
 // the live cell-local arrays, so a collision is visible to every later pair of the same cell
