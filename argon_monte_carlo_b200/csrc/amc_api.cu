@@ -16,6 +16,8 @@ struct amc_handle {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = true;
+    cudaStream_t aux = nullptr;          // second stream of amc_step: pair-pass bookkeeping beside the scatter
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool slab = false;
     int32_t xf_total = 0;
     int32_t *d_counters = nullptr; // slab mode: xf_count[nranks], n_in, bnd_n[2], rel_count, n_foreign, compact count
@@ -152,6 +154,9 @@ extern "C" int amc_destroy(amc_handle *h)
     for (cudaEvent_t e : h->events) cudaEventDestroy(e);
     for (cudaEvent_t e : h->det_events) cudaEventDestroy(e);
     if (h->h_stats) cudaFreeHost(h->h_stats);
+    if (h->aux) { cudaStreamSynchronize(h->aux); cudaStreamDestroy(h->aux); }
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
     return AMC_OK;
@@ -177,6 +182,9 @@ static int create_impl(amc_handle *h, const amc_config *cfg, int device)
     if (e != cudaSuccess || ndev == 0) return h->fail(AMC_E_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e));
     CK(cudaSetDevice(device));
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     P &p = h->p;
     memset(&p, 0, sizeof(p));
     h->cap = cfg->max_particles;
@@ -434,19 +442,33 @@ static int sort_scatter(amc_handle *h, int64_t *launches)
     return AMC_OK;
 }
 
-static int run_pairs(amc_handle *h, int64_t *launches)
+// bookkeeping of one pair pass that depends on the sorted layout only through cell_start / band_count (not on the
+// particle arrays): reset of the escaped list and of the worklists, list of the cells k_detect has to look at
+static int prepare_pairs(amc_handle *h, cudaStream_t st)
+{
+    P &p = h->p;
+    k_pp_begin<<<1, 256, 0, st>>>(p);
+    CK(cudaMemsetAsync(p.wl_count, 0, AMC_WL_COUNTERS * sizeof(int32_t), st));
+    int ncell = p.nc[0] * p.nc[1] * p.nc[2];
+    CK(cudaMemsetAsync(p.cell_active, 0, (size_t)p.wl_stride * 8 * sizeof(int32_t), st));
+    CK(cudaMemsetAsync(p.cell_n, 0, (size_t)p.wl_stride * 8 * sizeof(int32_t), st));
+    k_build_worklist<<<grid_for(ncell, ADVECT_THREADS), ADVECT_THREADS, 0, st>>>(p);
+    CK(cudaGetLastError());
+    return AMC_OK;
+}
+
+static int run_pairs(amc_handle *h, int64_t *launches, bool prepared = false)
 {
     P &p = h->p;
     if (p.pp_mode == AMC_PP_SWEEP) {
         k_cube_sweep<<<1, SWEEP_THREADS, 0, h->stream>>>(p);
         if (launches) *launches += 1;
     } else {
-        k_pp_begin<<<1, 256, 0, h->stream>>>(p);
-        CK(cudaMemsetAsync(p.wl_count, 0, AMC_WL_COUNTERS * sizeof(int32_t), h->stream));
+        if (!prepared) {
+            int rc = prepare_pairs(h, h->stream);
+            if (rc != AMC_OK) return rc;
+        }
         int ncell = p.nc[0] * p.nc[1] * p.nc[2];
-        CK(cudaMemsetAsync(p.cell_active, 0, (size_t)p.wl_stride * 8 * sizeof(int32_t), h->stream));
-        CK(cudaMemsetAsync(p.cell_n, 0, (size_t)p.wl_stride * 8 * sizeof(int32_t), h->stream));
-        k_build_worklist<<<grid_for(ncell, ADVECT_THREADS), ADVECT_THREADS, 0, h->stream>>>(p);
         if (h->det_slot >= 0) CK(cudaEventRecord(h->det_events[2 * h->det_slot], h->stream));
         k_detect<<<h->det_grid, DET_THREADS, 0, h->stream>>>(p);
         if (h->det_slot >= 0) CK(cudaEventRecord(h->det_events[2 * h->det_slot + 1], h->stream));
@@ -518,14 +540,20 @@ extern "C" int amc_step(amc_handle *h, int32_t n_steps, amc_step_stats *stats)
                     k_scan_tiles<<<ntiles, SCAN_THREADS, 0, h->stream>>>(p.band_count, p.rest_count, p.cell_start, h->d_tile_sums, m);
                     k_scan_sums<<<1, SCAN_THREADS, 0, h->stream>>>(h->d_tile_sums, ntiles);
                     k_scan_add<<<ntiles, SCAN_THREADS, 0, h->stream>>>(p.cell_start, h->d_tile_sums, m, (int32_t)h->n);
+                    // the bookkeeping of the pair pass needs the scan, not the scattered particles: it runs beside the scatter
+                    CK(cudaEventRecord(h->ev_fork, h->stream));
+                    CK(cudaStreamWaitEvent(h->aux, h->ev_fork, 0));
+                    if ((rc = prepare_pairs(h, h->aux)) != AMC_OK) return rc;
+                    CK(cudaEventRecord(h->ev_join, h->aux));
                     k_scatter_advect<false><<<grid_for(h->n, ADVECT_THREADS), ADVECT_THREADS, 0, h->stream>>>(p, phase);
                     CK(cudaGetLastError());
+                    CK(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
                     std::swap(p.a, p.b);
                     h->last_launches += 5;
                 }
                 CK(cudaEventRecord(h->events[4 * s + 2], h->stream));
                 h->det_slot = sweep ? -1 : s;
-                rc = run_pairs(h, &h->last_launches);
+                rc = run_pairs(h, &h->last_launches, !sweep);
                 h->det_slot = -1;
                 if (rc != AMC_OK) return rc;
                 CK(cudaEventRecord(h->events[4 * s + 3], h->stream));
