@@ -28,8 +28,7 @@
 #define AMC_HIT_REC (1 + 2 * AMC_MAX_HITS) /* ints per work item in wl_hit: count (-1: search the cell), then slot pairs */
 #define AMC_CELL_DIRTY 0x40000000 /* bit of cell_n: a particle entered / left the cell after k_detect looked at it */
 #define AMC_WL_COUNTERS 24 /* wl_count[8], wl_next[8], dl_count, padding */
-#define AMC_XBINS 64         /* slabs along x of the in-CTA neighbour search (multiple of 32) */
-#define AMC_SUB_MIN_N 48     /* below this many members the plain all-pairs scan is cheaper */
+#define AMC_XBINS 64         /* slabs along x of the neighbour search inside a flagged cell, at most */
 
 /* how much of a timestep's per-particle work a kernel carries out (advance_particle and the wall helpers):
    DRY: only what decides the final position; LIVE: everything; QUIET: the full state update, but no counters,
