@@ -1,6 +1,7 @@
 """Host-side logic and the C-ABI library, without a GPU: constants, exported symbols, loud failure
 when no device is present, the product never touching the oracle, output formats."""
 import ctypes
+import math
 import os
 import re
 
@@ -154,3 +155,98 @@ def test_shipped_histograms_are_consistent_with_the_density_rule():
         counts = np.rint(dens * 5e-9 * 30828).astype(np.int64)
         assert counts.sum() == 30828
         assert np.allclose(outputs.density(counts), dens, rtol=2e-8)
+
+
+def test_calm_regions_never_hide_a_wall_event(oracle, temp_cfg):
+    """advance_particle (amc_kernels.cuh) skips the wall masks, the recapture and the out-of-bounds census for
+    particles whose positions before and after the drift lie in one of three 'calm' regions whose bounds are the
+    min / max of the geometry's thresholds (amc_api.cu).  Property checked here against the oracle, on particles
+    thrown at every wall from both sides with displacements of up to several nanometres per step: for every particle
+    the predicate calls calm, the reference's step is the drift and nothing else."""
+    import math
+    g, dt = temp_cfg.geom, temp_cfg.dt
+
+    def sq_threshold_gt(R):           # amc_api.cu: largest double t with sqrt(t) <= R
+        t = R * R
+        while math.sqrt(t) <= R:
+            t = np.nextafter(t, np.inf)
+        while math.sqrt(t) > R:
+            t = np.nextafter(t, 0.0)
+        return float(t)
+    zs = [g.oah, g.zh3, g.z_gb, g.zgb_p, g.z_gt, g.zgt_m, g.z_cold, g.zc3]
+    zA, zB = min(zs + [g.H]), max(zs + [0.0])
+    rA = min(sq_threshold_gt(g.R_oa), g.R_oa_sq)
+    rC = min(rA, g.R_p_sq, g.R_g_c_sq, g.R_p_c_sq, g.R_g_sq)
+    assert 0 < zA < zB < g.H and 0 < rC < rA
+
+    rng = np.random.default_rng(42)
+    n = 600000
+    # z: uniform over the domain and a bit beyond, plus clusters within 2 nm of every threshold
+    z = rng.uniform(-3e-9, g.H + 3e-9, n)
+    k = rng.integers(0, len(zs) + 2, n)
+    near = np.array(zs + [0.0, g.H])[k] + rng.uniform(-2e-9, 2e-9, n)
+    z = np.where(rng.random(n) < 0.5, near, z)
+    radii = np.array([g.R_oa, math.sqrt(g.R_p_sq), math.sqrt(g.R_g_sq), math.sqrt(g.R_p_c_sq), math.sqrt(g.R_g_c_sq)])
+    r = np.where(rng.random(n) < 0.5, radii[rng.integers(0, 5, n)] + rng.uniform(-2e-9, 2e-9, n),
+                 g.R_oa * 1.02 * np.sqrt(rng.random(n)))
+    r = np.abs(r)
+    th = rng.uniform(0, 2 * np.pi, n)
+    x, y = r * np.cos(th), r * np.sin(th)
+    disp = rng.normal(0.0, 1.5e-9, (3, n))                     # ~20 x the thermal displacement of one step
+    vx, vy, vz = disp / dt
+    nx, ny, nz = x + dt * vx, y + dt * vy, z + dt * vz         # the device's drift, operation for operation
+    rmax = np.maximum(x * x + y * y, nx * nx + ny * ny)
+    zmin, zmax = np.minimum(z, nz), np.maximum(z, nz)
+    calm = ((rmax <= rA) & (((zmin >= 0.0) & (zmax < zA)) | ((zmin > zB) & (zmax <= g.H)))) | \
+           ((rmax < rC) & (zmin >= 0.0) & (zmax <= g.H))
+    assert 0.1 < calm.mean() < 0.9                              # the sample exercises both sides of the predicate
+    c = np.nonzero(calm)[0]
+    st = oracle.ParticleState(x[c], y[c], z[c], vx[c], vy[c], vz[c])
+    # closing recapture of the previous step on the pre-drift position: nothing to do
+    assert oracle.temp_oob_count(st, g) == 0 and oracle.temp_recapture(st, g) == 0
+    oracle.drift(st, dt, True)
+    from argon_monte_carlo_b200 import config
+    cheb = config.gap_energy_chebyshev(temp_cfg, 16)
+    counts, sums, errs, bits = oracle.temp_walls_philox(st, g, 1, 0, cheb, None, True)
+    assert counts.sum() == 0 and errs == 0 and not bits.any()
+    assert oracle.temp_oob_count(st, g) == 0 and oracle.temp_recapture(st, g) == 0
+    assert np.array_equal(st.x, nx[c]) and np.array_equal(st.y, ny[c]) and np.array_equal(st.z, nz[c])
+    assert np.array_equal(st.vx, vx[c]) and np.array_equal(st.vz, vz[c])
+    # and the predicate is not vacuous about the rest: the others do hit walls or leave the domain
+    o = np.nonzero(~calm)[0]
+    st2 = oracle.ParticleState(x[o], y[o], z[o], vx[o], vy[o], vz[o])
+    oracle.drift(st2, dt, True)
+    counts2, _, _, _ = oracle.temp_walls_philox(st2, g, 1, 0, cheb, None, True)
+    assert counts2.sum() > 1000
+
+
+def test_detection_filter_threshold_is_conservative(pore_cfg):
+    """k_detect decides in fp32 on cell-relative coordinates whether a pair may overlap; det_thr (amc_api.cu) widens
+    the threshold by the rounding bound so that no pair the exact fp64 test accepts is ever filtered out.  Emulated
+    here in NumPy float32 (both summation orders; the kernel's fused multiply-adds round less, not more) on pairs
+    placed within +-1e-4 relative of the collision range, anywhere in a cell, along random directions."""
+    from argon_monte_carlo_b200 import amc
+    g = pore_cfg.grid
+    cr = pore_cfg.collision_range
+    overlap_sq = amc.overlap_threshold(cr)
+    wmax = max(float(np.max(g.edge[a][1:] - g.lo[a])) for a in range(3))
+    e_abs = 6.0 * math.ldexp(wmax, -24)
+    r_f = math.sqrt(overlap_sq) * (1.0 + 1e-9) + 2.0 * e_abs
+    thr = np.nextafter(np.float32(r_f * r_f * (1.0 + math.ldexp(1.0, -20))), np.float32(np.inf))
+    rng = np.random.default_rng(7)
+    n = 2000000
+    lo = np.array([g.lo[a][3] for a in range(3)])
+    a = lo[:, None] + rng.uniform(0, wmax, (3, n))
+    d = rng.normal(size=(3, n)); d /= np.linalg.norm(d, axis=0)
+    b = a + d * cr * (1.0 + rng.uniform(-1e-4, 1e-4, n))
+    dd = b - a
+    exact = (dd[0] * dd[0] + dd[1] * dd[1]) + dd[2] * dd[2] < overlap_sq          # Pore:173-174 as the kernels evaluate it
+    fa, fb = (a - lo[:, None]).astype(np.float32), (b - lo[:, None]).astype(np.float32)
+    e = fb - fa
+    d2a = (e[0] * e[0] + e[1] * e[1]) + e[2] * e[2]
+    d2b = e[2] * e[2] + (e[1] * e[1] + e[0] * e[0])
+    assert exact.sum() > 500000
+    assert np.all(d2a[exact] < thr) and np.all(d2b[exact] < thr)
+    # the filter is not sloppy either: it widens the radius by ~5e-5 relative (a quarter of this +-1e-4 sample,
+    # 1.4e-4 of the true pairs of a uniform gas)
+    assert np.mean((d2a < thr) & ~exact) < 0.3 and math.sqrt(float(thr)) / cr - 1 < 1e-4
