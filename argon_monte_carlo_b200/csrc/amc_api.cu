@@ -134,7 +134,7 @@ static void stats_to_host(const amc_handle *h, const StatsDev &s, amc_step_stats
 static int check_overflow(amc_handle *h, const StatsDev &s)
 {
     if (s.cell_overflow) return h->fail(AMC_E_CAPACITY, "a collision cell holds more than AMC_MAX_MEMBERS particles");
-    if (s.cand_overflow) return h->fail(AMC_E_CAPACITY, "more than AMC_MAX_CAND simultaneously overlapping pairs in one cell");
+    if (s.cand_overflow) return h->fail(AMC_E_CAPACITY, "more than AMC_MAX_CAND simultaneously overlapping pairs, or more than AMC_MV_CAP particles moved, in one cell visit");
     if (s.esc_overflow) return h->fail(AMC_E_CAPACITY, "escaped-particle list overflow");
     return AMC_OK;
 }
