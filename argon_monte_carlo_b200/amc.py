@@ -89,7 +89,7 @@ EXPORTS = ("amc_create", "amc_destroy", "amc_last_error", "amc_abi_version", "am
            "amc_last_detect_ms", "amc_init_synthetic",
            "amc_get_outputs_raw", "amc_set_outputs_raw", "amc_get_step_index",
            "amc_slab_enable", "amc_set_stream", "amc_set_ids", "amc_slab_advect", "amc_slab_sort", "amc_slab_pairs_begin",
-           "amc_slab_group", "amc_slab_apply", "amc_slab_finish", "amc_slab_get_owned")
+           "amc_slab_group", "amc_slab_apply", "amc_slab_finish", "amc_slab_get_owned", "amc_state_digest")
 
 
 def load_library():
@@ -97,8 +97,12 @@ def load_library():
     global _lib
     if _lib is None:
         path = _build.library_path()
-        if not os.path.isfile(path):
-            _build.build_library()
+        if not os.environ.get("AMC_LIBRARY"):
+            try:
+                _build.build_library()       # returns at once unless a source is newer than the library
+            except Exception:
+                if not os.path.isfile(path):
+                    raise                    # no nvcc and no library: nothing to run (there is no CPU fallback)
         L = C.CDLL(path)
         L.amc_last_error.restype = C.c_char_p
         L.amc_last_error.argtypes = [C.c_void_p]
@@ -127,6 +131,40 @@ def overlap_threshold(collision_range: float) -> float:
 
 def _dp(a):
     return a.ctypes.data_as(c_double_p) if a is not None else None
+
+
+_M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def _mix64(z):
+    z = z + np.uint64(0x9E3779B97F4A7C15)
+    z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    return z ^ (z >> np.uint64(31))
+
+
+def digest_of_arrays(ids, state):
+    """NumPy restatement of amc_state_digest (include/amc.h): (sum0, sum1, count) over the given particles.
+    ids: global particle indices; state: mapping with the ten float64 arrays and 'flag'."""
+    keys = ("x", "y", "z", "vx", "vy", "vz", "dist", "dist_x", "dist_y", "dist_z")
+    ids = np.asarray(ids).astype(np.uint64)
+    s0 = s1 = np.uint64(0)
+    with np.errstate(over="ignore"):
+        for f, k in enumerate(keys + ("flag",)):
+            if k == "flag":
+                bits = (np.asarray(state[k]).astype(np.uint64) & np.uint64(1))
+            else:
+                bits = np.ascontiguousarray(state[k], dtype=np.float64).view(np.uint64)
+            a = _mix64(bits ^ _mix64(np.uint64(16) * ids + np.uint64(f)))
+            s0 = s0 + a.sum(dtype=np.uint64)
+            s1 = s1 + _mix64(a + np.uint64(0xD6E8FEB86659FD93)).sum(dtype=np.uint64)
+    return int(s0), int(s1), int(len(ids))
+
+
+def combine_digests(parts):
+    """Sum of per-rank digests (mod 2^64 per component)."""
+    m = (1 << 64) - 1
+    return tuple(sum(p[i] for p in parts) & m for i in range(3))
 
 
 class Simulation:
@@ -397,6 +435,11 @@ class Simulation:
         self._check(rc, "amc_get_outputs_raw")
         st.update(hist_counts=counts, n_paths=np.uint64(n.value), path_limbs=limbs,
                   step_index=np.int64(self.lib.amc_get_step_index(self.h)))
+        if self.rng_mode == RNG_HOST:
+            # parity mode draws from the two global Mersenne-Twister streams (host_rng.py): part of the state
+            import pickle
+            import random
+            st["host_rng"] = np.frombuffer(pickle.dumps((np.random.get_state(), random.getstate())), dtype=np.uint8)
         if path is not None:
             np.savez(path, **st)
         return st
@@ -412,6 +455,21 @@ class Simulation:
                                           limbs.ctypes.data_as(C.POINTER(C.c_uint64)))
         self._check(rc, "amc_set_outputs_raw")
         self.set_step_index(int(ck["step_index"]))
+        if self.rng_mode == RNG_HOST:
+            if "host_rng" not in ck:
+                raise AmcError("checkpoint of a host-RNG run without the Mersenne-Twister states: exact resume impossible")
+            import pickle
+            import random
+            np_state, py_state = pickle.loads(np.asarray(ck["host_rng"], dtype=np.uint8).tobytes())
+            np.random.set_state(np_state)
+            random.setstate(py_state)
+
+    def state_digest(self):
+        """(sum0, sum1, count): order-independent checksum of the owned particle state, computed on the device
+        (amc_state_digest); equals digest_of_arrays(arange(n), get_state()) for a single-domain handle."""
+        out = (C.c_uint64 * 3)()
+        self._check(self.lib.amc_state_digest(self.h, out), "amc_state_digest")
+        return int(out[0]), int(out[1]), int(out[2])
 
     def clear_taps(self):
         self._check(self.lib.amc_clear_taps(self.h), "amc_clear_taps")

@@ -188,6 +188,7 @@ static int create_impl(amc_handle *h, const amc_config *cfg, int device)
     P &p = h->p;
     memset(&p, 0, sizeof(p));
     h->cap = cfg->max_particles;
+    p.cap = h->cap;
     int rc;
     if ((rc = alloc_arrays(h, p.a, h->cap)) != AMC_OK) return rc;
     if ((rc = alloc_arrays(h, p.b, h->cap)) != AMC_OK) return rc;
@@ -246,7 +247,7 @@ static int create_impl(amc_handle *h, const amc_config *cfg, int device)
         CK(cudaMemcpy(dh, cfg->hist_edges, (AMC_NUM_BINS + 1) * sizeof(double), cudaMemcpyHostToDevice));
         p.hist_edges = dh; p.hist_first = cfg->hist_first; p.hist_last = cfg->hist_last;
     }
-    ALLOC(p.hist, 4 * AMC_NUM_BINS); ALLOC(p.path_count, 1); ALLOC(p.path_sums, 8);
+    ALLOC(p.hist, 4 * AMC_NUM_BINS); ALLOC(p.path_count, 1); ALLOC(p.path_sums, 8 + 3); /* + scratch of amc_state_digest */
     CK(cudaMemset(p.hist, 0, 4 * AMC_NUM_BINS * sizeof(unsigned long long)));
     CK(cudaMemset(p.path_count, 0, sizeof(unsigned long long)));
     CK(cudaMemset(p.path_sums, 0, 8 * sizeof(unsigned long long)));
@@ -413,6 +414,7 @@ extern "C" int amc_get_state(amc_handle *h, double *x, double *y, double *z, dou
                              double *dist, double *dist_x, double *dist_y, double *dist_z, uint8_t *flag)
 {
     if (!h) return AMC_E_INVALID;
+    if (h->slab) return h->fail(AMC_E_STATE, "slab handles hold global particle ids: read them with amc_slab_get_owned");
     CK(cudaSetDevice(h->device));
     int rc = unsort(h);
     if (rc != AMC_OK) return rc;
@@ -494,6 +496,7 @@ extern "C" int amc_step(amc_handle *h, int32_t n_steps, amc_step_stats *stats)
 {
     if (!h) return AMC_E_INVALID;
     if (n_steps < 0) return h->fail(AMC_E_INVALID, "n_steps < 0");
+    if (h->slab) return h->fail(AMC_E_STATE, "slab handles are stepped through the amc_slab_* entry points");
     if (h->cfg.kind == AMC_KIND_TEMP && h->cfg.rng_mode == AMC_RNG_HOST)
         return h->fail(AMC_E_STATE, "host-RNG handles are stepped through the phase-level entry points");
     CK(cudaSetDevice(h->device));
@@ -652,6 +655,7 @@ extern "C" int amc_recapture(amc_handle *h, int64_t *count, int64_t *count_after
 extern "C" int amc_pairs(amc_handle *h, amc_step_stats *stats)
 {
     if (!h) return AMC_E_INVALID;
+    if (h->slab) return h->fail(AMC_E_STATE, "slab handles are stepped through the amc_slab_* entry points");
     int rc = phase_begin(h);
     if (rc != AMC_OK) return rc;
     P &p = h->p;
@@ -797,6 +801,7 @@ extern "C" int amc_get_wall_bits(amc_handle *h, uint16_t *bits)
 {
     if (!h) return AMC_E_INVALID;
     if (!h->p.wall_bits) return h->fail(AMC_E_STATE, "AMC_TAP_WALL_BITS not enabled");
+    if (h->slab) return h->fail(AMC_E_STATE, "the wall-bits tap is indexed by particle id and not available on slab handles");
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaMemcpy(bits, h->p.wall_bits, h->n * sizeof(uint16_t), cudaMemcpyDeviceToHost));
@@ -911,6 +916,7 @@ extern "C" int amc_slab_enable(amc_handle *h, const amc_slab_config *c)
     if (h->cfg.pp_mode != AMC_PP_GROUPS) return h->fail(AMC_E_INVALID, "slabs need the colour-group schedule");
     if (c->nranks < 1 || c->rank < 0 || c->rank >= c->nranks || !c->cuts || !c->gz_edge || !c->gz_lo) return h->fail(AMC_E_INVALID, "bad slab config");
     if (c->cuts[c->rank + 1] - c->cuts[c->rank] != h->cfg.nc[2]) return h->fail(AMC_E_INVALID, "handle z grid does not match its slab");
+    if (h->p.wall_bits) return h->fail(AMC_E_INVALID, "AMC_TAP_WALL_BITS is indexed by particle id (global on a slab handle): not available with slabs");
     CK(cudaSetDevice(h->device));
     P &p = h->p;
     p.slab = 1; p.srank = c->rank; p.nranks = c->nranks; p.zoff = c->cuts[c->rank]; p.gncz = c->gncz;
@@ -969,8 +975,9 @@ static int slab_overflow_error(amc_handle *h, const unsigned long long ovf[4])
 {
     if (!(ovf[0] | ovf[1] | ovf[2] | ovf[3])) return AMC_OK;
     char msg[256];
-    snprintf(msg, sizeof(msg), "slab exchange overflow: %llu transfer records beyond xfer_capacity=%d, %llu relation-table entries, "
-             "%llu boundary records beyond bnd_capacity=%d, %llu foreign copies", ovf[0], h->p.xf_cap, ovf[1], ovf[2], h->p.bnd_cap, ovf[3]);
+    snprintf(msg, sizeof(msg), "slab exchange overflow (the particle state of this handle is invalid from here on): %llu transfer records beyond "
+             "xfer_capacity=%d or max_particles, %llu relation-table entries, %llu boundary records beyond bnd_capacity=%d, %llu foreign copies",
+             ovf[0], h->p.xf_cap, ovf[1], ovf[2], h->p.bnd_cap, ovf[3]);
     return h->fail(AMC_E_CAPACITY, msg);
 }
 
@@ -997,6 +1004,7 @@ extern "C" int amc_slab_advect(amc_handle *h)
     h->slab_phase = PH_DRIFT | PH_WALLS | (p.kind != AMC_KIND_CUBE ? PH_RECAP : 0);
     if (h->n) k_keys<true><<<grid_for(h->n, ADVECT_THREADS), ADVECT_THREADS, 0, h->stream>>>(p, h->slab_phase);
     k_xfer_headers<<<1, 32, 0, h->stream>>>(p);
+    h->last_launches += (h->n ? 1 : 0) + 1; /* slab handles: cumulative (amc_last_timing) */
     CK(cudaGetLastError());
     return AMC_OK;
 }
@@ -1016,6 +1024,7 @@ extern "C" int amc_slab_sort(amc_handle *h, int64_t *n_resident)
     k_scan_sums<<<1, SCAN_THREADS, 0, h->stream>>>(h->d_tile_sums, ntiles);
     k_scan_add<<<ntiles, SCAN_THREADS, 0, h->stream>>>(p.cell_start, h->d_tile_sums, m, 0);
     if (bound) k_scatter_advect<true><<<grid_for(bound, ADVECT_THREADS), ADVECT_THREADS, 0, h->stream>>>(p, h->slab_phase);
+    h->last_launches += 4 + (bound ? 1 : 0);
     CK(cudaGetLastError());
     std::swap(p.a, p.b);
     int32_t counts[2] = {0, 0}; // resident = start of the GONE bucket; n_in for the capacity check
@@ -1052,6 +1061,7 @@ extern "C" int amc_slab_pairs_begin(amc_handle *h, int32_t pre_round)
     CK(cudaEventRecord(h->det_events[1], h->stream));
     h->slab_det_pending = true;
     if (pre_round) k_bnd_pack<<<2, ADVECT_THREADS, 0, h->stream>>>(p); // immigrants that landed in the top band; else they travel after group 0
+    h->last_launches += 2 + (h->n ? 1 : 0) + (pre_round ? 1 : 0);
     CK(cudaGetLastError());
     return AMC_OK;
 }
@@ -1066,6 +1076,7 @@ extern "C" int amc_slab_group(amc_handle *h, int32_t g)
     unsigned grid = (unsigned)std::min<int64_t>((int64_t)h->pair_grid, std::max<int64_t>(ncell / 8, 1));
     if (h->n) k_pairs_group<<<grid, PAIR_THREADS, 0, h->stream>>>(p, g);
     k_bnd_pack<<<2, ADVECT_THREADS, 0, h->stream>>>(p);
+    h->last_launches += (h->n ? 1 : 0) + 1;
     CK(cudaGetLastError());
     return AMC_OK;
 }
@@ -1076,7 +1087,7 @@ extern "C" int amc_slab_apply(amc_handle *h, int32_t group_done)
     if (rc != AMC_OK) return rc;
     P &p = h->p;
     p.group_done = group_done;
-    if (p.nranks > 1) k_bnd_apply<<<dim3(48, 2), 128, 0, h->stream>>>(p);
+    if (p.nranks > 1) { k_bnd_apply<<<dim3(48, 2), 128, 0, h->stream>>>(p); h->last_launches += 1; }
     CK(cudaGetLastError());
     return AMC_OK;
 }
@@ -1088,7 +1099,7 @@ extern "C" int amc_slab_finish(amc_handle *h, amc_step_stats *stats)
     P &p = h->p;
     int32_t nf = 0;
     CK(cudaMemcpyAsync(&nf, p.n_foreign, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
-    if (h->n && p.kind != AMC_KIND_CUBE) k_recapture_list<<<148, ADVECT_THREADS, 0, h->stream>>>(p);
+    if (h->n && p.kind != AMC_KIND_CUBE) { k_recapture_list<<<148, ADVECT_THREADS, 0, h->stream>>>(p); h->last_launches += 1; }
     unsigned long long ovf[4] = {0, 0, 0, 0};
     CK(cudaMemcpyAsync(ovf, h->d_slab_overflow, sizeof(ovf), cudaMemcpyDeviceToHost, h->stream));
     rc = phase_end(h, stats);
@@ -1100,6 +1111,7 @@ extern "C" int amc_slab_finish(amc_handle *h, amc_step_stats *stats)
         h->slab_det_pending = false;
     }
     if ((rc = slab_overflow_error(h, ovf)) != AMC_OK) return rc;
+    if (h->n + nf > h->cap) return h->fail(AMC_E_CAPACITY, "max_particles too small for the foreign copies of this step (state invalid)");
     h->n += nf; // foreign copies appended behind the sorted particles; dropped by the next amc_slab_advect
     p.n = h->n;
     return AMC_OK;
@@ -1130,6 +1142,21 @@ extern "C" int amc_slab_get_owned(amc_handle *h, int64_t cap, int64_t *n, int64_
     if (ids && c) CK(cudaMemcpyAsync(tmp.data(), b.id, c * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     if (ids) for (int32_t k = 0; k < c; k++) ids[k] = tmp[(size_t)k];
+    return AMC_OK;
+}
+
+extern "C" int amc_state_digest(amc_handle *h, uint64_t out[3])
+{
+    if (!h || !out) return AMC_E_INVALID;
+    CK(cudaSetDevice(h->device));
+    unsigned long long *d = reinterpret_cast<unsigned long long *>(h->p.path_sums) + 8; /* three spare words behind the path sums */
+    CK(cudaMemsetAsync(d, 0, 3 * sizeof(unsigned long long), h->stream));
+    if (h->n) k_state_digest<<<148 * 4, ADVECT_THREADS, 0, h->stream>>>(h->p, d);
+    CK(cudaGetLastError());
+    unsigned long long v[3];
+    CK(cudaMemcpyAsync(v, d, sizeof(v), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    out[0] = v[0]; out[1] = v[1]; out[2] = v[2];
     return AMC_OK;
 }
 

@@ -51,6 +51,7 @@ struct StatsDev {
 
 struct P {
     int64_t n;
+    int64_t cap;          /* slots of every per-particle array */
     Arrays a, b;
     double *px, *py, *pz;
     int32_t *key, *rank;

@@ -295,7 +295,7 @@ template <bool SLAB>
 __global__ void __launch_bounds__(ADVECT_THREADS, 3) k_scatter_advect(const __grid_constant__ P p, const int phase)
 {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= p.n + (SLAB ? *p.n_in : 0)) return;
+    if (s >= p.n + (SLAB ? *p.n_in : 0) || s >= p.cap) return;
     Part q;
     load_part(p.a, s, q);
     const int32_t id = p.a.id[s];
@@ -398,7 +398,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_add(int32_t *out, const i
 __global__ void __launch_bounds__(ADVECT_THREADS) k_scatter(const __grid_constant__ P p)
 {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= p.n + (p.slab ? *p.n_in : 0)) return;
+    if (s >= p.n + (p.slab ? *p.n_in : 0) || s >= p.cap) return;
     int32_t k = p.key[s], r = p.rank[s];
     int64_t t = (int64_t)p.cell_start[k] + (r >= 0 ? r : p.band_count[k] + ~r);
     p.b.x[t] = p.a.x[s]; p.b.y[t] = p.a.y[s]; p.b.z[t] = p.a.z[s];
@@ -1600,6 +1600,7 @@ __global__ void __launch_bounds__(ADVECT_THREADS) k_xfer_unpack(const __grid_con
     if (j >= cnt) return;
     const double *r = blk + (size_t)(1 + j) * AMC_REC;
     int64_t s = p.n + atomicAdd(p.n_in, 1);
+    if (s >= p.cap) { atomicAdd(p.slab_overflow + 0, 1ull); return; } /* reported by amc_slab_sort; the state is invalid afterwards */
     Part q;
     q.x = r[0]; q.y = r[1]; q.z = r[2]; q.vx = r[3]; q.vy = r[4]; q.vz = r[5]; q.d = r[6]; q.dx = r[7]; q.dy = r[8]; q.dz = r[9];
     q.flag = (uint32_t)r[11];
@@ -1660,7 +1661,7 @@ __global__ void __launch_bounds__(128) k_bnd_apply(const __grid_constant__ P p)
     const Arrays &A = p.a;
     if (tid == 0 && s_slot < 0) { // unknown here: a particle the neighbour moved into this rank's reach
         int f = atomicAdd(p.n_foreign, 1);
-        if (f >= p.foreign_cap) { atomicAdd(p.slab_overflow + 3, 1ull); s_slot = -2; }
+        if (f >= p.foreign_cap || p.n + f >= p.cap) { atomicAdd(p.slab_overflow + 3, 1ull); s_slot = -2; }
         else {
             int s = (int)p.n + f;
             s_slot = s;
@@ -1743,4 +1744,44 @@ __global__ void __launch_bounds__(ADVECT_THREADS) k_compact_owned(const __grid_c
     p.b.d[t] = p.a.d[s]; p.b.dx[t] = p.a.dx[s]; p.b.dy[t] = p.a.dy[s]; p.b.dz[t] = p.a.dz[s];
     p.b.flag[t] = fl & AMC_FLAG_PATH;
     p.b.id[t] = p.a.id[s];
+}
+
+// Order-independent 128-bit checksum of the particles this handle owns (ghost copies excluded): for every
+// particle and field f, a = mix64(bits(value) ^ mix64(16 * id + f)); out[0] += a, out[1] += mix64(a + C), out[2] += 1
+// per particle (all mod 2^64).  Sums commute, so the value does not depend on the slot order or on how the
+// particles are spread over ranks: a 1-GPU run and an N-rank slab run of the same job agree iff their id-ordered
+// states agree bit for bit (amc.digest_of_arrays is the NumPy restatement).
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z)
+{
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__global__ void __launch_bounds__(ADVECT_THREADS) k_state_digest(const __grid_constant__ P p, unsigned long long *out)
+{
+    __shared__ unsigned long long sh[3];
+    if (threadIdx.x < 3) sh[threadIdx.x] = 0;
+    __syncthreads();
+    unsigned long long a0 = 0, a1 = 0, cnt = 0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < p.n; s += stride) {
+        const unsigned fl = p.a.flag[s];
+        if (fl & AMC_FLAG_GHOST) continue;
+        const unsigned long long id = (unsigned long long)(uint32_t)p.a.id[s];
+        const double v[10] = {p.a.x[s], p.a.y[s], p.a.z[s], p.a.vx[s], p.a.vy[s], p.a.vz[s], p.a.d[s], p.a.dx[s], p.a.dy[s], p.a.dz[s]};
+#pragma unroll
+        for (int f = 0; f < 11; f++) {
+            const unsigned long long bits = f < 10 ? (unsigned long long)__double_as_longlong(v[f < 10 ? f : 0]) : (unsigned long long)(fl & AMC_FLAG_PATH);
+            const unsigned long long a = mix64(bits ^ mix64(16ull * id + (unsigned long long)f));
+            a0 += a; a1 += mix64(a + 0xD6E8FEB86659FD93ull);
+        }
+        cnt++;
+    }
+    for (int o = 16; o; o >>= 1) {
+        a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o); cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&sh[0], a0); atomicAdd(&sh[1], a1); atomicAdd(&sh[2], cnt); }
+    __syncthreads();
+    if (threadIdx.x < 3 && sh[threadIdx.x]) atomicAdd(&out[threadIdx.x], sh[threadIdx.x]);
 }

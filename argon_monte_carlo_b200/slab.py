@@ -192,6 +192,9 @@ class LocalTransport:
     def allreduce_sum(self, value):
         return value
 
+    def allreduce_u64(self, values):
+        return tuple(values)
+
 
 class DistTransport:
     """One rank per process over torch.distributed (NCCL over NVLink on the GPU box; gloo on CPU tensors
@@ -249,6 +252,16 @@ class DistTransport:
             t = t.cuda()
         self.dist.all_reduce(t, group=self.group)
         return t.cpu().numpy()
+
+
+    def allreduce_u64(self, values):
+        """Component-wise sum mod 2^64 over all ranks (int64 adds wrap like uint64 ones)."""
+        import torch
+        t = torch.as_tensor(np.array(values, dtype=np.uint64).view(np.int64).copy())
+        if self.dist.get_backend(self.group) == "nccl":
+            t = t.cuda()
+        self.dist.all_reduce(t, group=self.group)
+        return tuple(int(v) for v in t.cpu().numpy().view(np.uint64))
 
 
 SUM_KEYS = ("wall_collisions", "pp_collisions", "pair_checks_ref", "pair_checks_exec", "oob_after_walls", "oob_after_pp",
@@ -449,6 +462,12 @@ class SlabSimulation:
             seen += len(ids)
         out["_owned_total"] = seen
         return out
+
+    def state_digest(self, reduce=True):
+        """(sum0, sum1, count) of amc_state_digest over the owned particles of all ranks: equal to the digest of
+        the single-domain run of the same job iff the id-ordered states agree bit for bit."""
+        d = amc.combine_digests([r.sim.state_digest() for r in self.ranks])
+        return self.transport.allreduce_u64(d) if reduce else d
 
     def histograms(self):
         counts, n, sums = None, 0, None

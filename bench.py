@@ -15,10 +15,16 @@ config 5).  The state (1 GB per GPU at fp64) is far larger than the 126 MB L2, s
 steps never re-read a warm cache.  `also` carries the same measurement for config 2
 (Open_Air_Pore_MC.py at the reference particle count, L2 flushed between timed steps).
 
---impl reference: the reference's CPU implementation of the path, timed on the host cores.  The
-upstream project is pure Python and cannot travel to the GPU box, so this arm times the C port of
-its algorithm (oracle/amc_oracle.c, OpenMP over the cells of a colour group) on a bounded sample
-of the same workload; its measured Python multiprocessing rate is quoted in BASELINE.md.
+--impl reference: the reference's CPU implementation of the path, timed on the host cores: the
+unmodified Temperature_Pore_MC.py (staged into the git-ignored baseline/_ref by __graft_entry__.build(),
+baseline/stage.py; one timestep of its 557,649-particle configuration, ~1.5 minutes, times taken from
+the script's own prints).  The C port of its algorithm (oracle/amc_oracle.c, OpenMP over the cells of
+a colour group, thread count pinned to os.cpu_count()) is timed beside it as `cpu_baseline_port` and
+stands in when the staged copy is missing.
+
+Out of band (never inside a timed region): N = 1 replays two steps of the workload through the CPU
+oracle and compares the states bit for bit (`verify`); N > 1 replays the whole job as one domain on
+rank 0's GPU and compares the order-independent state checksum (`verify.identical_to_single_gpu`).
 """
 from __future__ import annotations
 
@@ -37,7 +43,20 @@ sys.path.insert(0, ROOT)
 
 B_STEP = 162.0      # algorithmic bytes per particle-step, fp64 state read + written once
 B_PAIR = 32.0       # algorithmic bytes per particle for the pair kernel: 3 x f64 position + cell header
-NCU_DETECT_TRAFFIC = 317.8e6   # dram__bytes_read.sum + dram__bytes_write.sum of one k_detect launch at 12,499,989 particles
+
+
+def ncu_traffic(kernel, particles):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of `kernel` from the committed ncu --set full
+    capture (profiles/ncu_traffic.json, written by tools/ncu_traffic.py from the capture's raw page); None unless
+    the capture was taken on this workload (same particle count)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            for rec in json.load(f)["kernels"]:
+                if kernel.startswith(rec["kernel"]) and abs(rec["particles"] - particles) <= 1e-3 * particles:
+                    return {"bytes": rec["dram_bytes"], "source": rec["source"]}
+    except Exception:
+        pass
+    return None
 
 
 def measured_peaks():
@@ -217,6 +236,7 @@ def run_ours(args):
     ms, launches = sim.last_timing()
     barrier()
     clk = clocks.stop()
+    digest = sim.state_digest()
     dev_ms = max_over_ranks(ms[4])
     total_particles = sum_over_ranks(float(n))
     value = total_particles * args.steps / (dev_ms * 1e-3)
@@ -229,12 +249,13 @@ def run_ours(args):
     # ordered resolution that follows only visits the ~0.05 % of cells it flags).  Per launch: algorithmic bytes =
     # 32 B x particles (3 x f64 position + cell header), duration = CUDA events around the launch on the
     # handle's stream; traffic = dram read + write of one launch from the ncu --set full capture of this workload
-    # (profiles/r1_v8_ncu_full_summary.csv)
+    # (profiles/ncu_traffic.json; null when no capture of this workload is committed)
+    traffic = ncu_traffic("k_detect", n)
     roofline = {"bound": "hbm", "kernel": "k_detect (pair detection, 1 launch per step)",
                 "achieved": B_PAIR * n / (det_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": B_PAIR * n,
                 "avg_launch_ms": det_ms,
-                "traffic": NCU_DETECT_TRAFFIC * n / 12499989 if abs(n - 12499989) < 1e5 else None}
+                "traffic": traffic["bytes"] if traffic else None, "traffic_source": traffic["source"] if traffic else None}
     roofline["frac"] = roofline["achieved"] / hbm_peak
     whole = {"achieved": B_STEP * n * args.steps / (ms[4] * 1e-3) / 1e9, "unit": "GB/s"}
     whole["frac"] = whole["achieved"] / hbm_peak
@@ -291,13 +312,18 @@ def run_ours(args):
         "collision_checks_per_s": {"reference_equivalent": checks_ref * world / (dev_ms / args.steps * 1e-3),
                                    "executed": checks_exec * world / (dev_ms / args.steps * 1e-3)},
         "collisions_per_step": collisions, "wall_s": wall,
+        "state_digest": {"digest": ["%016x" % d for d in digest[:2]], "particles_counted": digest[2], "steps": args.warmup + args.steps},
     }
 
     # ---------------------------------------------------------------- config 2 beside it (rank 0, N = 1 only)
     if rank == 0 and world == 1 and not args.no_also:
         out["also"] = bench_pore_ref(args, hbm_peak)
+    if rank == 0 and world == 1 and not args.no_verify:
+        out["verify"] = verify_against_oracle(cfg, state if not args.device_init else None, local)
     if rank == 0 and world == 1 and not args.no_cpu:
         out["cpu_baseline"] = cpu_baseline(steps=8, warmup=2)
+        if not args.no_ref:
+            out["cpu_baseline_reference"] = reference_baseline(1)
     if rank == 0:
         emit(out)
     if world > 1:
@@ -315,14 +341,14 @@ def run_slabs(args, world, rank, local, dev, hbm_peak, peak_src, barrier, max_ov
     _, _, _, zs, _, _, _ = init_state.synthetic_pore_chunk(cfg, 17, 0, 1 << 22)   # representative sample: regions are drawn at random
     cuts = slab.balanced_cuts(zs, edges, world)
 
-    def keep(z):
-        layer = slab.owner_layer(z, edges)
-        return (layer >= cuts[rank]) & (layer < cuts[rank + 1])
-    ids, *state = init_state.synthetic_pore_chunked(cfg, 17, keep=keep)
-    n = len(ids)
+    from argon_monte_carlo_b200 import amc
     sim = slab.SlabSimulation(cfg, world, zs, transport=slab.DistTransport(), local_ranks=[rank], devices=[local],
                               cuts=cuts, n_total=cfg.num_molecules, seed=17)
-    sim.set_local_state(ids, *state, n_global=cfg.num_molecules)
+    # the gas is generated on the devices (amc_init_synthetic): particle i depends only on (seed, i), so every rank
+    # makes exactly its own slab and the 1-GPU replay below makes the very same job
+    sim.init_synthetic(lambda kz: init_state.pore_spec(cfg, 17, keep_z=kz))
+    n = sim.particles_per_rank()[0]
+    launches0 = sim.ranks[0].sim.last_timing()[1]
     sim.step(args.warmup, reduce=False)
     clocks = ClockSampler(local)
     barrier()
@@ -334,6 +360,9 @@ def run_slabs(args, world, rank, local, dev, hbm_peak, peak_src, barrier, max_ov
     ms = sim.phase_ms
     barrier()
     clk = clocks.stop()
+    launches = sim.ranks[0].sim.last_timing()[1] - launches0       # counted by the library: kernels this rank launched
+    launches_timed = launches * args.steps // (args.steps + args.warmup)
+    digest = sim.state_digest()                                    # id-ordered state of all ranks after warmup + steps
     dev_ms = max_over_ranks(float(ms.sum()))
     per_rank = torch.zeros(world, 5, dtype=torch.float64, device=dev)
     per_rank[rank, :4] = torch.as_tensor(ms / args.steps, dtype=torch.float64)
@@ -370,17 +399,36 @@ def run_slabs(args, world, rank, local, dev, hbm_peak, peak_src, barrier, max_ov
     e2e = {"value": total_particles * e2e_steps / e2e_s, "unit": "particle-steps/s", "steps": e2e_steps,
            "h2d_bytes_per_step": int(n * 89), "d2h_bytes_per_step": int(n * 89)}
     sim.close()
+    # out of band: rank 0 repeats the whole job as ONE domain on its own GPU; the N-rank run must have left the
+    # same id-ordered state (order-independent checksum over all particles, amc_state_digest)
+    verify = {"skipped": "--no-verify"}
+    if not args.no_verify:
+        verify = {"digest": ["%016x" % d for d in digest[:2]], "particles_counted": digest[2],
+                  "steps": args.warmup + args.steps}
+        if rank == 0:
+            try:
+                torch.cuda.empty_cache()
+                one = amc.Simulation(cfg, seed=17, device=local, max_particles=cfg.num_molecules)
+                one.init_synthetic(init_state.pore_spec(cfg, 17))
+                one.step_quiet(args.warmup + args.steps)
+                d1 = one.state_digest()
+                one.close()
+                verify.update(digest_single_gpu=["%016x" % d for d in d1[:2]], identical_to_single_gpu=tuple(d1) == tuple(digest))
+            except Exception as exc:
+                verify["single_gpu_replay_failed"] = str(exc)[-200:]
+        barrier()
     out = {
         "metric": "collision-resolved particle-steps/s", "value": value, "unit": "particle-steps/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "verify": verify,
         "config": {"workload": "temp_pore_scaled: ONE energized thruster pore (Temperature_Pore_MC geometry x %.3f), "
                                "%d particles = %d per GPU, device RNG, slab-decomposed along z over %d GPUs"
                                % (scale, cfg.num_molecules, args.particles_per_gpu, world),
                    "particles_total": int(total_particles), "cells": list(cfg.grid.nc), "cuts": [int(c) for c in cuts],
                    "particles_max_per_gpu": int(n_max), "parallelism": "z slabs, NCCL all-to-all + neighbour send/recv",
                    "l2": "inputs larger than L2"},
-        "clocks": clk, "e2e": e2e, "gpu_launches": 54 * args.steps,
+        "clocks": clk, "e2e": e2e, "gpu_launches": int(launches_timed),
         "roofline": roofline,
         "phases_ms_per_step": {"advect_walls": ms[0] / args.steps, "exchange_sort": ms[1] / args.steps,
                                "pairs_and_handover": ms[2] / args.steps, "pair_detect_slowest_rank": det_ms,
@@ -423,12 +471,55 @@ def bench_pore_ref(args, hbm_peak):
             "launches_per_step": launches, "steps": k}
 
 
+def verify_against_oracle(cfg, state, device, steps=2):
+    """Outside every timed region: `steps` timesteps of the benchmarked workload from its initial state on the GPU
+    and through the CPU oracle; the id-ordered states must agree bit for bit (tests/test_gpu_bench_workload.py is
+    the same check under pytest, pair set included)."""
+    from oracle import oracle as O, steps as S
+    from argon_monte_carlo_b200 import amc, config, init_state
+    if state is None:
+        return {"skipped": "device-initialised state"}
+    O.set_ref_mode(False)
+    O.set_num_threads(os.cpu_count())
+    cheb = config.gap_energy_chebyshev(cfg, 16)
+    sim = amc.Simulation(cfg, seed=17, cheb=cheb, device=device, max_particles=len(state[0]))
+    sim.set_state(*state)
+    st = O.ParticleState(*state)
+    g = sim.step(steps)
+    got, dig = sim.get_state(), sim.state_digest()
+    sim.close()
+    t0 = time.perf_counter()
+    r = [S.temp_step_philox(st, cfg, 17, k, cheb) for k in range(steps)]
+    ok = all(np.array_equal(got[k], getattr(st, k)) for k in O.STATE_KEYS) and np.array_equal(got["flag"].astype(bool), st.flag.astype(bool))
+    ok_counts = all(a["collisions"] == b["collisions"] and a["pair_checks_ref"] == b["checks"] for a, b in zip(g, r))
+    return {"against": "oracle/amc_oracle.c (CPU restatement of the reference algorithm)", "steps": steps, "particles": st.n,
+            "state_bit_identical": bool(ok), "counters_identical": bool(ok_counts),
+            "digest_matches": dig == amc.digest_of_arrays(np.arange(st.n), st.arrays()),
+            "collisions_per_step": [int(a["collisions"]) for a in g], "oracle_s": time.perf_counter() - t0}
+
+
+def reference_baseline(steps, kind="temp"):
+    """the unmodified upstream script on the host cores (baseline/stage.py; the staged copy lives in
+    the git-ignored baseline/_ref, which travels to the GPU box)."""
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "baseline"))
+        import stage
+        if not stage.staged():
+            return {"unavailable": "baseline/_ref not staged (python baseline/stage.py stage in the build container)"}
+        return stage.run(kind, steps, timeout=1500)
+    except Exception as exc:
+        return {"unavailable": str(exc)[-300:]}
+
+
 def cpu_baseline(steps, warmup, particles=None):
     """The oracle port on the host cores, on a bounded sample of the workload: the energized pore at
-    the reference particle count (same density, cell size and step as the GPU run)."""
+    the reference particle count (same density, cell size and step as the GPU run).  The OpenMP team is pinned
+    to os.cpu_count() threads so that `cores` is the same whatever OMP_NUM_THREADS the launcher exported
+    (torchrun sets it to 1)."""
     from oracle import oracle as O, steps as S
     from argon_monte_carlo_b200 import config, init_state
     O.set_ref_mode(False)
+    O.set_num_threads(os.cpu_count())
     cfg = config.pore_config(True)
     cheb = config.gap_energy_chebyshev(cfg, 16)
     st = O.ParticleState(*init_state.synthetic_pore_state(cfg, seed=17))
@@ -450,16 +541,22 @@ def run_reference(args):
         return
     world = int(os.environ.get("WORLD_SIZE", "1"))
     steps = max(1, min(args.steps, 20))
-    cb = cpu_baseline(steps=steps, warmup=min(args.warmup, 3))
-    cfg, scale = scaled_temp_config(args.particles_per_gpu)
+    port = cpu_baseline(steps=steps, warmup=min(args.warmup, 3))
+    # the reference's own implementation of the path: the unmodified Temperature_Pore_MC.py (multiprocessing over
+    # cpu_count()+1 workers), one timestep of ~1.5 min; the C port of its algorithm is reported beside it and stands
+    # in when the staged copy is missing
+    ref = {"unavailable": "--port-only"} if args.port_only else reference_baseline(1)
+    cb = ref if "value" in ref else port
     out = {"impl": "reference", "metric": "collision-resolved particle-steps/s", "value": cb["value"],
-           "unit": "particle-steps/s", "n_gpus": world, "steps": steps, "warmup": min(args.warmup, 3),
+           "unit": "particle-steps/s", "n_gpus": world, "steps": 1 if cb is ref else steps, "warmup": 0 if cb is ref else min(args.warmup, 3),
            "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-           "dtype": "f64", "data": "synthetic",
+           "dtype": "f64", "data": "synthetic" if cb is port else "reference initial state (seeds 17)",
            "config": {"workload": "temp_pore_scaled (bounded sample: the same energized pore at the reference size, "
                                   "557,649 particles; throughput per particle is size-independent at fixed density)"},
-           "cpu_baseline": cb,
+           "cpu_baseline": cb, "cpu_baseline_port": port,
            "e2e": {"value": cb["value"], "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if cb is port:
+        out["reference_script"] = ref
     emit(out)
 
 
@@ -495,6 +592,9 @@ def main():
     ap.add_argument("--device-init", action="store_true", help="1 GPU: generate the synthetic state on the device instead of on the host")
     ap.add_argument("--no-also", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-ref", action="store_true", help="skip the 1.5-minute run of the unmodified upstream script (cpu_baseline_reference)")
+    ap.add_argument("--no-verify", action="store_true", help="skip the out-of-band check against the oracle / the 1-GPU replay")
+    ap.add_argument("--port-only", action="store_true", help="--impl reference: time only the C port of the reference algorithm")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -201,6 +201,13 @@ int amc_get_outputs_raw(amc_handle *h, uint64_t *counts, uint64_t *n_paths, uint
 int amc_set_outputs_raw(amc_handle *h, const uint64_t *counts, uint64_t n_paths, const uint64_t *limbs8);
 int64_t amc_get_step_index(const amc_handle *h);
 
+/* Order-independent checksum of the particle state this handle owns (slab handles: ghost copies excluded), computed
+ * on the device: out[0], out[1] = two 64-bit sums over all (particle id, field, value bits) triples of the ten state
+ * arrays and the full_path_traveled flag (Pore:385-400), out[2] = number of particles counted.  Sums of the values of
+ * all ranks of a slab run (mod 2^64) equal the value of the single-domain run of the same job iff the id-ordered
+ * states are bit-identical -- the check that replaces reading 8 GB of state back at 100 M particles. */
+int amc_state_digest(amc_handle *h, uint64_t out[3]);
+
 /* set the step counter that keys the device RNG (default: counts amc_step / amc_walls calls from 0) */
 int amc_set_step_index(amc_handle *h, int64_t step);
 

@@ -783,6 +783,12 @@ void orc_histogram(const double *v, int64_t n, int nbins, double first, double l
     }
 }
 
+/* pin the OpenMP team size (bench.py: the same thread count at every GPU count, whatever OMP_NUM_THREADS the launcher exported) */
+void orc_set_num_threads(int n)
+{
+    if (n > 0) omp_set_num_threads(n);
+}
+
 int orc_num_threads(void)
 {
 #ifdef _OPENMP

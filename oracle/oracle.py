@@ -290,3 +290,8 @@ def cheb_eval(cheb, z):
 
 def num_threads():
     return int(lib().orc_num_threads())
+
+
+def set_num_threads(n):
+    lib().orc_set_num_threads(int(n))
+    return num_threads()
