@@ -39,8 +39,8 @@ def line(name, n, ms, launches, extra=None):
 
 
 def main():
-    args = [a for a in sys.argv[1:] if not a.startswith("--")]
     steps = int(sys.argv[sys.argv.index("--steps") + 1]) if "--steps" in sys.argv else 50
+    args = [a for a in sys.argv[1:] if a.startswith("cfg")]
     which = args or ["cfg1", "cfg2", "cfg3", "cfg3host"]
     if "cfg1" in which:
         cfg = config.cube_config()
