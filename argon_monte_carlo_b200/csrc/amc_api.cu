@@ -7,6 +7,7 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <unistd.h>
 #include "amc_kernels.cuh"
 
 static thread_local std::string g_create_error;
@@ -20,6 +21,13 @@ struct amc_handle {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool slab = false;
     int32_t xf_total = 0;
+    // peer-to-peer exchange (amc_slab_p2p_*): one allocation = flag words + both halves of every receive buffer
+    char *p2p_base = nullptr;
+    bool p2p = false;
+    std::vector<void *> p2p_opened;  // cudaIpcOpenMemHandle mappings, closed in amc_destroy
+    uint32_t xf_seq = 0, bnd_seq = 0;
+    int32_t *d_n = nullptr;          // device-resident particle count of amc_slab_step
+    amc_slab_p2p_desc p2p_desc;
     int32_t *d_counters = nullptr; // slab mode: xf_count[nranks], n_in, bnd_n[2], rel_count, n_foreign, compact count
     unsigned long long *d_slab_overflow = nullptr;
     P p;                        // kernel parameter block (device pointers)
@@ -150,6 +158,7 @@ extern "C" int amc_destroy(amc_handle *h)
     if (!h) return AMC_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    for (void *q : h->p2p_opened) cudaIpcCloseMemHandle(q);
     for (void *q : h->allocs) cudaFree(q);
     for (cudaEvent_t e : h->events) cudaEventDestroy(e);
     for (cudaEvent_t e : h->det_events) cudaEventDestroy(e);
@@ -931,6 +940,7 @@ extern "C" int amc_slab_enable(amc_handle *h, const amc_slab_config *c)
     p.down_thr = c->rank > 0 ? c->gz_edge[c->cuts[c->rank]] : -INFINITY;
     p.down_band = c->rank > 0 ? c->gz_lo[c->cuts[c->rank]] : INFINITY;
     p.xf_cap = std::max(c->xfer_capacity, c->xfer_capacity_far); p.bnd_cap = c->bnd_capacity;
+    p.xf_cap_nb = c->xfer_capacity; p.xf_cap_far = c->xfer_capacity_far;
     {
         std::vector<int32_t> off(c->nranks), capv(c->nranks);
         int32_t o = 0;
@@ -946,7 +956,7 @@ extern "C" int amc_slab_enable(amc_handle *h, const amc_slab_config *c)
         p.xf_off = doff; p.xf_capv = dcap;
         h->xf_total = o;
     }
-    p.xf_send = (double *)c->xfer_send; p.xf_recv = (const double *)c->xfer_recv;
+    p.xf_send = (double *)c->xfer_send; p.xf_recv = (const double *)c->xfer_recv; /* may be null: amc_slab_p2p_setup allocates */
     p.bnd_send[0] = (double *)c->bnd_send_up; p.bnd_send[1] = (double *)c->bnd_send_down;
     p.bnd_recv[0] = (const double *)c->bnd_recv_up; p.bnd_recv[1] = (const double *)c->bnd_recv_down;
     {
@@ -1142,6 +1152,190 @@ extern "C" int amc_slab_get_owned(amc_handle *h, int64_t cap, int64_t *n, int64_
     if (ids && c) CK(cudaMemcpyAsync(tmp.data(), b.id, c * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     if (ids) for (int32_t k = 0; k < c; k++) ids[k] = tmp[(size_t)k];
+    return AMC_OK;
+}
+
+// ---- device-resident multi-GPU stepping ---------------------------------------------------------------
+extern "C" int amc_slab_p2p_setup(amc_handle *h, amc_slab_p2p_desc *out)
+{
+    int rc = slab_check(h);
+    if (rc != AMC_OK) return rc;
+    if (!out) return h->fail(AMC_E_INVALID, "null descriptor");
+    P &p = h->p;
+    if (!h->p2p_base) {
+        const size_t flag_bytes = ((size_t)(p.nranks + 2) * sizeof(uint32_t) + 255) / 256 * 256;
+        const size_t xf_half = (size_t)h->xf_total * AMC_REC, bnd_half = (size_t)(p.bnd_cap + 1) * AMC_REC; /* doubles */
+        const size_t bytes = flag_bytes + (2 * xf_half + 4 * bnd_half) * sizeof(double);
+        ALLOC(h->p2p_base, bytes);
+        CK(cudaMemset(h->p2p_base, 0, bytes));
+        amc_slab_p2p_desc &d = h->p2p_desc;
+        memset(&d, 0, sizeof(d));
+        d.pid = (int64_t)getpid(); d.device = h->device; d.rank = p.srank; d.base = (uint64_t)(uintptr_t)h->p2p_base;
+        d.off_flags = 0; d.off_xfer = (int64_t)flag_bytes;
+        d.off_bnd_up = d.off_xfer + (int64_t)(2 * xf_half * sizeof(double));
+        d.off_bnd_down = d.off_bnd_up + (int64_t)(2 * bnd_half * sizeof(double));
+        d.xfer_stride = (int64_t)xf_half; d.bnd_stride = (int64_t)bnd_half;
+        cudaIpcMemHandle_t ipc;
+        CK(cudaIpcGetMemHandle(&ipc, h->p2p_base));
+        static_assert(sizeof(ipc) <= sizeof(d.ipc), "ipc handle size");
+        memcpy(d.ipc, &ipc, sizeof(ipc));
+        if (!p.xf_send) { double *snd = nullptr; ALLOC(snd, (size_t)h->xf_total * AMC_REC); p.xf_send = snd; }
+        ALLOC(h->d_n, 2);
+    }
+    *out = h->p2p_desc;
+    return AMC_OK;
+}
+
+extern "C" int amc_slab_p2p_connect(amc_handle *h, const amc_slab_p2p_desc *all)
+{
+    int rc = slab_check(h);
+    if (rc != AMC_OK) return rc;
+    if (!all || !h->p2p_base) return h->fail(AMC_E_STATE, "amc_slab_p2p_setup first");
+    P &p = h->p;
+    std::vector<double *> xf(p.nranks);
+    std::vector<uint32_t *> fl(p.nranks);
+    std::vector<char *> base(p.nranks, nullptr);
+    for (int r = 0; r < p.nranks; r++) {
+        const amc_slab_p2p_desc &d = all[r];
+        if (d.rank != r) return h->fail(AMC_E_INVALID, "descriptors must be ordered by rank");
+        if (d.xfer_stride != h->p2p_desc.xfer_stride || d.bnd_stride != h->p2p_desc.bnd_stride)
+            return h->fail(AMC_E_INVALID, "ranks disagree on the exchange buffer sizes");
+        if (r == p.srank) base[r] = h->p2p_base;
+        else if (d.pid == (int64_t)getpid()) { /* same process: the address is valid here, the devices need peer access */
+            base[r] = (char *)(uintptr_t)d.base;
+            if (d.device != h->device) {
+                cudaError_t e = cudaDeviceEnablePeerAccess(d.device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return h->fail(AMC_E_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+                cudaGetLastError();
+            }
+        } else {
+            cudaIpcMemHandle_t ipc;
+            memcpy(&ipc, d.ipc, sizeof(ipc));
+            void *q = nullptr;
+            CK(cudaIpcOpenMemHandle(&q, ipc, cudaIpcMemLazyEnablePeerAccess));
+            h->p2p_opened.push_back(q);
+            base[r] = (char *)q;
+        }
+        xf[r] = (double *)(base[r] + d.off_xfer);
+        fl[r] = (uint32_t *)(base[r] + d.off_flags);
+    }
+    double **dxf = nullptr; uint32_t **dfl = nullptr;
+    ALLOC(dxf, p.nranks); ALLOC(dfl, p.nranks);
+    CK(cudaMemcpy(dxf, xf.data(), p.nranks * sizeof(double *), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dfl, fl.data(), p.nranks * sizeof(uint32_t *), cudaMemcpyHostToDevice));
+    p.peer_xf = dxf; p.peer_flag = dfl;
+    const amc_slab_p2p_desc &me = h->p2p_desc;
+    p.flags = (const uint32_t *)(h->p2p_base + me.off_flags);
+    p.xf_recv = (const double *)(h->p2p_base + me.off_xfer);
+    p.bnd_recv[0] = (const double *)(h->p2p_base + me.off_bnd_up);
+    p.bnd_recv[1] = (const double *)(h->p2p_base + me.off_bnd_down);
+    p.peer_bnd[0] = p.srank + 1 < p.nranks ? (double *)(base[p.srank + 1] + all[p.srank + 1].off_bnd_down) : nullptr;
+    p.peer_bnd[1] = p.srank > 0 ? (double *)(base[p.srank - 1] + all[p.srank - 1].off_bnd_up) : nullptr;
+    p.xf_stride = (int32_t)me.xfer_stride; p.bnd_stride = (int32_t)me.bnd_stride;
+    h->p2p = true;
+    CK(cudaDeviceSynchronize());
+    return AMC_OK;
+}
+
+extern "C" int amc_slab_step(amc_handle *h, int32_t n_steps, int32_t pre_round, amc_step_stats *stats)
+{
+    int rc = slab_check(h);
+    if (rc != AMC_OK) return rc;
+    if (!h->p2p) return h->fail(AMC_E_STATE, "amc_slab_p2p_connect first");
+    if (n_steps < 0) return h->fail(AMC_E_INVALID, "n_steps < 0");
+    P &p = h->p;
+    const int ncell = p.nc[0] * p.nc[1] * p.nc[2];
+    const unsigned pgrid = (unsigned)std::min<int64_t>((int64_t)h->pair_grid, std::max<int64_t>(ncell / 8, 1));
+    const unsigned full = grid_for(h->cap, ADVECT_THREADS);
+    const int phase = PH_DRIFT | PH_WALLS | (p.kind != AMC_KIND_CUBE ? PH_RECAP : 0);
+    memset(h->last_ms, 0, sizeof(h->last_ms));
+    int32_t n32 = (int32_t)h->n;
+    CK(cudaMemcpyAsync(h->d_n, &n32, sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    p.n_dev = h->d_n;
+    int done = 0;
+    while (done < n_steps) {
+        const int chunk = std::min(n_steps - done, h->stats_cap);
+        if ((rc = ensure_events(h, (size_t)chunk * 4 + 1)) != AMC_OK) { p.n_dev = nullptr; return rc; }
+        while (h->det_events.size() < (size_t)chunk * 2) {
+            cudaEvent_t e;
+            CK(cudaEventCreate(&e));
+            h->det_events.push_back(e);
+        }
+        CK(cudaMemsetAsync(h->d_stats, 0, chunk * sizeof(StatsDev), h->stream));
+        CK(cudaEventRecord(h->events[0], h->stream));
+        for (int s = 0; s < chunk; s++) {
+            p.stats = h->d_stats + s;
+            p.step = h->step_index++;
+            p.xf_seq = ++h->xf_seq;
+            p.parity = (int32_t)(p.xf_seq & 1u);
+            // ---- advect (dry run) + packing, all-to-all, unpack, sort
+            CK(cudaMemsetAsync(h->d_counters, 0, (p.nranks + 8) * sizeof(int32_t), h->stream));
+            CK(cudaMemsetAsync(p.rel_id, 0xff, (size_t)p.rel_cap * sizeof(int32_t), h->stream));
+            CK(cudaMemsetAsync(p.band_count, 0, (h->n_buckets + 2) * sizeof(int32_t), h->stream));
+            CK(cudaMemsetAsync(p.rest_count, 0, (h->n_buckets + 1) * sizeof(int32_t), h->stream));
+            k_keys<true><<<full, ADVECT_THREADS, 0, h->stream>>>(p, phase);
+            CK(cudaEventRecord(h->events[4 * s + 1], h->stream));
+            if (p.nranks > 1) {
+                k_xfer_push<<<p.nranks, ADVECT_THREADS, 0, h->stream>>>(p);
+                k_xfer_unpack<<<dim3(grid_for(p.xf_cap, ADVECT_THREADS), p.nranks), ADVECT_THREADS, 0, h->stream>>>(p);
+            }
+            int m = h->n_buckets, ntiles = (m + SCAN_TILE - 1) / SCAN_TILE;
+            k_scan_tiles<<<ntiles, SCAN_THREADS, 0, h->stream>>>(p.band_count, p.rest_count, p.cell_start, h->d_tile_sums, m);
+            k_scan_sums<<<1, SCAN_THREADS, 0, h->stream>>>(h->d_tile_sums, ntiles);
+            k_scan_add<<<ntiles, SCAN_THREADS, 0, h->stream>>>(p.cell_start, h->d_tile_sums, m, 0);
+            k_scatter_advect<true><<<full, ADVECT_THREADS, 0, h->stream>>>(p, phase);
+            std::swap(p.a, p.b);
+            k_slab_set_n<<<1, 32, 0, h->stream>>>(p, 1);
+            CK(cudaEventRecord(h->events[4 * s + 2], h->stream));
+            // ---- pair pass: detection once, then the colour groups with a hand-over after each
+            p.group_done = -1;
+            if ((rc = prepare_pairs(h, h->stream)) != AMC_OK) { p.n_dev = nullptr; return rc; }
+            CK(cudaEventRecord(h->det_events[2 * s], h->stream));
+            k_detect<<<h->det_grid, DET_THREADS, 0, h->stream>>>(p);
+            CK(cudaEventRecord(h->det_events[2 * s + 1], h->stream));
+            h->last_launches += 12;
+            for (int g = pre_round ? -1 : 0; g < 8; g++) {
+                if (g >= 0) { k_pairs_group<<<pgrid, PAIR_THREADS, 0, h->stream>>>(p, g); h->last_launches += 1; }
+                p.bnd_seq = ++h->bnd_seq;
+                k_bnd_pack<<<2, ADVECT_THREADS, 0, h->stream>>>(p);
+                p.group_done = g;
+                if (p.nranks > 1) { k_bnd_apply<<<dim3(48, 2), 128, 0, h->stream>>>(p); h->last_launches += 1; }
+                h->last_launches += 1;
+            }
+            CK(cudaEventRecord(h->events[4 * s + 3], h->stream));
+            if (p.kind != AMC_KIND_CUBE) { k_recapture_list<<<148, ADVECT_THREADS, 0, h->stream>>>(p); h->last_launches += 1; }
+            k_slab_set_n<<<1, 32, 0, h->stream>>>(p, 0);
+            CK(cudaEventRecord(h->events[4 * s + 4], h->stream));
+            CK(cudaGetLastError());
+        }
+        unsigned long long ovf[4] = {0, 0, 0, 0};
+        CK(cudaMemcpyAsync(h->h_stats, h->d_stats, chunk * sizeof(StatsDev), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(ovf, h->d_slab_overflow, sizeof(ovf), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(&n32, h->d_n, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+        cudaError_t e = cudaStreamSynchronize(h->stream);
+        p.n_dev = nullptr;
+        if (e != cudaSuccess) return h->fail(AMC_E_CUDA, std::string("amc_slab_step: ") + cudaGetErrorString(e));
+        h->n = n32; p.n = n32;
+        p.n_dev = h->d_n;
+        for (int s = 0; s < chunk; s++) {
+            float ms;
+            for (int k = 0; k < 4; k++) {
+                CK(cudaEventElapsedTime(&ms, h->events[4 * s + k], h->events[4 * s + k + 1]));
+                h->last_ms[k] += ms;
+            }
+            CK(cudaEventElapsedTime(&ms, h->det_events[2 * s], h->det_events[2 * s + 1]));
+            h->last_detect_ms += ms;
+        }
+        if ((rc = slab_overflow_error(h, ovf)) != AMC_OK) { p.n_dev = nullptr; return rc; }
+        for (int s = 0; s < chunk; s++) {
+            if ((rc = check_overflow(h, h->h_stats[s])) != AMC_OK) { p.n_dev = nullptr; return rc; }
+            if (stats) stats_to_host(h, h->h_stats[s], stats + done + s);
+        }
+        done += chunk;
+    }
+    h->last_ms[4] = h->last_ms[0] + h->last_ms[1] + h->last_ms[2] + h->last_ms[3];
+    p.n_dev = nullptr;
+    p.stats = h->d_stats;
     return AMC_OK;
 }
 

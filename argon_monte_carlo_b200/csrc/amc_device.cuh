@@ -120,6 +120,7 @@ struct P {
     const double *xf_recv;
     int32_t *xf_count;        /* [nranks] */
     int32_t xf_cap;           /* largest per-peer capacity */
+    int32_t xf_cap_nb, xf_cap_far; /* capacity of the blocks exchanged with rank +-1 / with every other rank */
     const int32_t *xf_off, *xf_capv; /* [nranks] record offset / capacity of each peer's block (same layout for send and recv) */
     int32_t *n_in;            /* particles unpacked from xf_recv in this step */
     int32_t *bnd_dirty[2];    /* [0] = up, [1] = down: slots moved in the current group that the neighbour must see */
@@ -134,6 +135,19 @@ struct P {
     int32_t *n_foreign;       /* foreign copies appended after the sort */
     int32_t foreign_cap;
     int32_t group_done;       /* last finished colour group (-1 before the first) */
+    /* device-resident stepping (amc_slab_step): the particle count lives on the device, the exchange buffers of the
+       other ranks are mapped peer-to-peer and every transfer is a kernel that writes the records straight into the
+       receiver's buffer, then a sequence number into the receiver's flag word (release / acquire at system scope) */
+    int32_t *n_dev;           /* [0] particles in the arrays (null: p.n is authoritative) */
+    int32_t parity;           /* buffer half used by this step's all-to-all */
+    uint32_t xf_seq;          /* sequence number of this step's all-to-all */
+    uint32_t bnd_seq;         /* sequence number of the hand-over round being packed / applied */
+    double *const *peer_xf;   /* [nranks] base of every rank's xfer_recv (both halves); [srank] = own */
+    uint32_t *const *peer_flag; /* [nranks] base of every rank's flag words */
+    double *peer_bnd[2];      /* [0] bnd_recv_down of the rank above, [1] bnd_recv_up of the rank below (both halves) */
+    const uint32_t *flags;    /* own flag words: [0..nranks) all-to-all from rank r, [nranks] hand-over from above, [nranks+1] from below */
+    int32_t bnd_stride;       /* doubles per half of a hand-over buffer */
+    int32_t xf_stride;        /* doubles per half of xfer_recv */
     unsigned long long *slab_overflow;
     int32_t *touched;         /* slots the closing recapture of this step has to look at (touch_slot) */
     int32_t *touched_n;       /* lives behind the last band counter: cleared with them at the start of a step */
@@ -623,6 +637,25 @@ __device__ __forceinline__ int32_t rel_find(const P &p, int32_t id)
         if (k == id) return p.rel_slot[h];
         if (k == -1) return -1;
         h = (h + 1) & mask;
+    }
+}
+
+__device__ __forceinline__ int64_t cur_n(const P &p) { return p.n_dev ? (int64_t)*p.n_dev : p.n; }
+
+// flag words of the peer-to-peer exchange: the writer publishes with a release store at system scope after its data
+// stores, the reader spins with acquire loads; sequence numbers only grow (compare as signed differences)
+__device__ __forceinline__ void flag_publish(uint32_t *f, const uint32_t seq)
+{
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(seq) : "memory");
+}
+__device__ __forceinline__ void flag_wait(const uint32_t *f, const uint32_t seq)
+{
+    uint32_t v;
+    while (true) {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+        if ((int32_t)(v - seq) >= 0) break;
+        __nanosleep(64);
     }
 }
 

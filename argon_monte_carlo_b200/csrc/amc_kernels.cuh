@@ -255,7 +255,7 @@ template <bool SLAB>
 __global__ void __launch_bounds__(ADVECT_THREADS, 6) k_keys(const __grid_constant__ P p, const int phase)
 {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= p.n) return;
+    if (s >= (SLAB ? cur_n(p) : p.n)) return;
     if (SLAB && (p.a.flag[s] & AMC_FLAG_GHOST)) { // last step's copy of a neighbour's particle: drop it
         p.key[s] = p.ncell_pad + 1; p.rank[s] = ~atomicAdd(&p.rest_count[p.ncell_pad + 1], 1);
         return;
@@ -295,12 +295,13 @@ template <bool SLAB>
 __global__ void __launch_bounds__(ADVECT_THREADS, 3) k_scatter_advect(const __grid_constant__ P p, const int phase)
 {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= p.n + (SLAB ? *p.n_in : 0) || s >= p.cap) return;
+    const int64_t n0 = SLAB ? cur_n(p) : p.n;
+    if (s >= n0 + (SLAB ? *p.n_in : 0) || s >= p.cap) return;
     Part q;
     load_part(p.a, s, q);
     const int32_t id = p.a.id[s];
     const int32_t k = p.key[s], r = p.rank[s];
-    if (s < p.n && !(SLAB && (q.flag & AMC_FLAG_GHOST))) {
+    if (s < n0 && !(SLAB && (q.flag & AMC_FLAG_GHOST))) {
         q.flag &= AMC_FLAG_PATH;
         advance_particle<AMC_LIVE>(p, q, id, phase);
         if (SLAB) {
@@ -500,7 +501,7 @@ __global__ void __launch_bounds__(ADVECT_THREADS) k_recapture_list(const __grid_
     const int nt = *p.touched_n;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x, first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (nt > p.touched_cap) { /* list overflowed: everything */
-        for (int64_t s = first; s < p.n; s += stride) recapture_slot(p, s);
+        for (int64_t s = first, n = cur_n(p); s < n; s += stride) recapture_slot(p, s);
     } else {
         for (int64_t i = first; i < nt; i += stride) recapture_slot(p, p.touched[i]);
     }
@@ -1589,27 +1590,52 @@ __global__ void k_xfer_headers(const __grid_constant__ P p)
     }
 }
 
+// peer-to-peer all-to-all: block d copies this rank's records for rank d (count first) into rank d's xfer_recv and
+// then publishes the step's sequence number in rank d's flag word for this rank
+__global__ void __launch_bounds__(ADVECT_THREADS) k_xfer_push(const __grid_constant__ P p)
+{
+    const int d = blockIdx.x;
+    if (d == p.srank) return;
+    const int c = min(p.xf_count[d], p.xf_capv[d]);
+    const double *src = p.xf_send + (size_t)p.xf_off[d] * AMC_REC;
+    // where rank d keeps the block of this rank: its blocks are ordered by source rank, sized by |source - d|
+    int64_t off = 0;
+    for (int e = 0; e < p.srank; e++) off += ((e - d == 1 || d - e == 1) ? p.xf_cap_nb : p.xf_cap_far) + 1;
+    double *dst = p.peer_xf[d] + (size_t)p.parity * p.xf_stride + (size_t)off * AMC_REC;
+    for (int i = threadIdx.x; i < c * AMC_REC; i += blockDim.x) dst[AMC_REC + i] = src[AMC_REC + i];
+    if (threadIdx.x == 0) dst[0] = (double)c;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) flag_publish(p.peer_flag[d] + p.srank, p.xf_seq);
+}
+
 // unpack immigrants and ghost copies received from every rank behind the current particles
 // (slots n .. n + n_in) and give them owner keys / ranks like k_advect does
 __global__ void __launch_bounds__(ADVECT_THREADS) k_xfer_unpack(const __grid_constant__ P p)
 {
     int src = blockIdx.y;
-    const double *blk = p.xf_recv + (size_t)p.xf_off[src] * AMC_REC;
-    int cnt = (int)blk[0];
+    if (p.peer_xf) { /* peer-to-peer mode: rank `src` wrote the block itself; wait for its sequence number */
+        if (src == p.srank) return;
+        if (threadIdx.x == 0) flag_wait(p.flags + src, p.xf_seq);
+        __syncthreads();
+    }
+    const double *blk = p.xf_recv + (p.peer_xf ? (size_t)p.parity * p.xf_stride : 0) + (size_t)p.xf_off[src] * AMC_REC;
+    int cnt = (int)__ldcg(blk);
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= cnt) return;
     const double *r = blk + (size_t)(1 + j) * AMC_REC;
-    int64_t s = p.n + atomicAdd(p.n_in, 1);
+    int64_t s = cur_n(p) + atomicAdd(p.n_in, 1);
     if (s >= p.cap) { atomicAdd(p.slab_overflow + 0, 1ull); return; } /* reported by amc_slab_sort; the state is invalid afterwards */
     Part q;
-    q.x = r[0]; q.y = r[1]; q.z = r[2]; q.vx = r[3]; q.vy = r[4]; q.vz = r[5]; q.d = r[6]; q.dx = r[7]; q.dy = r[8]; q.dz = r[9];
-    q.flag = (uint32_t)r[11];
+    q.x = __ldcg(r + 0); q.y = __ldcg(r + 1); q.z = __ldcg(r + 2); q.vx = __ldcg(r + 3); q.vy = __ldcg(r + 4); q.vz = __ldcg(r + 5);
+    q.d = __ldcg(r + 6); q.dx = __ldcg(r + 7); q.dy = __ldcg(r + 8); q.dz = __ldcg(r + 9);
+    q.flag = (uint32_t)__ldcg(r + 11);
     int o[3];
     int32_t k = owner_key(p, q.x, q.y, q.z, o);
     if (!(q.flag & (AMC_FLAG_GHOST | AMC_FLAG_REL_UP)) && p.srank + 1 < p.nranks && q.z > p.up_thr && k != p.ncell_pad)
         q.flag |= AMC_FLAG_REL_UP | AMC_FLAG_LATE_UP; /* immigrant inside the band below the upper cut */
     store_part(p.a, s, q);
-    p.a.id[s] = (int32_t)r[10];
+    p.a.id[s] = (int32_t)__ldcg(r + 10);
     p.key[s] = k;
     if (k != p.ncell_pad && any_band(p, q.x, q.y, q.z, o)) p.rank[s] = atomicAdd(&p.band_count[k], 1);
     else p.rank[s] = ~atomicAdd(&p.rest_count[k], 1);
@@ -1621,8 +1647,12 @@ __global__ void __launch_bounds__(ADVECT_THREADS) k_bnd_pack(const __grid_consta
 {
     const int dir = blockIdx.x;
     const int cnt = min(p.bnd_n[dir], p.bnd_cap);
-    double *buf = p.bnd_send[dir];
+    const bool peer = p.peer_xf != nullptr;
+    const bool has_nb = dir == 0 ? p.srank + 1 < p.nranks : p.srank > 0;
+    // peer-to-peer mode: the records go straight into the neighbour's receive buffer (half = parity of the round)
+    double *buf = peer ? (has_nb ? p.peer_bnd[dir] + (size_t)(p.bnd_seq & 1u) * p.bnd_stride : nullptr) : p.bnd_send[dir];
     const Arrays &A = p.a;
+    if (buf == nullptr) { if (threadIdx.x == 0) p.bnd_n[dir] = 0; return; }
     if (threadIdx.x == 0) buf[0] = (double)cnt;
     for (int j = threadIdx.x; j < cnt; j += blockDim.x) {
         int s = p.bnd_dirty[dir][j];
@@ -1635,8 +1665,12 @@ __global__ void __launch_bounds__(ADVECT_THREADS) k_bnd_pack(const __grid_consta
         uintptr_t addr = (uintptr_t)(A.flag + s);
         atomicAnd((unsigned *)(addr & ~(uintptr_t)3), ~(bit << (8 * (addr & 3))));
     }
+    if (peer) __threadfence_system();
     __syncthreads();
-    if (threadIdx.x == 0) p.bnd_n[dir] = 0;
+    if (threadIdx.x == 0) {
+        p.bnd_n[dir] = 0;
+        if (peer) flag_publish(p.peer_flag[dir == 0 ? p.srank + 1 : p.srank - 1] + p.nranks + (dir == 0 ? 1 : 0), p.bnd_seq); /* I am "below" for the rank above */
+    }
 }
 
 // apply the update records received from one neighbour (dir 0: from the rank above, 1: from below).
@@ -1648,11 +1682,17 @@ __global__ void __launch_bounds__(128) k_bnd_apply(const __grid_constant__ P p)
     const int dir = blockIdx.y;
     if (dir == 0 ? p.srank + 1 >= p.nranks : p.srank == 0) return; /* no neighbour on that side */
     const double *buf = p.bnd_recv[dir];
-    int cnt = (int)buf[0];
+    if (p.peer_xf) { /* peer-to-peer mode: the neighbour wrote the records itself; wait for this round's sequence number */
+        buf += (size_t)(p.bnd_seq & 1u) * p.bnd_stride;
+        if (threadIdx.x == 0) flag_wait(p.flags + p.nranks + dir, p.bnd_seq);
+        __syncthreads();
+    }
+    int cnt = (int)__ldcg(buf);
+    const int64_t n_base = cur_n(p);
     for (int j = blockIdx.x; j < cnt; j += gridDim.x) {
     __syncthreads();
     const double *r = buf + (size_t)(1 + j) * AMC_REC;
-    const int32_t id = (int32_t)r[10];
+    const int32_t id = (int32_t)__ldcg(r + 10);
     const int tid = threadIdx.x;
     if (tid == 0) { s_slot = -1; s_esc = -1; }
     __syncthreads();
@@ -1661,9 +1701,9 @@ __global__ void __launch_bounds__(128) k_bnd_apply(const __grid_constant__ P p)
     const Arrays &A = p.a;
     if (tid == 0 && s_slot < 0) { // unknown here: a particle the neighbour moved into this rank's reach
         int f = atomicAdd(p.n_foreign, 1);
-        if (f >= p.foreign_cap || p.n + f >= p.cap) { atomicAdd(p.slab_overflow + 3, 1ull); s_slot = -2; }
+        if (f >= p.foreign_cap || n_base + f >= p.cap) { atomicAdd(p.slab_overflow + 3, 1ull); s_slot = -2; }
         else {
-            int s = (int)p.n + f;
+            int s = (int)n_base + f;
             s_slot = s;
             A.id[s] = id;
             A.flag[s] = (uint8_t)(AMC_FLAG_GHOST | (dir == 0 ? AMC_FLAG_REL_UP : AMC_FLAG_REL_DOWN));
@@ -1682,8 +1722,8 @@ __global__ void __launch_bounds__(128) k_bnd_apply(const __grid_constant__ P p)
     }
     __syncthreads();
     if (tid >= 32) continue; /* warp 0: lane 0 places the record, lanes 0-7 take one colour group each */
-    const double x = r[0], y = r[1], z = r[2];
-    unsigned nf = (fl & ~AMC_FLAG_PATH) | ((unsigned)r[11] & AMC_FLAG_PATH);
+    const double x = __ldcg(r + 0), y = __ldcg(r + 1), z = __ldcg(r + 2);
+    unsigned nf = (fl & ~AMC_FLAG_PATH) | ((unsigned)__ldcg(r + 11) & AMC_FLAG_PATH);
     int o[3] = {0, 0, 0};
     const int e_old = s_esc;
     int e = -1, findable = 0, ok = 1;
@@ -1692,8 +1732,8 @@ __global__ void __launch_bounds__(128) k_bnd_apply(const __grid_constant__ P p)
     if (tid == 0) {
         if (p.skey[s] != -1 || (fl & AMC_FLAG_ESC)) { ux = A.x[s]; uy = A.y[s]; uz = A.z[s]; }
         owner_key(p, ux, uy, uz, q);
-        A.x[s] = x; A.y[s] = y; A.z[s] = z; A.vx[s] = r[3]; A.vy[s] = r[4]; A.vz[s] = r[5];
-        A.d[s] = r[6]; A.dx[s] = r[7]; A.dy[s] = r[8]; A.dz[s] = r[9];
+        A.x[s] = x; A.y[s] = y; A.z[s] = z; A.vx[s] = __ldcg(r + 3); A.vy[s] = __ldcg(r + 4); A.vz[s] = __ldcg(r + 5);
+        A.d[s] = __ldcg(r + 6); A.dx[s] = __ldcg(r + 7); A.dy[s] = __ldcg(r + 8); A.dz[s] = __ldcg(r + 9);
         int32_t k = owner_key(p, x, y, z, o);
         if (e_old < 0) {
             int32_t sk = p.skey[s];
@@ -1729,6 +1769,15 @@ __global__ void __launch_bounds__(128) k_bnd_apply(const __grid_constant__ P p)
         if (dc >= 0 && dc != cc) esc_link(p, g2, dc, dx, dy, dz, -1);
     }
     }
+}
+
+// device-resident stepping: the particle count after the sort (start of the bucket of the dropped particles) and,
+// at the end of the step, the foreign copies appended by the hand-overs
+__global__ void k_slab_set_n(const __grid_constant__ P p, const int after_sort)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (after_sort) p.n_dev[0] = p.cell_start[p.ncell_pad + 1];
+    else p.n_dev[0] += min(*p.n_foreign, p.foreign_cap);
 }
 
 // compact the particles this rank owns (everything that is not a ghost copy) into the b arrays

@@ -44,6 +44,13 @@ class AmcSlabConfig(C.Structure):
                 ("bnd_recv_down", C.c_void_p)]
 
 
+class AmcSlabP2PDesc(C.Structure):
+    """struct amc_slab_p2p_desc (include/amc.h): where a rank's exchange buffers live, for its peers to map."""
+    _fields_ = [("pid", C.c_int64), ("device", C.c_int32), ("rank", C.c_int32), ("base", C.c_uint64), ("ipc", C.c_uint8 * 64),
+                ("off_flags", C.c_int64), ("off_xfer", C.c_int64), ("off_bnd_up", C.c_int64), ("off_bnd_down", C.c_int64),
+                ("xfer_stride", C.c_int64), ("bnd_stride", C.c_int64)]
+
+
 def owner_layer(z, edges):
     """Global z layer of each particle, clamped into [0, ncz-1] like the device does for routing."""
     k = np.searchsorted(edges, z, side="right") - 1
@@ -125,14 +132,22 @@ class SlabRank:
     """One rank: a libamc handle restricted to its z layers plus its exchange buffers (torch tensors)."""
 
     def __init__(self, cfg, rank, cuts, device, xfer_capacity, bnd_capacity, max_particles, seed=None, kind=None,
-                 taps=0, cheb=None, xfer_capacity_far=512, grid=None):
-        import torch
+                 taps=0, cheb=None, xfer_capacity_far=512, grid=None, p2p=False):
         self.rank, self.nranks, self.cuts = rank, len(cuts) - 1, cuts
         self.device = device
         g = grid or cfg.grid
         self.sim = amc.Simulation(cfg, kind=kind, pp_mode=amc.PP_GROUPS, device=device, seed=seed,
                                   grid=local_grid(g, cuts[rank], cuts[rank + 1]), max_particles=max_particles, taps=taps,
                                   cheb=cheb)
+        self.p2p = p2p
+        if p2p:
+            # device-resident stepping (amc_slab_step): the handle owns the exchange buffers and runs on its own stream
+            c = self._slab_config(g, cuts, rank, xfer_capacity, xfer_capacity_far, bnd_capacity)
+            self.sim._check(self.sim.lib.amc_slab_enable(self.sim.h, C.byref(c)), "amc_slab_enable")
+            self.desc = AmcSlabP2PDesc()
+            self.sim._check(self.sim.lib.amc_slab_p2p_setup(self.sim.h, C.byref(self.desc)), "amc_slab_p2p_setup")
+            return
+        import torch
         dev = torch.device("cuda", device)
         with torch.cuda.device(dev):
             z = lambda *s: torch.zeros(*s, dtype=torch.float64, device=dev)
@@ -151,6 +166,15 @@ class SlabRank:
             self.bnd_send_down = self.bnd_send_all[rank - 1] if down else spare()
             self.bnd_recv_down = self.bnd_recv_all[rank - 1] if down else spare()
             stream = torch.cuda.current_stream(dev).cuda_stream
+        c = self._slab_config(g, cuts, rank, xfer_capacity, xfer_capacity_far, bnd_capacity)
+        c.xfer_send, c.xfer_recv = self.xfer_send.data_ptr(), self.xfer_recv.data_ptr()
+        c.bnd_send_up, c.bnd_send_down = self.bnd_send_up.data_ptr(), self.bnd_send_down.data_ptr()
+        c.bnd_recv_up, c.bnd_recv_down = self.bnd_recv_up.data_ptr(), self.bnd_recv_down.data_ptr()
+        lib, h = self.sim.lib, self.sim.h
+        self.sim._check(lib.amc_set_stream(h, C.c_void_p(stream)), "amc_set_stream")
+        self.sim._check(lib.amc_slab_enable(h, C.byref(c)), "amc_slab_enable")
+
+    def _slab_config(self, g, cuts, rank, xfer_capacity, xfer_capacity_far, bnd_capacity):
         c = AmcSlabConfig()
         c.rank, c.nranks = rank, self.nranks
         self._cuts = np.ascontiguousarray(cuts, dtype=np.int32)
@@ -159,12 +183,12 @@ class SlabRank:
         c.cuts = self._cuts.ctypes.data_as(C.POINTER(C.c_int32))
         c.gncz, c.gz_edge, c.gz_lo = g.nc[2], amc._dp(self._edge), amc._dp(self._lo)
         c.xfer_capacity, c.xfer_capacity_far, c.bnd_capacity = xfer_capacity, xfer_capacity_far, bnd_capacity
-        c.xfer_send, c.xfer_recv = self.xfer_send.data_ptr(), self.xfer_recv.data_ptr()
-        c.bnd_send_up, c.bnd_send_down = self.bnd_send_up.data_ptr(), self.bnd_send_down.data_ptr()
-        c.bnd_recv_up, c.bnd_recv_down = self.bnd_recv_up.data_ptr(), self.bnd_recv_down.data_ptr()
-        lib, h = self.sim.lib, self.sim.h
-        self.sim._check(lib.amc_set_stream(h, C.c_void_p(stream)), "amc_set_stream")
-        self.sim._check(lib.amc_slab_enable(h, C.byref(c)), "amc_slab_enable")
+        return c
+
+    def connect(self, descs):
+        """descs: the AmcSlabP2PDesc of every rank, ordered by rank."""
+        arr = (AmcSlabP2PDesc * len(descs))(*descs)
+        self.sim._check(self.sim.lib.amc_slab_p2p_connect(self.sim.h, arr), "amc_slab_p2p_connect")
 
     def call(self, name, *args):
         self.sim._check(getattr(self.sim.lib, name)(self.sim.h, *args), name)
@@ -254,6 +278,12 @@ class DistTransport:
         return t.cpu().numpy()
 
 
+    def allgather_bytes(self, blob):
+        """The byte strings of all ranks, ordered by rank (used once, to exchange the peer-to-peer descriptors)."""
+        out = [None] * self.world
+        self.dist.all_gather_object(out, bytes(blob), group=self.group)
+        return out
+
     def allreduce_u64(self, values):
         """Component-wise sum mod 2^64 over all ranks (int64 adds wrap like uint64 ones)."""
         import torch
@@ -274,7 +304,7 @@ class SlabSimulation:
     (all of them with LocalTransport, exactly one with DistTransport)."""
 
     def __init__(self, cfg, nranks, z_for_cuts, transport=None, local_ranks=None, devices=None, xfer_capacity=None,
-                 bnd_capacity=2048, slack=1.35, seed=None, kind=None, taps=0, cuts=None, n_total=None, grid=None):
+                 bnd_capacity=2048, slack=1.35, seed=None, kind=None, taps=0, cuts=None, n_total=None, grid=None, p2p=False):
         """grid: cell grid to decompose (default cfg.grid); the cube stage passes a colour-group grid here
         because its own serial sweep cannot be sharded (BASELINE config 4)."""
         self.cfg, self.nranks = cfg, nranks
@@ -301,8 +331,18 @@ class SlabSimulation:
         devices = devices or [0] * len(self.local_ranks)
         self.ranks = [SlabRank(cfg, r, self.cuts, devices[i], xfer_capacity, bnd_capacity,
                                int(per_rank[r] * slack) + 2 * xfer_capacity + nranks * 512 + 16 * bnd_capacity + 4096,
-                               seed=seed, kind=kind, taps=taps, cheb=cheb, grid=g)
+                               seed=seed, kind=kind, taps=taps, cheb=cheb, grid=g, p2p=p2p)
                       for i, r in enumerate(self.local_ranks)]
+        self.p2p = p2p
+        if p2p:
+            # one rank per GPU and process: exchange the buffer descriptors once, map the peers' buffers (NVLink)
+            if len(self.ranks) != 1 or isinstance(self.transport, LocalTransport):
+                if nranks != 1:
+                    raise ValueError("p2p stepping needs one rank per process and GPU (DistTransport)")
+                self.ranks[0].connect([self.ranks[0].desc])
+            else:
+                blobs = self.transport.allgather_bytes(bytes(self.ranks[0].desc))
+                self.ranks[0].connect([AmcSlabP2PDesc.from_buffer_copy(b) for b in blobs])
         self.n_global = 0
         # the hand-over round before the first colour group is only needed if some cut is even
         self.pre_round = any(int(c) % 2 == 0 for c in self.cuts[1:-1])
@@ -354,6 +394,26 @@ class SlabSimulation:
         ids = np.ascontiguousarray(ids, dtype=np.int64)
         r.call("amc_set_ids", ids.ctypes.data_as(amc.c_int64_p))
         self.n_global = n_global if n_global is not None else self.n_global
+
+    def step_fused(self, n_steps=1, reduce=True):
+        """n_steps timesteps through amc_slab_step: everything -- migration, ghost copies, the hand-over after every
+        colour group -- is enqueued by the library and moves peer to peer; one host synchronisation per call.  Returns
+        the per-step counter dicts (summed over all ranks if reduce) ; self.phase_ms = device time of
+        [advect, exchange + sort, pair groups + hand-over, finish] summed over the steps."""
+        (r,) = self.ranks
+        st = (amc.AmcStepStats * n_steps)()
+        r.call("amc_slab_step", C.c_int32(n_steps), C.c_int32(int(self.pre_round)), st)
+        ms, _ = r.sim.last_timing()
+        self.phase_ms = np.array(ms[:4])
+        out = [s.as_dict() for s in st]
+        if reduce and not isinstance(self.transport, LocalTransport):
+            mat = np.array([np.concatenate([[float(d[k]) for k in SUM_KEYS], d["wall_hits"].astype(np.float64)]) for d in out])
+            mat = self.transport.allreduce_sum(mat)
+            for d, vec in zip(out, mat):
+                for i, k in enumerate(SUM_KEYS):
+                    d[k] = type(d[k])(vec[i]) if not isinstance(d[k], float) else float(vec[i])
+                d["wall_hits"] = vec[len(SUM_KEYS):].astype(np.int64)
+        return out
 
     def step(self, n_steps=1, reduce=True, timing=False):
         """n_steps timesteps; returns per-step counter dicts summed over this process's ranks (and over

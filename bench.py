@@ -342,20 +342,22 @@ def run_slabs(args, world, rank, local, dev, hbm_peak, peak_src, barrier, max_ov
     cuts = slab.balanced_cuts(zs, edges, world)
 
     from argon_monte_carlo_b200 import amc
+    fused = os.environ.get("AMC_SLAB_MODE", "p2p") == "p2p"     # p2p: amc_slab_step; nccl: step-wise entry points over NCCL
     sim = slab.SlabSimulation(cfg, world, zs, transport=slab.DistTransport(), local_ranks=[rank], devices=[local],
-                              cuts=cuts, n_total=cfg.num_molecules, seed=17)
+                              cuts=cuts, n_total=cfg.num_molecules, seed=17, p2p=fused)
+    step = (lambda k, timing=False: sim.step_fused(k, reduce=False)) if fused else (lambda k, timing=False: sim.step(k, reduce=False, timing=timing))
     # the gas is generated on the devices (amc_init_synthetic): particle i depends only on (seed, i), so every rank
     # makes exactly its own slab and the 1-GPU replay below makes the very same job
     sim.init_synthetic(lambda kz: init_state.pore_spec(cfg, 17, keep_z=kz))
     n = sim.particles_per_rank()[0]
     launches0 = sim.ranks[0].sim.last_timing()[1]
-    sim.step(args.warmup, reduce=False)
+    step(args.warmup)
     clocks = ClockSampler(local)
     barrier()
     clocks.start()
     det0 = sim.ranks[0].sim.last_detect_ms()
     t0 = time.perf_counter()
-    stats = sim.step(args.steps, reduce=False, timing=True)
+    stats = step(args.steps, timing=True)
     wall = time.perf_counter() - t0
     ms = sim.phase_ms
     barrier()
@@ -392,7 +394,7 @@ def run_slabs(args, world, rank, local, dev, hbm_peak, peak_src, barrier, max_ov
     for _ in range(e2e_steps):
         (oid, od), = sim.owned(out=[pinned])
         sim.set_local_state(oid, *[od[k] for k in keys], flag=od["flag"])
-        sim.step(1, reduce=False)
+        step(1)
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     barrier()
@@ -426,7 +428,10 @@ def run_slabs(args, world, rank, local, dev, hbm_peak, peak_src, barrier, max_ov
                                "%d particles = %d per GPU, device RNG, slab-decomposed along z over %d GPUs"
                                % (scale, cfg.num_molecules, args.particles_per_gpu, world),
                    "particles_total": int(total_particles), "cells": list(cfg.grid.nc), "cuts": [int(c) for c in cuts],
-                   "particles_max_per_gpu": int(n_max), "parallelism": "z slabs, NCCL all-to-all + neighbour send/recv",
+                   "particles_max_per_gpu": int(n_max),
+                   "parallelism": "z slabs; migration, ghost copies and the hand-over after every colour group written peer to peer "
+                                  "over NVLink by kernels (amc_slab_step), torch.distributed/NCCL for set-up and reductions only" if fused
+                                  else "z slabs, NCCL all-to-all + neighbour send/recv (step-wise entry points)",
                    "l2": "inputs larger than L2"},
         "clocks": clk, "e2e": e2e, "gpu_launches": int(launches_timed),
         "roofline": roofline,

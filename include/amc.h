@@ -259,6 +259,31 @@ int amc_slab_finish(amc_handle *h, amc_step_stats *stats);
 int amc_slab_get_owned(amc_handle *h, int64_t cap, int64_t *n, int64_t *ids, double *x, double *y, double *z, double *vx,
                        double *vy, double *vz, double *dist, double *dist_x, double *dist_y, double *dist_z, uint8_t *flag);
 
+/* Device-resident multi-GPU stepping (one rank per GPU, e.g. one process per GPU under torchrun).  The step-wise
+ * entry points above leave the transport to the caller (NCCL through torch.distributed) and return to the host
+ * after every phase; here the handle owns the exchange buffers, maps the other ranks' buffers peer-to-peer over
+ * NVLink (cudaIpc across processes) and amc_slab_step enqueues whole timesteps: every transfer is a kernel that
+ * writes the records straight into the receiver's buffer and then a sequence number into the receiver's flag word;
+ * the receiving kernel spins on that word.  No NCCL call, no host synchronisation and no host code between the
+ * colour groups.  Results are identical to the step-wise path and to the single-domain run.
+ *   amc_slab_enable (buffer pointers of amc_slab_config may be NULL) -> amc_slab_p2p_setup on every rank
+ *   -> exchange the descriptors between the ranks (all-gather) -> amc_slab_p2p_connect -> amc_slab_step ...
+ * Ranks that wait on one another must run on different GPUs (kernels of two ranks on one GPU are not guaranteed to
+ * run at the same time); emulated ranks on one GPU use the step-wise entry points. */
+typedef struct amc_slab_p2p_desc {
+    int64_t pid;             /* process that owns the allocation */
+    int32_t device, rank;
+    uint64_t base;           /* device address of the allocation in that process */
+    uint8_t ipc[64];         /* cudaIpcMemHandle_t of the allocation */
+    int64_t off_flags, off_xfer, off_bnd_up, off_bnd_down; /* byte offsets inside the allocation */
+    int64_t xfer_stride, bnd_stride;                       /* doubles per buffer half */
+} amc_slab_p2p_desc;
+int amc_slab_p2p_setup(amc_handle *h, amc_slab_p2p_desc *out);
+int amc_slab_p2p_connect(amc_handle *h, const amc_slab_p2p_desc *all_ranks); /* nranks descriptors, indexed by rank */
+/* n_steps whole timesteps of this rank's slab; pre_round as in amc_slab_pairs_begin (the same value on every rank).
+ * stats: n_steps entries (this rank's share of every counter) or NULL. */
+int amc_slab_step(amc_handle *h, int32_t n_steps, int32_t pre_round, amc_step_stats *stats);
+
 #ifdef __cplusplus
 }
 #endif

@@ -3,8 +3,9 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         tests/nccl_slab_worker.py OUT.json [--particles M] [--steps K] [--kind temp|pore]
 
-Every rank drives one z slab of ONE synthetic pore on its own GPU (NCCL all-to-all + neighbour hand-over,
-slab.DistTransport); rank 0 then repeats the same job as a single domain on its GPU.  Compared: the per-step
+Every rank drives one z slab of ONE synthetic pore on its own GPU -- --mode p2p: amc_slab_step, every transfer a
+kernel writing into the peer's buffer over NVLink; --mode nccl: the step-wise entry points with NCCL all-to-all +
+neighbour send/recv (slab.DistTransport) -- and rank 0 then repeats the same job as a single domain on its GPU.  Compared: the per-step
 counters (summed over ranks) and the order-independent checksum of the id-ordered state (amc_state_digest).
 Exit code 0 only if everything is identical."""
 import argparse
@@ -27,6 +28,8 @@ def main():
     ap.add_argument("--particles", type=int, default=2_000_000)
     ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--kind", default="temp", choices=["temp", "pore"])
+    ap.add_argument("--mode", default="p2p", choices=["p2p", "nccl"],
+                    help="p2p: amc_slab_step (records written peer to peer by kernels); nccl: the step-wise entry points over torch.distributed")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -40,13 +43,14 @@ def main():
     zs = init_state.synthetic_pore_chunk(cfg, 17, 0, 1 << 20)[3]
     cuts = slab.balanced_cuts(zs, edges, world)
     sim = slab.SlabSimulation(cfg, world, zs, transport=slab.DistTransport(), local_ranks=[rank], devices=[local], cuts=cuts,
-                              n_total=cfg.num_molecules, seed=17)
+                              n_total=cfg.num_molecules, seed=17, p2p=args.mode == "p2p")
     sim.init_synthetic(lambda kz: init_state.pore_spec(cfg, 17, keep_z=kz))
-    stats = sim.step(args.steps, reduce=True)
+    dist.barrier()
+    stats = sim.step_fused(args.steps, reduce=True) if args.mode == "p2p" else sim.step(args.steps, reduce=True)
     digest = sim.state_digest()
     per_rank = sim.particles_per_rank()[0]
     sim.close()
-    result = {"world": world, "particles": int(cfg.num_molecules), "steps": args.steps, "kind": args.kind,
+    result = {"world": world, "particles": int(cfg.num_molecules), "steps": args.steps, "kind": args.kind, "mode": args.mode,
               "cuts": [int(c) for c in cuts], "ok": True, "mismatch": []}
     if rank == 0:
         one = amc.Simulation(cfg, seed=17, device=local, max_particles=cfg.num_molecules)

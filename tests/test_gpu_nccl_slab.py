@@ -1,5 +1,6 @@
 """The real multi-process path on real GPUs: N processes (one per GPU, torch.distributed.run, NCCL) run one
-slab-decomposed pore and must reproduce the single-GPU run of the same job -- per-step counters and the
+slab-decomposed pore -- through amc_slab_step (peer-to-peer transfers by kernels) and through the step-wise NCCL
+path -- and must reproduce the single-GPU run of the same job: per-step counters and the
 order-independent checksum of the id-ordered state (tests/nccl_slab_worker.py).  Needs >= 2 GPUs; on a
 one-GPU box it is skipped (the device side of the protocol is then covered by tests/test_gpu_slab.py, the
 transport by tests/test_slab_transport.py).  profiles/ holds the result files of the 2/4/8-GPU runs."""
@@ -23,8 +24,8 @@ def _free_port():
     return port
 
 
-@pytest.mark.parametrize("kind", ["temp", "pore"])
-def test_nccl_ranks_match_single_gpu(tmp_path, kind):
+@pytest.mark.parametrize("kind,mode", [("temp", "p2p"), ("pore", "p2p"), ("temp", "nccl")])
+def test_nccl_ranks_match_single_gpu(tmp_path, kind, mode):
     import torch
     ngpu = torch.cuda.device_count()
     if ngpu < 2:
@@ -33,7 +34,7 @@ def test_nccl_ranks_match_single_gpu(tmp_path, kind):
     out = tmp_path / "nccl.json"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr",
            "127.0.0.1", "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "nccl_slab_worker.py"), str(out),
-           "--kind", kind, "--particles", "2000000", "--steps", "6"]
+           "--kind", kind, "--mode", mode, "--particles", "2000000", "--steps", "6"]
     r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     res = json.loads(out.read_text())

@@ -115,3 +115,24 @@ def test_cube_geometry_slabs_bit_identical():
     slabs = (sim.get_state(), stats2, sim.pair_list(), sim.histograms(), sim.cuts)
     sim.close()
     compare(single, slabs, n)
+
+
+def test_device_resident_stepping_single_rank(temp_cfg, temp_init):
+    """amc_slab_step keeps the particle count on the device and never returns to the host inside a step; with one
+    rank (no peers) it must reproduce the single-domain run exactly -- the multi-rank version of this check needs
+    one GPU per rank (tests/test_gpu_nccl_slab.py)."""
+    from argon_monte_carlo_b200 import amc, slab
+    one = amc.Simulation(temp_cfg, seed=17)
+    one.set_state(*temp_init)
+    ref = one.step(6)
+    ref_digest = one.state_digest()
+    one.close()
+    sim = slab.SlabSimulation(temp_cfg, 1, temp_init[2], seed=17, p2p=True)
+    sim.set_state(*temp_init)
+    got = sim.step_fused(3) + sim.step_fused(3)
+    for a, b in zip(ref, got):
+        for k in ("wall_collisions", "pp_collisions", "pair_checks_ref", "oob_after_walls", "oob_after_pp", "errors", "completed_paths"):
+            assert a[k] == b[k], (k, a[k], b[k])
+        assert np.array_equal(a["wall_hits"], b["wall_hits"])
+    assert sim.state_digest() == ref_digest
+    sim.close()
