@@ -960,7 +960,9 @@ extern "C" int amc_slab_enable(amc_handle *h, const amc_slab_config *c)
     p.bnd_send[0] = (double *)c->bnd_send_up; p.bnd_send[1] = (double *)c->bnd_send_down;
     p.bnd_recv[0] = (const double *)c->bnd_recv_up; p.bnd_recv[1] = (const double *)c->bnd_recv_down;
     {
-        int64_t want = std::min<int64_t>(std::max<int64_t>(h->cap / 4, 1 << 16), 1 << 25);
+        // the table only ever holds the particles next to a cut (ghost copies, particles a neighbour holds a copy of,
+        // hand-overs): a few times the per-step transfer volume, not a fraction of all particles -- it is cleared every step
+        int64_t want = std::min<int64_t>(std::max<int64_t>(8 * (2 * (int64_t)c->xfer_capacity + 16 * (int64_t)c->bnd_capacity), 1 << 16), 1 << 25);
         int32_t pow2 = 1 << 16;
         while (pow2 < want) pow2 <<= 1;
         p.rel_cap = pow2;
@@ -1097,7 +1099,7 @@ extern "C" int amc_slab_apply(amc_handle *h, int32_t group_done)
     if (rc != AMC_OK) return rc;
     P &p = h->p;
     p.group_done = group_done;
-    if (p.nranks > 1) { k_bnd_apply<<<dim3(48, 2), 128, 0, h->stream>>>(p); h->last_launches += 1; }
+    if (p.nranks > 1) { k_bnd_apply<false><<<dim3(48, 2), 128, 0, h->stream>>>(p); h->last_launches += 1; }
     CK(cudaGetLastError());
     return AMC_OK;
 }
@@ -1195,11 +1197,12 @@ extern "C" int amc_slab_p2p_connect(amc_handle *h, const amc_slab_p2p_desc *all)
     std::vector<double *> xf(p.nranks);
     std::vector<uint32_t *> fl(p.nranks);
     std::vector<char *> base(p.nranks, nullptr);
+    std::vector<int64_t> strides(p.nranks, 0);
     for (int r = 0; r < p.nranks; r++) {
         const amc_slab_p2p_desc &d = all[r];
         if (d.rank != r) return h->fail(AMC_E_INVALID, "descriptors must be ordered by rank");
-        if (d.xfer_stride != h->p2p_desc.xfer_stride || d.bnd_stride != h->p2p_desc.bnd_stride)
-            return h->fail(AMC_E_INVALID, "ranks disagree on the exchange buffer sizes");
+        if (d.bnd_stride != h->p2p_desc.bnd_stride) return h->fail(AMC_E_INVALID, "ranks disagree on bnd_capacity");
+        strides[r] = d.xfer_stride;
         if (r == p.srank) base[r] = h->p2p_base;
         else if (d.pid == (int64_t)getpid()) { /* same process: the address is valid here, the devices need peer access */
             base[r] = (char *)(uintptr_t)d.base;
@@ -1224,6 +1227,18 @@ extern "C" int amc_slab_p2p_connect(amc_handle *h, const amc_slab_p2p_desc *all)
     CK(cudaMemcpy(dxf, xf.data(), p.nranks * sizeof(double *), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dfl, fl.data(), p.nranks * sizeof(uint32_t *), cudaMemcpyHostToDevice));
     p.peer_xf = dxf; p.peer_flag = dfl;
+    {
+        int64_t *dst = nullptr, *dof = nullptr;
+        ALLOC(dst, p.nranks); ALLOC(dof, p.nranks);
+        CK(cudaMemcpy(dst, strides.data(), p.nranks * sizeof(int64_t), cudaMemcpyHostToDevice));
+        p.peer_xf_stride = dst;
+        // where rank d keeps the block of this rank: its blocks are ordered by source rank and sized by |source - d|
+        std::vector<int64_t> offs(p.nranks, 0);
+        for (int d = 0; d < p.nranks; d++)
+            for (int e = 0; e < p.srank; e++) offs[d] += (std::abs(e - d) == 1 ? p.xf_cap_nb : p.xf_cap_far) + 1;
+        CK(cudaMemcpy(dof, offs.data(), p.nranks * sizeof(int64_t), cudaMemcpyHostToDevice));
+        p.peer_xf_off = dof;
+    }
     const amc_slab_p2p_desc &me = h->p2p_desc;
     p.flags = (const uint32_t *)(h->p2p_base + me.off_flags);
     p.xf_recv = (const double *)(h->p2p_base + me.off_xfer);
@@ -1246,7 +1261,6 @@ extern "C" int amc_slab_step(amc_handle *h, int32_t n_steps, int32_t pre_round, 
     P &p = h->p;
     const int ncell = p.nc[0] * p.nc[1] * p.nc[2];
     const unsigned pgrid = (unsigned)std::min<int64_t>((int64_t)h->pair_grid, std::max<int64_t>(ncell / 8, 1));
-    const unsigned full = grid_for(h->cap, ADVECT_THREADS);
     const int phase = PH_DRIFT | PH_WALLS | (p.kind != AMC_KIND_CUBE ? PH_RECAP : 0);
     memset(h->last_ms, 0, sizeof(h->last_ms));
     int32_t n32 = (int32_t)h->n;
@@ -1254,7 +1268,10 @@ extern "C" int amc_slab_step(amc_handle *h, int32_t n_steps, int32_t pre_round, 
     p.n_dev = h->d_n;
     int done = 0;
     while (done < n_steps) {
-        const int chunk = std::min(n_steps - done, h->stats_cap);
+        const int chunk = std::min(n_steps - done, std::min(h->stats_cap, 64));
+        // the count changes by a few hundred per step (migration); the launches of this chunk cover a generous bound
+        p.n_hint = std::min<int64_t>(h->cap, h->n + h->n / 32 + 2 * (int64_t)h->xf_total + 4 * (int64_t)p.foreign_cap);
+        const unsigned full = grid_for(p.n_hint, ADVECT_THREADS);
         if ((rc = ensure_events(h, (size_t)chunk * 4 + 1)) != AMC_OK) { p.n_dev = nullptr; return rc; }
         while (h->det_events.size() < (size_t)chunk * 2) {
             cudaEvent_t e;
@@ -1276,7 +1293,7 @@ extern "C" int amc_slab_step(amc_handle *h, int32_t n_steps, int32_t pre_round, 
             k_keys<true><<<full, ADVECT_THREADS, 0, h->stream>>>(p, phase);
             CK(cudaEventRecord(h->events[4 * s + 1], h->stream));
             if (p.nranks > 1) {
-                k_xfer_push<<<p.nranks, ADVECT_THREADS, 0, h->stream>>>(p);
+                k_xfer_push<<<p.nranks, 32, 0, h->stream>>>(p);
                 k_xfer_unpack<<<dim3(grid_for(p.xf_cap, ADVECT_THREADS), p.nranks), ADVECT_THREADS, 0, h->stream>>>(p);
             }
             int m = h->n_buckets, ntiles = (m + SCAN_TILE - 1) / SCAN_TILE;
@@ -1297,9 +1314,9 @@ extern "C" int amc_slab_step(amc_handle *h, int32_t n_steps, int32_t pre_round, 
             for (int g = pre_round ? -1 : 0; g < 8; g++) {
                 if (g >= 0) { k_pairs_group<<<pgrid, PAIR_THREADS, 0, h->stream>>>(p, g); h->last_launches += 1; }
                 p.bnd_seq = ++h->bnd_seq;
-                k_bnd_pack<<<2, ADVECT_THREADS, 0, h->stream>>>(p);
                 p.group_done = g;
-                if (p.nranks > 1) { k_bnd_apply<<<dim3(48, 2), 128, 0, h->stream>>>(p); h->last_launches += 1; }
+                if (p.nranks > 1) k_bnd_apply<true><<<dim3(48, 2), 128, 0, h->stream>>>(p); /* sends, then waits for and applies the neighbours' records */
+                else k_bnd_pack<<<2, ADVECT_THREADS, 0, h->stream>>>(p);
                 h->last_launches += 1;
             }
             CK(cudaEventRecord(h->events[4 * s + 3], h->stream));

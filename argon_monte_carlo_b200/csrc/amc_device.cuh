@@ -139,10 +139,13 @@ struct P {
        other ranks are mapped peer-to-peer and every transfer is a kernel that writes the records straight into the
        receiver's buffer, then a sequence number into the receiver's flag word (release / acquire at system scope) */
     int32_t *n_dev;           /* [0] particles in the arrays (null: p.n is authoritative) */
+    int64_t n_hint;           /* host-side upper bound of the count during this call: the grids are sized by it */
     int32_t parity;           /* buffer half used by this step's all-to-all */
     uint32_t xf_seq;          /* sequence number of this step's all-to-all */
     uint32_t bnd_seq;         /* sequence number of the hand-over round being packed / applied */
     double *const *peer_xf;   /* [nranks] base of every rank's xfer_recv (both halves); [srank] = own */
+    const int64_t *peer_xf_stride; /* [nranks] doubles per half of that rank's xfer_recv (end ranks have one big block, inner ranks two) */
+    const int64_t *peer_xf_off;    /* [nranks] record offset of THIS rank's block inside that rank's xfer_recv */
     uint32_t *const *peer_flag; /* [nranks] base of every rank's flag words */
     double *peer_bnd[2];      /* [0] bnd_recv_down of the rank above, [1] bnd_recv_up of the rank below (both halves) */
     const uint32_t *flags;    /* own flag words: [0..nranks) all-to-all from rank r, [nranks] hand-over from above, [nranks+1] from below */

@@ -240,7 +240,10 @@ __device__ __noinline__ void slab_pack(const P &p, const int64_t s, const int32_
     load_part(p.a, s, q);
     q.flag &= AMC_FLAG_PATH;
     advance_particle<AMC_QUIET>(p, q, id, phase);
-    double *r = p.xf_send + ((size_t)p.xf_off[to] + 1 + j) * AMC_REC;
+    // peer-to-peer mode: the record goes straight into the receiver's buffer over NVLink (stores from all SMs side
+    // by side); k_xfer_push only adds the count and the sequence number
+    double *r = p.peer_xf ? p.peer_xf[to] + (size_t)p.parity * (size_t)p.peer_xf_stride[to] + ((size_t)p.peer_xf_off[to] + 1 + j) * AMC_REC
+                          : p.xf_send + ((size_t)p.xf_off[to] + 1 + j) * AMC_REC;
     r[0] = q.x; r[1] = q.y; r[2] = q.z; r[3] = q.vx; r[4] = q.vy; r[5] = q.vz;
     r[6] = q.d; r[7] = q.dx; r[8] = q.dy; r[9] = q.dz; r[10] = (double)id;
     r[11] = (double)((q.flag & AMC_FLAG_PATH) | extra);
@@ -249,27 +252,43 @@ __device__ __noinline__ void slab_pack(const P &p, const int64_t s, const int32_
 // pass 1 of the fused step: owner cell of the position each particle will have after the step, and its
 // rank inside that cell (band particles first, see k_advect).  Slab mode: also decides which rank owns
 // the particle after the step and packs the records that travel (see k_advect for the protocol).
+#ifndef KEYS_OCC_SLAB
+#define KEYS_OCC_SLAB 6      /* resident CTAs per SM of the slab variant of k_keys (5 at 48 registers and 4 at 64 measured slower: latency-bound) */
+#endif
 #define AUX_GHOST_UP 1u      /* kept, and copied to the rank above */
 #define AUX_STAY_AS_GHOST 2u /* owned by the rank below from now on, the local copy stays as its ghost */
 template <bool SLAB>
-__global__ void __launch_bounds__(ADVECT_THREADS, 6) k_keys(const __grid_constant__ P p, const int phase)
+__global__ void __launch_bounds__(ADVECT_THREADS, SLAB ? KEYS_OCC_SLAB : 6) k_keys(const __grid_constant__ P p, const int phase)
 {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= (SLAB ? cur_n(p) : p.n)) return;
-    if (SLAB && (p.a.flag[s] & AMC_FLAG_GHOST)) { // last step's copy of a neighbour's particle: drop it
-        p.key[s] = p.ncell_pad + 1; p.rank[s] = ~atomicAdd(&p.rest_count[p.ncell_pad + 1], 1);
-        return;
-    }
+    if (s >= (SLAB ? p.cap : p.n)) return;
+    // slab mode: the particle count lives on the device; its load travels together with the particle's own loads
+    // (slots behind the count are allocated, their contents are ignored)
     Part q;
     q.x = p.a.x[s]; q.y = p.a.y[s]; q.z = p.a.z[s]; q.vx = p.a.vx[s]; q.vy = p.a.vy[s]; q.vz = p.a.vz[s];
     q.d = q.dx = q.dy = q.dz = 0.0; q.flag = 0;
     const int32_t id = (p.kind == AMC_KIND_TEMP || SLAB) ? p.a.id[s] : 0; /* keys the device RNG of the energized walls */
-    advance_particle<AMC_DRY>(p, q, id, phase);
     if (SLAB) {
-        int gz = owner_axis(p.gz_edge, p.gncz, p.g_e0z, p.g_inv_dz, q.z);
-        int layer = gz < 0 ? 0 : (gz >= p.gncz ? p.gncz - 1 : gz);
-        int dest = 0;
-        while (dest + 1 < p.nranks && layer >= p.cuts[dest + 1]) dest++;
+        const unsigned fl0 = p.a.flag[s];
+        if (s >= cur_n(p)) return;
+        if (fl0 & AMC_FLAG_GHOST) { // last step's copy of a neighbour's particle: drop it
+            p.key[s] = p.ncell_pad + 1; p.rank[s] = ~atomicAdd(&p.rest_count[p.ncell_pad + 1], 1);
+            return;
+        }
+    }
+    advance_particle<AMC_DRY>(p, q, id, phase);
+    int o[3];
+    const int32_t k = owner_key(p, q.x, q.y, q.z, o);
+    if (SLAB) {
+        // the local z tables are a window of the global ones: only a particle outside the window (below the first
+        // local edge or not below the last) needs the global look-up to find its new rank
+        int dest = p.srank;
+        if (o[2] < 0 || o[2] >= p.nc[2]) {
+            int gz = owner_axis(p.gz_edge, p.gncz, p.g_e0z, p.g_inv_dz, q.z);
+            int layer = gz < 0 ? 0 : (gz >= p.gncz ? p.gncz - 1 : gz);
+            dest = 0;
+            while (dest + 1 < p.nranks && layer >= p.cuts[dest + 1]) dest++;
+        }
         const bool ghost_up = dest == p.srank && p.srank + 1 < p.nranks && q.z > p.up_thr;
         const bool stay_as_ghost = dest == p.srank - 1 && q.z > p.down_band;
         if (dest != p.srank) slab_pack(p, s, id, phase, dest, stay_as_ghost ? AMC_FLAG_REL_UP : 0u);
@@ -280,8 +299,6 @@ __global__ void __launch_bounds__(ADVECT_THREADS, 6) k_keys(const __grid_constan
             return;
         }
     }
-    int o[3];
-    int32_t k = owner_key(p, q.x, q.y, q.z, o);
     p.key[s] = k;
     bool band = k != p.ncell_pad && any_band(p, q.x, q.y, q.z, o);
     int r = warp_rank(band ? &p.band_count[k] : &p.rest_count[k], (k << 1) | (int)band);
@@ -295,12 +312,13 @@ template <bool SLAB>
 __global__ void __launch_bounds__(ADVECT_THREADS, 3) k_scatter_advect(const __grid_constant__ P p, const int phase)
 {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t n0 = SLAB ? cur_n(p) : p.n;
-    if (s >= n0 + (SLAB ? *p.n_in : 0) || s >= p.cap) return;
+    if (s >= (SLAB ? p.cap : p.n)) return;
     Part q;
     load_part(p.a, s, q);
     const int32_t id = p.a.id[s];
     const int32_t k = p.key[s], r = p.rank[s];
+    const int64_t n0 = SLAB ? cur_n(p) : p.n; /* slab mode: on the device, loaded together with the record */
+    if (SLAB && s >= n0 + *p.n_in) return;
     if (s < n0 && !(SLAB && (q.flag & AMC_FLAG_GHOST))) {
         q.flag &= AMC_FLAG_PATH;
         advance_particle<AMC_LIVE>(p, q, id, phase);
@@ -1590,23 +1608,18 @@ __global__ void k_xfer_headers(const __grid_constant__ P p)
     }
 }
 
-// peer-to-peer all-to-all: block d copies this rank's records for rank d (count first) into rank d's xfer_recv and
-// then publishes the step's sequence number in rank d's flag word for this rank
-__global__ void __launch_bounds__(ADVECT_THREADS) k_xfer_push(const __grid_constant__ P p)
+// peer-to-peer all-to-all: block d writes the number of records this rank has for rank d into rank d's xfer_recv
+// and then publishes the step's sequence number in rank d's flag word for this rank
+__global__ void __launch_bounds__(32) k_xfer_push(const __grid_constant__ P p)
 {
     const int d = blockIdx.x;
     if (d == p.srank) return;
+    if (threadIdx.x != 0) return;
+    // the records were written by k_keys (slab_pack); a kernel boundary lies between those stores and this release
     const int c = min(p.xf_count[d], p.xf_capv[d]);
-    const double *src = p.xf_send + (size_t)p.xf_off[d] * AMC_REC;
-    // where rank d keeps the block of this rank: its blocks are ordered by source rank, sized by |source - d|
-    int64_t off = 0;
-    for (int e = 0; e < p.srank; e++) off += ((e - d == 1 || d - e == 1) ? p.xf_cap_nb : p.xf_cap_far) + 1;
-    double *dst = p.peer_xf[d] + (size_t)p.parity * p.xf_stride + (size_t)off * AMC_REC;
-    for (int i = threadIdx.x; i < c * AMC_REC; i += blockDim.x) dst[AMC_REC + i] = src[AMC_REC + i];
-    if (threadIdx.x == 0) dst[0] = (double)c;
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) flag_publish(p.peer_flag[d] + p.srank, p.xf_seq);
+    double *dst = p.peer_xf[d] + (size_t)p.parity * (size_t)p.peer_xf_stride[d] + (size_t)p.peer_xf_off[d] * AMC_REC;
+    dst[0] = (double)c;
+    flag_publish(p.peer_flag[d] + p.srank, p.xf_seq);
 }
 
 // unpack immigrants and ghost copies received from every rank behind the current particles
@@ -1643,9 +1656,8 @@ __global__ void __launch_bounds__(ADVECT_THREADS) k_xfer_unpack(const __grid_con
 
 // after a colour group: turn the dirty slots into update records, one block per direction (up, down);
 // the block clears its queue counter when it is done
-__global__ void __launch_bounds__(ADVECT_THREADS) k_bnd_pack(const __grid_constant__ P p)
+__device__ __forceinline__ void bnd_pack_dir(const P &p, const int dir)
 {
-    const int dir = blockIdx.x;
     const int cnt = min(p.bnd_n[dir], p.bnd_cap);
     const bool peer = p.peer_xf != nullptr;
     const bool has_nb = dir == 0 ? p.srank + 1 < p.nranks : p.srank > 0;
@@ -1672,14 +1684,19 @@ __global__ void __launch_bounds__(ADVECT_THREADS) k_bnd_pack(const __grid_consta
         if (peer) flag_publish(p.peer_flag[dir == 0 ? p.srank + 1 : p.srank - 1] + p.nranks + (dir == 0 ? 1 : 0), p.bnd_seq); /* I am "below" for the rank above */
     }
 }
+__global__ void __launch_bounds__(ADVECT_THREADS) k_bnd_pack(const __grid_constant__ P p) { bnd_pack_dir(p, blockIdx.x); }
 
 // apply the update records received from one neighbour (dir 0: from the rank above, 1: from below).
 // One CTA per record: find the particle by id among the related particles, or append it as a new
 // foreign copy; then make sure the later colour groups of this pass can find it (escaped list).
+template <bool PACK>
 __global__ void __launch_bounds__(128) k_bnd_apply(const __grid_constant__ P p)
 {
     __shared__ int s_slot, s_esc;
     const int dir = blockIdx.y;
+    // peer-to-peer mode: the same launch first sends this rank's own records (block 0 of each direction) -- nothing
+    // below depends on them: a particle is moved by exactly one rank per colour group
+    if (PACK && blockIdx.x == 0) { bnd_pack_dir(p, dir); __syncthreads(); }
     if (dir == 0 ? p.srank + 1 >= p.nranks : p.srank == 0) return; /* no neighbour on that side */
     const double *buf = p.bnd_recv[dir];
     if (p.peer_xf) { /* peer-to-peer mode: the neighbour wrote the records itself; wait for this round's sequence number */
@@ -1776,8 +1793,10 @@ __global__ void __launch_bounds__(128) k_bnd_apply(const __grid_constant__ P p)
 __global__ void k_slab_set_n(const __grid_constant__ P p, const int after_sort)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    if (after_sort) p.n_dev[0] = p.cell_start[p.ncell_pad + 1];
-    else p.n_dev[0] += min(*p.n_foreign, p.foreign_cap);
+    if (after_sort) {
+        if ((int64_t)p.n_dev[0] + *p.n_in > p.n_hint) atomicAdd(p.slab_overflow + 0, 1ull); /* the grids of this call were too small */
+        p.n_dev[0] = p.cell_start[p.ncell_pad + 1];
+    } else p.n_dev[0] += min(*p.n_foreign, p.foreign_cap);
 }
 
 // compact the particles this rank owns (everything that is not a ghost copy) into the b arrays
