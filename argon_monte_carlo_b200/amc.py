@@ -90,7 +90,7 @@ EXPORTS = ("amc_create", "amc_destroy", "amc_last_error", "amc_abi_version", "am
            "amc_get_outputs_raw", "amc_set_outputs_raw", "amc_get_step_index",
            "amc_slab_enable", "amc_set_stream", "amc_set_ids", "amc_slab_advect", "amc_slab_sort", "amc_slab_pairs_begin",
            "amc_slab_group", "amc_slab_apply", "amc_slab_finish", "amc_slab_get_owned", "amc_state_digest",
-           "amc_slab_p2p_setup", "amc_slab_p2p_connect", "amc_slab_step")
+           "amc_slab_p2p_setup", "amc_slab_p2p_connect", "amc_slab_step", "amc_wall_operator", "amc_seed_relax")
 
 
 def load_library():
@@ -267,6 +267,13 @@ class Simulation:
         self._check(self.lib.amc_init_synthetic(self.h, C.byref(spec), C.byref(n)), "amc_init_synthetic")
         self.n = int(n.value)
         return self.n
+
+    def seed_relax(self, max_rounds=8):
+        """Overlap-free seeding after init_synthetic (amc_seed_relax): returns (positions re-drawn, particles still
+        overlapping a neighbour afterwards)."""
+        a, b = C.c_int64(0), C.c_int64(0)
+        self._check(self.lib.amc_seed_relax(self.h, C.c_int32(max_rounds), C.byref(a), C.byref(b)), "amc_seed_relax")
+        return int(a.value), int(b.value)
 
     def get_state(self, out=None):
         """dict of the ten float64 arrays and the uint8 flag, original particle index order.

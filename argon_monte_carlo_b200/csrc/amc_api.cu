@@ -28,6 +28,8 @@ struct amc_handle {
     uint32_t xf_seq = 0, bnd_seq = 0;
     int32_t *d_n = nullptr;          // device-resident particle count of amc_slab_step
     amc_slab_p2p_desc p2p_desc;
+    amc_init_spec init_spec;         // of the last amc_init_synthetic call (amc_seed_relax re-draws from it)
+    bool have_init_spec = false;
     int32_t *d_counters = nullptr; // slab mode: xf_count[nranks], n_in, bnd_n[2], rel_count, n_foreign, compact count
     unsigned long long *d_slab_overflow = nullptr;
     P p;                        // kernel parameter block (device pointers)
@@ -142,7 +144,7 @@ static void stats_to_host(const amc_handle *h, const StatsDev &s, amc_step_stats
 static int check_overflow(amc_handle *h, const StatsDev &s)
 {
     if (s.cell_overflow) return h->fail(AMC_E_CAPACITY, "a collision cell holds more than AMC_MAX_MEMBERS particles");
-    if (s.cand_overflow) return h->fail(AMC_E_CAPACITY, "more than AMC_MAX_CAND simultaneously overlapping pairs, or more than AMC_MV_CAP particles moved, in one cell visit");
+    if (s.cand_overflow) return h->fail(AMC_E_CAPACITY, "internal: candidate bookkeeping overflow in one cell visit");
     if (s.esc_overflow) return h->fail(AMC_E_CAPACITY, "escaped-particle list overflow");
     return AMC_OK;
 }
@@ -326,9 +328,10 @@ static int create_impl(amc_handle *h, const amc_config *cfg, int device)
         CK(cudaFuncSetAttribute(k_pairs_group, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pairs_group, PAIR_THREADS, 0));
         h->pair_grid = std::max(1, sms * std::max(per_sm, 1));
-        CK(cudaFuncSetAttribute(k_detect, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_detect, DET_THREADS, 0));
+        CK(cudaFuncSetAttribute(k_detect<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_detect<false>, DET_THREADS, 0));
         h->det_grid = std::max(1, sms * std::max(per_sm, 1));
+        ALLOC(p.mv_spill, (size_t)std::max(h->pair_grid, 1) * AMC_MAX_MEMBERS * 3);
     }
     CK(cudaDeviceSynchronize());
     return AMC_OK;
@@ -404,6 +407,8 @@ extern "C" int amc_init_synthetic(amc_handle *h, const amc_init_spec *spec, int6
     if (n > h->cap) return h->fail(AMC_E_CAPACITY, "max_particles too small for the particles of this slab");
     h->n = n;
     h->p.n = n;
+    h->init_spec = *spec;
+    h->have_init_spec = keep_all;
     if (n_kept) *n_kept = n;
     return AMC_OK;
 }
@@ -481,7 +486,7 @@ static int run_pairs(amc_handle *h, int64_t *launches, bool prepared = false)
         }
         int ncell = p.nc[0] * p.nc[1] * p.nc[2];
         if (h->det_slot >= 0) CK(cudaEventRecord(h->det_events[2 * h->det_slot], h->stream));
-        k_detect<<<h->det_grid, DET_THREADS, 0, h->stream>>>(p);
+        k_detect<false><<<h->det_grid, DET_THREADS, 0, h->stream>>>(p);
         if (h->det_slot >= 0) CK(cudaEventRecord(h->det_events[2 * h->det_slot + 1], h->stream));
         unsigned grid = (unsigned)std::min<int64_t>((int64_t)h->pair_grid, std::max<int64_t>(ncell / 8, 1));
         for (int g = 0; g < 8; g++) k_pairs_group<<<grid, PAIR_THREADS, 0, h->stream>>>(p, g);
@@ -680,6 +685,63 @@ extern "C" int amc_pairs(amc_handle *h, amc_step_stats *stats)
         if ((rc = run_pairs(h, nullptr)) != AMC_OK) return rc;
     }
     return phase_end(h, stats);
+}
+
+// Overlap-free seeding: the reference's random initial state leaves ~0.2 % of the particles
+// overlapping a neighbour (1,051 pairs at 557,649 particles, Open_Air_Pore_MC.py:106-158), which the first timesteps
+// resolve as a burst of unphysical collisions.  Each round sorts the particles into cells, runs the detection pass in
+// seed mode (exact overlap test on the pairs its filter finds; the particle with the higher index of every
+// overlapping pair is marked) and gives the marked particles a fresh position from the same generator.
+extern "C" int amc_seed_relax(amc_handle *h, int32_t max_rounds, int64_t *n_redrawn, int64_t *n_left)
+{
+    if (!h) return AMC_E_INVALID;
+    if (!h->have_init_spec) return h->fail(AMC_E_STATE, "amc_seed_relax follows amc_init_synthetic on a single-domain handle");
+    if (h->slab || h->cfg.pp_mode != AMC_PP_GROUPS) return h->fail(AMC_E_STATE, "amc_seed_relax needs a single-domain handle with the colour-group schedule");
+    P &p = h->p;
+    int64_t total = 0, left = 0;
+    for (int round = 0; round <= max_rounds; round++) { /* the last round only counts */
+        int rc = phase_begin(h);
+        if (rc != AMC_OK) return rc;
+        if (h->n == 0) break;
+        CK(cudaMemsetAsync(p.band_count, 0, (h->n_buckets + 2) * sizeof(int32_t), h->stream));
+        CK(cudaMemsetAsync(p.rest_count, 0, (h->n_buckets + 1) * sizeof(int32_t), h->stream));
+        k_advect<<<grid_for(h->n, ADVECT_THREADS), ADVECT_THREADS, 0, h->stream>>>(p, PH_KEYS);
+        if ((rc = sort_scatter(h, nullptr)) != AMC_OK) return rc;
+        if ((rc = prepare_pairs(h, h->stream)) != AMC_OK) return rc;
+        CK(cudaMemsetAsync(p.rank, 0, h->n * sizeof(int32_t), h->stream));
+        k_detect<true><<<h->det_grid, DET_THREADS, 0, h->stream>>>(p);
+        if (round < max_rounds) k_seed_redraw<<<grid_for(h->n, ADVECT_THREADS), ADVECT_THREADS, 0, h->stream>>>(p, h->init_spec, (uint32_t)(round + 1));
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(h->h_stats, h->d_stats, sizeof(StatsDev), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        left = (int64_t)h->h_stats[0].pp;
+        if (left == 0 || round == max_rounds) break;
+        total += left;
+    }
+    // worklists built by the seed-mode passes are reset by the next pair pass (prepare_pairs)
+    if (n_redrawn) *n_redrawn = total;
+    if (n_left) *n_left = left;
+    return AMC_OK;
+}
+
+extern "C" int amc_wall_operator(amc_handle *h, int32_t op, const uint8_t *mask, double param, int64_t *n_hits, int64_t *errors)
+{
+    if (!h) return AMC_E_INVALID;
+    if (op < AMC_OP_PLANE_MFP || op > AMC_OP_SIDE_SPECULAR) return h->fail(AMC_E_INVALID, "unknown wall operator");
+    if (h->n && !mask) return h->fail(AMC_E_INVALID, "null mask");
+    if (h->slab) return h->fail(AMC_E_STATE, "operator-level entry points work on single-domain handles");
+    int rc = phase_begin(h);
+    if (rc != AMC_OK) return rc;
+    if (h->n) {
+        uint8_t *dm = reinterpret_cast<uint8_t *>(h->p.key); /* scratch until the next sort: n bytes of the n-int key array */
+        CK(cudaMemcpyAsync(dm, mask, h->n, cudaMemcpyHostToDevice, h->stream));
+        k_wall_operator<<<grid_for(h->n, ADVECT_THREADS), ADVECT_THREADS, 0, h->stream>>>(h->p, op, dm, param);
+    }
+    amc_step_stats st;
+    rc = phase_end(h, &st);
+    if (n_hits) *n_hits = st.wall_hits[0];
+    if (errors) *errors = st.errors;
+    return rc;
 }
 
 // ---- host-RNG parity hooks ----------------------------------------------------------------------
@@ -1069,7 +1131,7 @@ extern "C" int amc_slab_pairs_begin(amc_handle *h, int32_t pre_round)
         for (int k = 0; k < 2; k++) { cudaEvent_t e; CK(cudaEventCreate(&e)); h->det_events.push_back(e); }
     }
     CK(cudaEventRecord(h->det_events[0], h->stream));
-    if (h->n) k_detect<<<h->det_grid, DET_THREADS, 0, h->stream>>>(p);
+    if (h->n) k_detect<false><<<h->det_grid, DET_THREADS, 0, h->stream>>>(p);
     CK(cudaEventRecord(h->det_events[1], h->stream));
     h->slab_det_pending = true;
     if (pre_round) k_bnd_pack<<<2, ADVECT_THREADS, 0, h->stream>>>(p); // immigrants that landed in the top band; else they travel after group 0
@@ -1308,7 +1370,7 @@ extern "C" int amc_slab_step(amc_handle *h, int32_t n_steps, int32_t pre_round, 
             p.group_done = -1;
             if ((rc = prepare_pairs(h, h->stream)) != AMC_OK) { p.n_dev = nullptr; return rc; }
             CK(cudaEventRecord(h->det_events[2 * s], h->stream));
-            k_detect<<<h->det_grid, DET_THREADS, 0, h->stream>>>(p);
+            k_detect<false><<<h->det_grid, DET_THREADS, 0, h->stream>>>(p);
             CK(cudaEventRecord(h->det_events[2 * s + 1], h->stream));
             h->last_launches += 12;
             for (int g = pre_round ? -1 : 0; g < 8; g++) {

@@ -103,6 +103,7 @@ struct P {
     int32_t *cell_n;      /* [8][wl_stride] members counted by the detection pass for cells it did not flag (0 otherwise) */
     float det_thr;        /* fp32 squared distance below which the detection pass treats a pair as overlapping (conservative) */
     float det_w;          /* minimal bin width of the detection pass: 1.05 * sqrt(det_thr) */
+    double *mv_spill;     /* [CTAs of the pair kernel][AMC_MAX_MEMBERS][3]: pre-visit positions of moved members beyond AMC_MV_CAP */
     int32_t det_own_is_member; /* lo[k] < edge[k] everywhere: a particle of owner cell k is a member of reference cell k */
     int32_t *cell_active; /* [8][wl_stride] 0: not on its group's worklist, 1: on it, e + 2: on it and escaped entry e heads its list (esc_link) */
     int32_t wl_stride;    /* reference cells per colour group */

@@ -551,6 +551,8 @@ struct CellShared {
     unsigned long long cand_key[AMC_MAX_CAND];
     int32_t cand_ab[AMC_MAX_CAND]; /* a | b << 16 */
     int n, ncand, sel, done;
+    int cand_lost;               /* the candidate list overflowed in this visit: every pick re-scans all pairs (slow, exact) */
+    unsigned long long best_key; /* scan mode: smallest pair key above the cursor that overlaps */
     unsigned long long cursor;
     int moved_a, moved_b;
     int kx, ky, kz; /* 0-based cell indices of this visit (colour-group mode) */
@@ -561,7 +563,7 @@ struct CellShared {
     /* neighbour search: members chained per slab along x (>= 1.05 filter radii wide) */
     int head[AMC_XBINS + 2];     /* last member hashed into the slab (index + 1), 0 = empty; zero on entry of cell_process */
     uint16_t nxt[AMC_MAX_MEMBERS];
-    uint8_t mv[AMC_MAX_MEMBERS];      /* 0, or 1 + index of the member's pre-visit position in ox/oy/oz (moved by a collision of this visit) */
+    uint16_t mv[AMC_MAX_MEMBERS];     /* 0, or 1 + index of the member's pre-visit position in ox/oy/oz (beyond AMC_MV_CAP: in P::mv_spill) */
     uint16_t mvlist[AMC_MAX_MEMBERS]; /* the moved members, compacted at the end of the visit */
     double ox[AMC_MV_CAP], oy[AMC_MV_CAP], oz[AMC_MV_CAP];
     int nmv, nold;
@@ -589,7 +591,7 @@ __device__ __forceinline__ void push_cand(CellShared &S, const P &p, int a, int 
 {
     int k = atomicAdd(&S.ncand, 1);
     if (k < AMC_MAX_CAND) { S.cand_key[k] = pair_key(S.id[a], S.id[b]); S.cand_ab[k] = a | (b << 16); }
-    else atomicAdd(&p.stats->cand_overflow, 1ull);
+    else S.cand_lost = 1; /* more overlapping pairs at once than the list holds: the visit switches to scan mode */
     // the resolution will read the velocity / path records of both particles: start them on their way from HBM
     for (int w = 0; w < 2; w++) {
         int s = S.slot[w ? b : a];
@@ -756,8 +758,9 @@ __device__ __forceinline__ void resolve_pair(const P &p, CellShared &S, int m1, 
     }
     if (lane < 2 && S.mv[mo] == 0) { /* the later colour groups learn about the move when the visit is over (activate_moved) */
         int i = atomicAdd(&S.nold, 1);
-        if (i < AMC_MV_CAP) { S.ox[i] = oldx; S.oy[i] = oldy; S.oz[i] = oldz; S.mv[mo] = (uint8_t)(i + 1); }
-        else atomicAdd(&p.stats->cand_overflow, 1ull);
+        if (i < AMC_MV_CAP) { S.ox[i] = oldx; S.oy[i] = oldy; S.oz[i] = oldz; }
+        else { double *sp = p.mv_spill + ((size_t)blockIdx.x * AMC_MAX_MEMBERS + i) * 3; sp[0] = oldx; sp[1] = oldy; sp[2] = oldz; }
+        S.mv[mo] = (uint16_t)(i + 1);
     }
     if (lane < 2) A.flag[so] = (uint8_t)of;
     __syncwarp();
@@ -787,7 +790,8 @@ __device__ __forceinline__ void activate_moved(const P &p, CellShared &S, const 
             const int m = S.mvlist[base + pw];
             x = S.x[m]; y = S.y[m]; z = S.z[m];
             const int io = S.mv[m] - 1;
-            ux = S.ox[io]; uy = S.oy[io]; uz = S.oz[io];
+            if (io < AMC_MV_CAP) { ux = S.ox[io]; uy = S.oy[io]; uz = S.oz[io]; }
+            else { const double *sp = p.mv_spill + ((size_t)blockIdx.x * AMC_MAX_MEMBERS + io) * 3; ux = sp[0]; uy = sp[1]; uz = sp[2]; }
             if ((lane & 7) == 0 && lane < 16) { /* lanes 0 and 8: one per particle */
                 const int so = S.slot[m];
                 int32_t k = owner_key(p, x, y, z, o);
@@ -829,6 +833,23 @@ __device__ __forceinline__ void activate_moved(const P &p, CellShared &S, const 
             if (dc >= 0 && dc != cc) esc_link(p, g2, dc, dx, dy, dz, -1);
         }
     }
+}
+
+// scan mode of cell_process (kept out of line: rare, and it must not weigh on the register budget of the normal visit):
+// smallest pair key above `cur` among the overlapping pairs whose higher-index member this thread owns
+__device__ __noinline__ unsigned long long scan_min_key(const P &p, const CellShared &S, const int n, const unsigned long long cur)
+{
+    unsigned long long mine = ~0ull;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double xi = S.x[i], yi = S.y[i], zi = S.z[i];
+        const int32_t idi = S.id[i];
+        for (int j = 0; j < n; j++) {
+            if (S.id[j] >= idi) continue; /* each unordered pair once, from its higher-index member */
+            const unsigned long long key = pair_key(idi, S.id[j]);
+            if (key > cur && key < mine && overlap(p, xi, yi, zi, S.x[j], S.y[j], S.z[j])) mine = key;
+        }
+    }
+    return mine;
 }
 
 // members are in S.{x,y,z,id,slot,src}[0..S.n); all threads of the block call this
@@ -931,6 +952,30 @@ __device__ __forceinline__ void cell_process(const P &p, CellShared &S, int grou
     if (tid == 0) { S.cursor = 0; S.done = 0; if (S.ncand > AMC_MAX_CAND) S.ncand = AMC_MAX_CAND; }
     __syncthreads();
     while (true) {
+        if (S.cand_lost) {
+            // Scan mode: more pairs overlapped at once than the candidate list holds (a cell far denser than the gas
+            // this code is tuned for).  Every pick is a search over all member pairs for the smallest key above the
+            // cursor that overlaps right now -- the reference's own sweep order, at O(n^2 / threads) per collision.
+            if (tid == 0) S.best_key = ~0ull;
+            __syncthreads();
+            const unsigned long long mine = scan_min_key(p, S, n, S.cursor);
+            if (tid == 0) atomicAdd(&S.nexec, (unsigned int)min((long long)n * (n - 1) / 2, 0x7fffffffLL));
+            if (mine != ~0ull) atomicMin(&S.best_key, mine);
+            __syncthreads();
+            const unsigned long long bk = S.best_key;
+            if (bk == ~0ull) break;
+            for (int k = tid; k < n; k += nthreads) {
+                if ((uint32_t)S.id[k] == (uint32_t)(bk >> 32)) S.moved_b = k;      /* higher index: the reference's particle 2 */
+                if ((uint32_t)S.id[k] == (uint32_t)(bk & 0xffffffffull)) S.moved_a = k;
+            }
+            __syncthreads();
+            if (warp == 0) {
+                resolve_pair(p, S, S.moved_a, S.moved_b, group, cell);
+                if (lane == 0) S.cursor = bk;
+            }
+            __syncthreads();
+            continue;
+        }
         if (warp == 0) { /* warp-uniform: every lane scans the (few) candidates itself */
             int best = -1;
             unsigned long long bk = ~0ull;
@@ -1087,6 +1132,35 @@ __device__ __forceinline__ int det_slot(const DetShared &S, int buf, int t)
     return S.rbeg[buf][nb] + (t - S.rcum[buf][nb]);
 }
 
+// Overlap-free seeding (amc_seed_relax), both out of line: the detection pass of a timestep never gets here.
+// A pair that passed the fp32 filter: exact test (Pore:173-174); the particle with the higher index is marked.
+__device__ __noinline__ void det_seed_mark(const P &p, const int sa, const int sb)
+{
+    const Arrays &A = p.a;
+    if (overlap(p, A.x[sa], A.y[sa], A.z[sa], A.x[sb], A.y[sb], A.z[sb]))
+        if (atomicExch(&p.rank[A.id[sa] > A.id[sb] ? sa : sb], 1) == 0) atomicAdd(&p.stats->pp, 1ull);
+}
+// A cell with more candidates than the table holds is searched pair by pair on the fp64 positions (one-time work at
+// initialisation; the timestep leaves such cells to the ordered resolution).
+__device__ __noinline__ void det_seed_big_cell(const P &p, const DetShared &S, const int cur, const int total)
+{
+    const Arrays &A = p.a;
+    const double *bd = reinterpret_cast<const double *>(&S.hdr[cur][20]);
+    for (int i = threadIdx.x; i < total; i += DET_THREADS) {
+        const int si = det_slot(S, cur, i);
+        const double xi = A.x[si], yi = A.y[si], zi = A.z[si];
+        if (!(bd[0] < xi && xi < bd[1] && bd[2] < yi && yi < bd[3] && bd[4] < zi && zi < bd[5])) continue;
+        for (int j = 0; j < i; j++) {
+            const int sj = det_slot(S, cur, j);
+            const double xj = A.x[sj], yj = A.y[sj], zj = A.z[sj];
+            if (!(bd[0] < xj && xj < bd[1] && bd[2] < yj && yj < bd[3] && bd[4] < zj && zj < bd[5])) continue;
+            if (overlap(p, xi, yi, zi, xj, yj, zj))
+                if (atomicExch(&p.rank[A.id[si] > A.id[sj] ? si : sj], 1) == 0) atomicAdd(&p.stats->pp, 1ull);
+        }
+    }
+}
+
+template <bool SEED> /* SEED: the marking variant of amc_seed_relax; the detection pass of a timestep is k_detect<false> */
 __global__ void __launch_bounds__(DET_THREADS, DET_OCC) k_detect(const __grid_constant__ P p)
 {
     __shared__ DetShared S;
@@ -1131,6 +1205,7 @@ __global__ void __launch_bounds__(DET_THREADS, DET_OCC) k_detect(const __grid_co
         // ---- hash the members of the current cell
         const int total = S.rcum[cur][8];
         bool hit = total > DET_CAND;
+        if (SEED && hit) det_seed_big_cell(p, S, cur, total);
         float fx[DET_K], fy[DET_K], fz[DET_K];
         int bin[DET_K], older[DET_K];
         {
@@ -1224,6 +1299,7 @@ __global__ void __launch_bounds__(DET_THREADS, DET_OCC) k_detect(const __grid_co
                     if (fmaf(ez, ez, fmaf(ey, ey, ex * ex)) < thr) {
                         const int hh = atomicAdd(&S.nhit[cur], 1);
                         if (hh < AMC_MAX_HITS) S.hit[cur][hh] = ((unsigned int)(tid + k * DET_THREADS) << 16) | (e - 1);
+                        if (SEED) det_seed_mark(p, det_slot(S, cur, tid + k * DET_THREADS), det_slot(S, cur, (int)e - 1));
                     }
                     e = S.next[e - 1];
                 }
@@ -1375,7 +1451,7 @@ __global__ void __launch_bounds__(PAIR_THREADS, 6) k_pairs_group(const __grid_co
                     int nb = (int)fminf((float)AMC_XBINS, floorf(wd / p.det_w));
                     if (nb < 1) nb = 1;
                     S.nb = nb; S.inv_w = (float)nb / wd;
-                    S.rcum[0] = 0; S.n = 0; S.ncand = 0; S.kx = s_hdr[1]; S.ky = s_hdr[2]; S.kz = s_hdr[3];
+                    S.rcum[0] = 0; S.n = 0; S.ncand = 0; S.cand_lost = 0; S.kx = s_hdr[1]; S.ky = s_hdr[2]; S.kz = s_hdr[3];
                 }
             }
         }
@@ -1452,7 +1528,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_cube_sweep(const __grid_const
             __syncthreads();
             for (int zl = 0; zl < p.nc[2]; zl++) {
                 if (tid == 0) {
-                    S.n = 0; S.ncand = 0; S.use_hits = 0; S.org[0] = p.lo[0][xl]; S.org[1] = p.lo[1][yl]; S.org[2] = p.lo[2][zl];
+                    S.n = 0; S.ncand = 0; S.cand_lost = 0; S.use_hits = 0; S.org[0] = p.lo[0][xl]; S.org[1] = p.lo[1][yl]; S.org[2] = p.lo[2][zl];
                     float wd = (float)(p.edge[0][xl + 1] - p.lo[0][xl]);
                     int nb = (int)fminf((float)AMC_XBINS, floorf(wd / p.det_w));
                     if (nb < 1) nb = 1;
@@ -1543,31 +1619,82 @@ __global__ void __launch_bounds__(ADVECT_THREADS) k_case_apply(const __grid_cons
     out_dpz[k] = dpz; out_de[k] = c == AMC_CASE_4 ? 0.0 : dE;
     store_part(p.a, s, q);
 }
+// operator-level entry point (amc_wall_operator): one wall operator of the reference applied to the particles an
+// N-long boolean mask selects, exactly as the reference functions take it (Pore:257-348, Temp:311-347)
+__global__ void __launch_bounds__(ADVECT_THREADS) k_wall_operator(const __grid_constant__ P p, const int op, const uint8_t *mask, const double param)
+{
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= p.n) return;
+    if (!mask[p.a.id[s]]) return;
+    Part q;
+    load_part(p.a, s, q);
+    q.px = q.x; q.py = q.y; q.pz = q.z;
+    switch (op) {
+    case AMC_OP_PLANE_MFP: pore_plane_wall<AMC_LIVE>(p, q, param); break;  /* hit_vertical_wall, Pore:257-292 */
+    case AMC_OP_SIDE_MFP: pore_side_wall<AMC_LIVE>(p, q, param); break;    /* hit_cylinder_side_wall, Pore:294-348 */
+    case AMC_OP_PLANE_SPECULAR: {                                          /* hit_vertical_specular_wall, Temp:311-315 */
+        double t = (q.z - param) / q.vz;
+        q.vz = -q.vz;
+        q.z = param + t * q.vz;
+        break;
+    }
+    case AMC_OP_SIDE_SPECULAR: {                                           /* hit_cylinder_specular_side_wall, Temp:317-347 */
+        double t;
+        if (!side_quadratic(q.x, q.y, q.vx, q.vy, param, t)) { atomicAdd(&p.stats->errors, 1ull); return; }
+        reflect_xy(q, param, t);
+        break;
+    }
+    }
+    atomicAdd(&p.stats->wall_hits[0], 1ull);
+    store_part(p.a, s, q);
+}
+
 // synthetic Maxwellian state (amc_init_synthetic): one thread per global particle index, grid-stride
+// position of synthetic particle i: region by cumulative weight, uniform inside it.  attempt 0 = the draw of
+// amc_init_synthetic; amc_seed_relax re-draws overlapping particles with attempt 1, 2, ...
+__device__ __forceinline__ void synthetic_position(const amc_init_spec &sp, const int64_t i, const uint32_t attempt, const double u[4],
+                                                   double &x, double &y, double &z)
+{
+    int reg = 0;
+    while (reg + 1 < sp.n_regions && u[0] >= sp.cum_weight[reg]) reg++;
+    if (sp.shape == 0) {
+        double rr = sp.radius[reg] * sqrt(u[1]), s, c;
+        sincos(6.283185307179586 * u[2], &s, &c);
+        x = rr * c; y = rr * s;
+    } else {
+        x = sp.bx[reg] * u[1]; y = sp.by[reg] * u[2];
+    }
+    z = sp.z_lo[reg] + (sp.z_hi[reg] - sp.z_lo[reg]) * u[3];
+}
+__device__ __forceinline__ void synthetic_uniforms(const amc_init_spec &sp, const int64_t i, const uint32_t attempt, const int c0, const int nc, double *u)
+{
+    const uint32_t k0 = (uint32_t)sp.seed, k1 = (uint32_t)(sp.seed >> 32);
+    for (int c = 0; c < nc; c++) {
+        uint32_t r[4] = {(uint32_t)i, (uint32_t)((uint64_t)i >> 32), 0x1417u + (attempt << 16), (uint32_t)(c0 + c)};
+        philox4x32_10(r, k0, k1);
+        u[2 * c] = u53(r[0], r[1]); u[2 * c + 1] = u53(r[2], r[3]);
+    }
+}
+// amc_seed_relax: new positions for the particles the detection pass marked (rank[slot] = 1)
+__global__ void __launch_bounds__(ADVECT_THREADS) k_seed_redraw(const __grid_constant__ P p, const __grid_constant__ amc_init_spec sp, const uint32_t attempt)
+{
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= p.n || p.rank[s] != 1) return;
+    double u[4], x, y, z;
+    synthetic_uniforms(sp, p.a.id[s], attempt, 0, 2, u);
+    synthetic_position(sp, p.a.id[s], attempt, u, x, y, z);
+    p.a.x[s] = x; p.a.y[s] = y; p.a.z[s] = z;
+}
+
 __global__ void __launch_bounds__(ADVECT_THREADS) k_init_synthetic(const __grid_constant__ P p, const __grid_constant__ amc_init_spec sp,
                                                                    const int keep_all, int32_t *count, const int64_t cap)
 {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    const uint32_t k0 = (uint32_t)sp.seed, k1 = (uint32_t)(sp.seed >> 32);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < sp.n_total; i += stride) {
         double u[8];
-#pragma unroll
-        for (int c = 0; c < 4; c++) {
-            uint32_t r[4] = {(uint32_t)i, (uint32_t)((uint64_t)i >> 32), 0x1417u, (uint32_t)c};
-            philox4x32_10(r, k0, k1);
-            u[2 * c] = u53(r[0], r[1]); u[2 * c + 1] = u53(r[2], r[3]);
-        }
-        int reg = 0;
-        while (reg + 1 < sp.n_regions && u[0] >= sp.cum_weight[reg]) reg++;
-        double x, y;
-        if (sp.shape == 0) {
-            double rr = sp.radius[reg] * sqrt(u[1]), s, c;
-            sincos(6.283185307179586 * u[2], &s, &c);
-            x = rr * c; y = rr * s;
-        } else {
-            x = sp.bx[reg] * u[1]; y = sp.by[reg] * u[2];
-        }
-        const double z = sp.z_lo[reg] + (sp.z_hi[reg] - sp.z_lo[reg]) * u[3];
+        synthetic_uniforms(sp, i, 0u, 0, 4, u);
+        double x, y, z;
+        synthetic_position(sp, i, 0u, u, x, y, z);
         if (!keep_all && !(z >= sp.keep_z_lo && z < sp.keep_z_hi)) continue;
         double s1, c1, s2, c2;
         const double r1 = sp.sigma * sqrt(-2.0 * log(1.0 - u[4])), r2 = sp.sigma * sqrt(-2.0 * log(1.0 - u[6]));

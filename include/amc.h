@@ -146,6 +146,18 @@ int amc_walls(amc_handle *h, amc_step_stats *stats);
 int amc_recapture(amc_handle *h, int64_t *count, int64_t *count_after);
 int amc_pairs(amc_handle *h, amc_step_stats *stats);
 
+/* operator-level entry point: ONE wall operator of the reference applied to the particles selected by an N-long
+ * boolean mask (indexed by particle), the way the reference's functions are called:
+ *   AMC_OP_PLANE_MFP       hit_vertical_wall(hits, z_plane, 4 lists)              Open_Air_Pore_MC.py:257-292
+ *   AMC_OP_SIDE_MFP        hit_cylinder_side_wall(hits, collision_radius, ...)    Open_Air_Pore_MC.py:294-348
+ *   AMC_OP_PLANE_SPECULAR  hit_vertical_specular_wall(hits, z_plane)              Temperature_Pore_MC.py:311-315
+ *   AMC_OP_SIDE_SPECULAR   hit_cylinder_specular_side_wall(hits, R, total_errs)   Temperature_Pore_MC.py:317-347
+ * param = z_plane or collision_radius.  *n_hits = particles processed, *errors = floating-point error path taken
+ * (the reference's try/except).  Completed free paths go to the handle's histograms / AMC_TAP_PATHS as usual.
+ * (The energized operators Temp:349-553 are reached through amc_wall_hits_pending / amc_wall_apply_directions.) */
+enum { AMC_OP_PLANE_MFP = 0, AMC_OP_SIDE_MFP = 1, AMC_OP_PLANE_SPECULAR = 2, AMC_OP_SIDE_SPECULAR = 3 };
+int amc_wall_operator(amc_handle *h, int32_t op, const uint8_t *mask, double param, int64_t *n_hits, int64_t *errors);
+
 /* parity hooks for the energized walls (AMC_KIND_TEMP): one wall case at a time, in AMC_CASE_*
  * order, after amc_drift.  Specular cases (AMC_CASE_1, _2A, _2B): call amc_wall_case.
  * Energized cases: amc_wall_hits_pending reports the hits in ascending particle index with the
@@ -182,6 +194,14 @@ typedef struct amc_init_spec {
     double keep_z_lo, keep_z_hi;
 } amc_init_spec;
 int amc_init_synthetic(amc_handle *h, const amc_init_spec *spec, int64_t *n_kept);
+
+/* Overlap-free seeding for the state amc_init_synthetic just generated on a single-domain handle: the reference's own
+ * random initial state leaves ~0.2 % of the particles overlapping a neighbour (1,051 pairs at 557,649 particles,
+ * Pore:106-158) and resolves them as a transient burst of collisions in the first timesteps.  Up to max_rounds times:
+ * find every overlapping pair (the detection pass of the step, exact test Pore:173-174), re-draw the position of its
+ * higher-index particle from the same generator (attempt counter in the Philox counter).  *n_redrawn = positions
+ * re-drawn in total, *n_left = particles still marked after the last round (0 = no overlapping pair left). */
+int amc_seed_relax(amc_handle *h, int32_t max_rounds, int64_t *n_redrawn, int64_t *n_left);
 
 /* outputs: completed free paths (the four lists Pore:410-413) as device-side histograms with
  * np.histogram's uniform-bin rule (Pore:575-596), their count and sums (for the printed means

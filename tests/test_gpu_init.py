@@ -76,3 +76,35 @@ def test_cube_spec_and_bad_arguments(cube_cfg):
     with pytest.raises(amc.AmcError):
         sim.init_synthetic(spec)
     sim.close()
+
+
+def test_overlap_free_seeding(oracle):
+    """amc_seed_relax: the synthetic state starts with ~0.2 % of its particles overlapping a neighbour, like the
+    reference's own (1,051 pairs at 557,649 particles); after relaxing, a census with a KD-tree finds no pair closer
+    than the collision range, untouched particles keep their positions, velocities are untouched, and the first
+    timestep resolves (almost) no particle-particle collision instead of the initial burst."""
+    from scipy.spatial import cKDTree
+    from argon_monte_carlo_b200 import amc, config, init_state
+    cfg = config.pore_config(True)
+    n = cfg.num_molecules
+    sim = amc.Simulation(cfg, seed=17, max_particles=n)
+    sim.init_synthetic(init_state.pore_spec(cfg, 17))
+    before = sim.get_state()
+    pairs0 = cKDTree(np.column_stack([before["x"], before["y"], before["z"]])).query_pairs(cfg.collision_range)
+    assert 800 < len(pairs0) < 1400                      # the reference's initial state: 1,051
+    redrawn, left = sim.seed_relax(8)
+    after = sim.get_state()
+    assert left == 0 and len(pairs0) * 0.9 <= redrawn <= len(pairs0) * 1.2
+    pts = np.column_stack([after["x"], after["y"], after["z"]])
+    assert len(cKDTree(pts).query_pairs(cfg.collision_range)) == 0
+    moved = (after["x"] != before["x"]) | (after["y"] != before["y"]) | (after["z"] != before["z"])
+    assert moved.sum() <= redrawn and moved.sum() >= 0.9 * len(pairs0) * 0.95
+    hi = np.array([max(a, b) for a, b in pairs0])
+    assert moved[hi].all()                               # in every overlapping pair the higher index was re-drawn
+    for k in ("vx", "vy", "vz"):
+        assert np.array_equal(after[k], before[k])
+    r = np.hypot(after["x"], after["y"])
+    assert r.max() <= cfg.open_air_radius and after["z"].min() > 0 and after["z"].max() < cfg.total_height
+    first = sim.step(1)[0]
+    assert first["pp_collisions"] < 600                  # steady state ~260 per step; the un-relaxed start resolves ~1,070
+    sim.close()
