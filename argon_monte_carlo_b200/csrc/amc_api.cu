@@ -1035,7 +1035,8 @@ extern "C" int amc_slab_enable(amc_handle *h, const amc_slab_config *c)
     p.xf_count = h->d_counters; p.n_in = h->d_counters + c->nranks; p.bnd_n = h->d_counters + c->nranks + 1;
     p.rel_count = h->d_counters + c->nranks + 3; p.n_foreign = h->d_counters + c->nranks + 4;
     ALLOC(p.bnd_dirty[0], p.bnd_cap); ALLOC(p.bnd_dirty[1], p.bnd_cap);
-    ALLOC(p.rel_id, p.rel_cap); ALLOC(p.rel_slot, p.rel_cap); ALLOC(p.skey, h->cap); ALLOC(p.aux, h->cap);
+    ALLOC(p.xf_pack, h->xf_total);
+    ALLOC(p.rel_id, p.rel_cap); ALLOC(p.rel_slot, p.rel_cap); ALLOC(p.aux, h->cap);
     ALLOC(h->d_slab_overflow, 4);
     CK(cudaMemset(h->d_slab_overflow, 0, 4 * sizeof(unsigned long long)));
     p.slab_overflow = h->d_slab_overflow;
@@ -1076,9 +1077,12 @@ extern "C" int amc_slab_advect(amc_handle *h)
     CK(cudaMemsetAsync(p.band_count, 0, (h->n_buckets + 2) * sizeof(int32_t), h->stream));
     CK(cudaMemsetAsync(p.rest_count, 0, (h->n_buckets + 1) * sizeof(int32_t), h->stream));
     h->slab_phase = PH_DRIFT | PH_WALLS | (p.kind != AMC_KIND_CUBE ? PH_RECAP : 0);
-    if (h->n) k_keys<true><<<grid_for(h->n, ADVECT_THREADS), ADVECT_THREADS, 0, h->stream>>>(p, h->slab_phase);
+    if (h->n) {
+        k_keys<true><<<grid_for(h->n, ADVECT_THREADS), ADVECT_THREADS, 0, h->stream>>>(p, h->slab_phase);
+        if (p.nranks > 1) k_slab_pack<<<dim3(grid_for(p.xf_cap, ADVECT_THREADS), p.nranks), ADVECT_THREADS, 0, h->stream>>>(p, h->slab_phase);
+    }
     k_xfer_headers<<<1, 32, 0, h->stream>>>(p);
-    h->last_launches += (h->n ? 1 : 0) + 1; /* slab handles: cumulative (amc_last_timing) */
+    h->last_launches += (h->n ? 2 : 0) + 1; /* slab handles: cumulative (amc_last_timing) */
     CK(cudaGetLastError());
     return AMC_OK;
 }
@@ -1355,6 +1359,7 @@ extern "C" int amc_slab_step(amc_handle *h, int32_t n_steps, int32_t pre_round, 
             k_keys<true><<<full, ADVECT_THREADS, 0, h->stream>>>(p, phase);
             CK(cudaEventRecord(h->events[4 * s + 1], h->stream));
             if (p.nranks > 1) {
+                k_slab_pack<<<dim3(grid_for(p.xf_cap, ADVECT_THREADS), p.nranks), ADVECT_THREADS, 0, h->stream>>>(p, phase);
                 k_xfer_push<<<p.nranks, 32, 0, h->stream>>>(p);
                 k_xfer_unpack<<<dim3(grid_for(p.xf_cap, ADVECT_THREADS), p.nranks), ADVECT_THREADS, 0, h->stream>>>(p);
             }

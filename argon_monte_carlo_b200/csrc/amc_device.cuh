@@ -120,6 +120,7 @@ struct P {
     double *xf_send;          /* per peer d: records [xf_off[d], xf_off[d] + xf_capv[d]], the first one = header (count) */
     const double *xf_recv;
     int32_t *xf_count;        /* [nranks] */
+    int2 *xf_pack;            /* same block layout as the records: {slot, flag bits} of every particle k_keys found to travel; k_slab_pack makes the records */
     int32_t xf_cap;           /* largest per-peer capacity */
     int32_t xf_cap_nb, xf_cap_far; /* capacity of the blocks exchanged with rank +-1 / with every other rank */
     const int32_t *xf_off, *xf_capv; /* [nranks] record offset / capacity of each peer's block (same layout for send and recv) */
@@ -131,7 +132,6 @@ struct P {
     const double *bnd_recv[2];
     int32_t *rel_id, *rel_slot, *rel_count; /* open-addressing hash: particles a neighbour may send updates for, id -> slot */
     int32_t rel_cap;          /* power of two; rel_id[] == -1: empty */
-    int32_t *skey;            /* owner key each slot was sorted into (-1: appended foreign copy) */
     uint8_t *aux;             /* per slot, k_keys -> k_scatter_advect: AUX_* bits of the slab protocol */
     int32_t *n_foreign;       /* foreign copies appended after the sort */
     int32_t foreign_cap;

@@ -149,18 +149,30 @@ def run_cube(args, world, rank, local, dev, barrier, max_over_ranks, sum_over_ra
         cuts = slab.balanced_cuts(state[2], grid.edge[2], world)
         layer = slab.owner_layer(state[2], grid.edge[2])
         m = (layer >= cuts[rank]) & (layer < cuts[rank + 1])
+        fused = os.environ.get("AMC_SLAB_MODE", "p2p") == "p2p"
         sim = slab.SlabSimulation(cfg, world, state[2], transport=slab.DistTransport(), local_ranks=[rank], devices=[local],
-                                  cuts=cuts, kind=amc.KIND_CUBE, grid=grid, seed=127)
+                                  cuts=cuts, kind=amc.KIND_CUBE, grid=grid, seed=127, p2p=fused)
         sim.set_local_state(np.nonzero(m)[0], *[a[m] for a in state], n_global=n)
-        sim.step(args.warmup, reduce=False)
+        step = (lambda k, timing=False: sim.step_fused(k, reduce=False)) if fused else (lambda k, timing=False: sim.step(k, reduce=False, timing=timing))
+        step(args.warmup)
         barrier()
-        sim.step(args.steps, reduce=False, timing=True)
+        step(args.steps, timing=True)
         ms = sim.phase_ms
         barrier()
+        digest = sim.state_digest()
         dev_ms = max_over_ranks(float(ms.sum()))
         phases = {"advect_walls": ms[0] / args.steps, "exchange_sort": ms[1] / args.steps,
                   "pairs_and_handover": ms[2] / args.steps, "finish": ms[3] / args.steps}
         sim.close()
+        verify = {"digest": ["%016x" % d for d in digest[:2]], "particles_counted": digest[2], "steps": args.warmup + args.steps}
+        if rank == 0 and not args.no_verify:     # out of band: the same job as one domain on rank 0's GPU
+            one = amc.Simulation(cfg, kind=amc.KIND_CUBE, pp_mode=amc.PP_GROUPS, grid=grid, max_particles=n, device=local)
+            one.set_state(*state)
+            one.step_quiet(args.warmup + args.steps)
+            d1 = one.state_digest()
+            one.close()
+            verify.update(digest_single_gpu=["%016x" % d for d in d1[:2]], identical_to_single_gpu=tuple(d1) == tuple(digest))
+        barrier()
     out = {"metric": "collision-resolved particle-steps/s", "value": n * args.steps / (dev_ms * 1e-3), "unit": "particle-steps/s",
            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -168,6 +180,8 @@ def run_cube(args, world, rank, local, dev, barrier, max_over_ranks, sum_over_ra
                                   "%d^3 cells, z slabs over %d GPU(s)" % (n // 1000000, cfg.cube_x * 1e9, n_sub, world),
                       "particles_total": n, "l2": "inputs larger than L2"},
            "phases_ms_per_step": phases}
+    if world > 1:
+        out["verify"] = verify
     if rank == 0:
         emit(out)
     if world > 1:
