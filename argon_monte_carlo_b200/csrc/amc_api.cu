@@ -28,6 +28,8 @@ struct amc_handle {
     uint32_t xf_seq = 0, bnd_seq = 0;
     int32_t *d_n = nullptr;          // device-resident particle count of amc_slab_step
     amc_slab_p2p_desc p2p_desc;
+    std::vector<cudaEvent_t> grp_events; // amc_slab_step with AMC_SLAB_TRACE: around every colour-group launch of the last step of a chunk
+    double group_ms[10] = {0};           // [0..7] group launches, [8] closing hand-over, [9] steps accumulated
     amc_init_spec init_spec;         // of the last amc_init_synthetic call (amc_seed_relax re-draws from it)
     bool have_init_spec = false;
     int32_t *d_counters = nullptr; // slab mode: xf_count[nranks], n_in, bnd_n[2], rel_count, n_foreign, compact count
@@ -489,7 +491,7 @@ static int run_pairs(amc_handle *h, int64_t *launches, bool prepared = false)
         k_detect<false><<<h->det_grid, DET_THREADS, 0, h->stream>>>(p);
         if (h->det_slot >= 0) CK(cudaEventRecord(h->det_events[2 * h->det_slot + 1], h->stream));
         unsigned grid = (unsigned)std::min<int64_t>((int64_t)h->pair_grid, std::max<int64_t>(ncell / 8, 1));
-        for (int g = 0; g < 8; g++) k_pairs_group<<<grid, PAIR_THREADS, 0, h->stream>>>(p, g);
+        for (int g = 0; g < 8; g++) k_pairs_group<<<grid, PAIR_THREADS, 0, h->stream>>>(p, g, 0);
         if (launches) *launches += 11;
     }
     CK(cudaGetLastError());
@@ -1030,8 +1032,9 @@ extern "C" int amc_slab_enable(amc_handle *h, const amc_slab_config *c)
         p.rel_cap = pow2;
     }
     p.foreign_cap = std::max(c->bnd_capacity * 16, 4096);
-    ALLOC(h->d_counters, c->nranks + 8);
-    CK(cudaMemset(h->d_counters, 0, (c->nranks + 8) * sizeof(int32_t)));
+    ALLOC(h->d_counters, c->nranks + 12);
+    CK(cudaMemset(h->d_counters, 0, (c->nranks + 12) * sizeof(int32_t)));
+    p.applied = reinterpret_cast<uint32_t *>(h->d_counters + c->nranks + 6); p.pg_done = h->d_counters + c->nranks + 8;
     p.xf_count = h->d_counters; p.n_in = h->d_counters + c->nranks; p.bnd_n = h->d_counters + c->nranks + 1;
     p.rel_count = h->d_counters + c->nranks + 3; p.n_foreign = h->d_counters + c->nranks + 4;
     ALLOC(p.bnd_dirty[0], p.bnd_cap); ALLOC(p.bnd_dirty[1], p.bnd_cap);
@@ -1072,7 +1075,7 @@ extern "C" int amc_slab_advect(amc_handle *h)
     p.stats = h->d_stats;
     p.step = h->step_index++;
     CK(cudaMemsetAsync(h->d_stats, 0, sizeof(StatsDev), h->stream));
-    CK(cudaMemsetAsync(h->d_counters, 0, (p.nranks + 8) * sizeof(int32_t), h->stream));
+    CK(cudaMemsetAsync(h->d_counters, 0, (p.nranks + 12) * sizeof(int32_t), h->stream));
     CK(cudaMemsetAsync(p.rel_id, 0xff, (size_t)p.rel_cap * sizeof(int32_t), h->stream));
     CK(cudaMemsetAsync(p.band_count, 0, (h->n_buckets + 2) * sizeof(int32_t), h->stream));
     CK(cudaMemsetAsync(p.rest_count, 0, (h->n_buckets + 1) * sizeof(int32_t), h->stream));
@@ -1152,7 +1155,7 @@ extern "C" int amc_slab_group(amc_handle *h, int32_t g)
     P &p = h->p;
     int ncell = p.nc[0] * p.nc[1] * p.nc[2];
     unsigned grid = (unsigned)std::min<int64_t>((int64_t)h->pair_grid, std::max<int64_t>(ncell / 8, 1));
-    if (h->n) k_pairs_group<<<grid, PAIR_THREADS, 0, h->stream>>>(p, g);
+    if (h->n) k_pairs_group<<<grid, PAIR_THREADS, 0, h->stream>>>(p, g, 0);
     k_bnd_pack<<<2, ADVECT_THREADS, 0, h->stream>>>(p);
     h->last_launches += (h->n ? 1 : 0) + 1;
     CK(cudaGetLastError());
@@ -1352,7 +1355,7 @@ extern "C" int amc_slab_step(amc_handle *h, int32_t n_steps, int32_t pre_round, 
             p.xf_seq = ++h->xf_seq;
             p.parity = (int32_t)(p.xf_seq & 1u);
             // ---- advect (dry run) + packing, all-to-all, unpack, sort
-            CK(cudaMemsetAsync(h->d_counters, 0, (p.nranks + 8) * sizeof(int32_t), h->stream));
+            CK(cudaMemsetAsync(h->d_counters, 0, (p.nranks + 12) * sizeof(int32_t), h->stream));
             CK(cudaMemsetAsync(p.rel_id, 0xff, (size_t)p.rel_cap * sizeof(int32_t), h->stream));
             CK(cudaMemsetAsync(p.band_count, 0, (h->n_buckets + 2) * sizeof(int32_t), h->stream));
             CK(cudaMemsetAsync(p.rest_count, 0, (h->n_buckets + 1) * sizeof(int32_t), h->stream));
@@ -1378,8 +1381,33 @@ extern "C" int amc_slab_step(amc_handle *h, int32_t n_steps, int32_t pre_round, 
             k_detect<false><<<h->det_grid, DET_THREADS, 0, h->stream>>>(p);
             CK(cudaEventRecord(h->det_events[2 * s + 1], h->stream));
             h->last_launches += 12;
+            if (p.nranks > 1 && pgrid >= 2 * BND_HEAD_CTAS && !getenv("AMC_SLAB_UNFUSED")) {
+                // the hand-over rides inside the group launches (k_pairs_group, fused): records of group g are sent by the
+                // last CTA of launch g and applied at the head of launch g + 1 while the cells away from the cuts run
+                uint32_t prev = 0;
+                if (pre_round) { /* immigrants that landed in the band below an even cut travel before the first group */
+                    p.bnd_seq = ++h->bnd_seq;
+                    k_bnd_apply<true><<<dim3(48, 2), 128, 0, h->stream>>>(p);
+                    h->last_launches += 1;
+                }
+                const bool trace = getenv("AMC_SLAB_TRACE") && s == chunk - 1;
+                if (trace) while (h->grp_events.size() < 10) { cudaEvent_t e; CK(cudaEventCreate(&e)); h->grp_events.push_back(e); }
+                for (int g = 0; g < 8; g++) {
+                    p.bnd_seq_apply = prev;
+                    p.bnd_seq = ++h->bnd_seq;
+                    p.group_done = g - 1;
+                    if (trace) CK(cudaEventRecord(h->grp_events[g], h->stream));
+                    k_pairs_group<<<pgrid, PAIR_THREADS, 0, h->stream>>>(p, g, 1);
+                    prev = p.bnd_seq;
+                }
+                p.group_done = 7;                      /* the records of the last group: wait and apply */
+                if (trace) CK(cudaEventRecord(h->grp_events[8], h->stream));
+                k_bnd_apply<false><<<dim3(48, 2), 128, 0, h->stream>>>(p);
+                if (trace) CK(cudaEventRecord(h->grp_events[9], h->stream));
+                h->last_launches += 9;
+            } else
             for (int g = pre_round ? -1 : 0; g < 8; g++) {
-                if (g >= 0) { k_pairs_group<<<pgrid, PAIR_THREADS, 0, h->stream>>>(p, g); h->last_launches += 1; }
+                if (g >= 0) { k_pairs_group<<<pgrid, PAIR_THREADS, 0, h->stream>>>(p, g, 0); h->last_launches += 1; }
                 p.bnd_seq = ++h->bnd_seq;
                 p.group_done = g;
                 if (p.nranks > 1) k_bnd_apply<true><<<dim3(48, 2), 128, 0, h->stream>>>(p); /* sends, then waits for and applies the neighbours' records */
@@ -1410,6 +1438,13 @@ extern "C" int amc_slab_step(amc_handle *h, int32_t n_steps, int32_t pre_round, 
             CK(cudaEventElapsedTime(&ms, h->det_events[2 * s], h->det_events[2 * s + 1]));
             h->last_detect_ms += ms;
         }
+        if (getenv("AMC_SLAB_TRACE") && h->grp_events.size() >= 10 && p.nranks > 1) {
+            for (int g = 0; g < 9; g++) {
+                float ms = 0;
+                if (cudaEventElapsedTime(&ms, h->grp_events[g], h->grp_events[g + 1]) == cudaSuccess) h->group_ms[g] += ms;
+            }
+            h->group_ms[9] += 1;
+        }
         if ((rc = slab_overflow_error(h, ovf)) != AMC_OK) { p.n_dev = nullptr; return rc; }
         for (int s = 0; s < chunk; s++) {
             if ((rc = check_overflow(h, h->h_stats[s])) != AMC_OK) { p.n_dev = nullptr; return rc; }
@@ -1420,6 +1455,29 @@ extern "C" int amc_slab_step(amc_handle *h, int32_t n_steps, int32_t pre_round, 
     h->last_ms[4] = h->last_ms[0] + h->last_ms[1] + h->last_ms[2] + h->last_ms[3];
     p.n_dev = nullptr;
     p.stats = h->d_stats;
+    return AMC_OK;
+}
+
+#ifdef AMC_SLAB_PROBE
+// debug build: read (and reset) the wall-clock marks of the fused group launches (see g_probe)
+extern "C" int amc_debug_probe(unsigned long long out[64], int reset)
+{
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, g_probe, 64 * sizeof(unsigned long long));
+    if (reset) {
+        unsigned long long z[8][8];
+        for (int g = 0; g < 8; g++) for (int k = 0; k < 8; k++) z[g][k] = k == 0 ? ~0ull : 0ull;
+        cudaMemcpyToSymbol(g_probe, z, sizeof(z));
+    }
+    return 0;
+}
+#endif
+
+// debug (AMC_SLAB_TRACE=1): device time of the colour-group launches of amc_slab_step, summed over the traced steps
+extern "C" int amc_debug_group_ms(amc_handle *h, double out[10])
+{
+    if (!h || !out) return AMC_E_INVALID;
+    memcpy(out, h->group_ms, sizeof(h->group_ms));
     return AMC_OK;
 }
 

@@ -144,6 +144,9 @@ struct P {
     int32_t parity;           /* buffer half used by this step's all-to-all */
     uint32_t xf_seq;          /* sequence number of this step's all-to-all */
     uint32_t bnd_seq;         /* sequence number of the hand-over round being packed / applied */
+    uint32_t bnd_seq_apply;   /* fused hand-over (k_pairs_group): round whose records are applied at the head of the launch, 0 = none */
+    uint32_t *applied;        /* [2] fused hand-over: bnd_seq of the launch whose head has finished applying direction d */
+    int32_t *pg_done;         /* fused hand-over: CTAs of the current k_pairs_group launch that have finished */
     double *const *peer_xf;   /* [nranks] base of every rank's xfer_recv (both halves); [srank] = own */
     const int64_t *peer_xf_stride; /* [nranks] doubles per half of that rank's xfer_recv (end ranks have one big block, inner ranks two) */
     const int64_t *peer_xf_off;    /* [nranks] record offset of THIS rank's block inside that rank's xfer_recv */

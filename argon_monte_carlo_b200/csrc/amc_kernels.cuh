@@ -676,8 +676,9 @@ __device__ __forceinline__ void resolve_pair(const P &p, CellShared &S, int m1, 
             asm volatile("prefetch.global.L1 [%0];" ::"l"(p.band_count + oc));
         }
     }
-    const double ovx = A.vx[so], ovy = A.vy[so], ovz = A.vz[so], od = A.d[so], odx = A.dx[so], ody = A.dy[so], odz = A.dz[so];
-    uint32_t of = A.flag[so];
+    const double ovx = __ldcg(A.vx + so), ovy = __ldcg(A.vy + so), ovz = __ldcg(A.vz + so), od = __ldcg(A.d + so), odx = __ldcg(A.dx + so),
+                 ody = __ldcg(A.dy + so), odz = __ldcg(A.dz + so);
+    uint32_t of = __ldcg(A.flag + so);
     const double qvx = __shfl_xor_sync(FULL, ovx, 1), qvy = __shfl_xor_sync(FULL, ovy, 1), qvz = __shfl_xor_sync(FULL, ovz, 1);
     double x1 = S.x[m1], y1 = S.y[m1], z1 = S.z[m1], x2 = S.x[m2], y2 = S.y[m2], z2 = S.z[m2];
     const double vx1 = w ? qvx : ovx, vy1 = w ? qvy : ovy, vz1 = w ? qvz : ovz;
@@ -1373,7 +1374,7 @@ __device__ __forceinline__ void gather_members(const P &p, CellShared &S, const 
             // particles that left their sorted owner cell earlier in this pass and are members of this cell now hang
             // on the cell's own list (head in cell_active, see esc_link): one load for nearly every cell
             int esc_head = 0;
-            if (tid == PAIR_THREADS - 1) esc_head = p.cell_active[(size_t)group * p.wl_stride + cell];
+            if (tid == PAIR_THREADS - 1) esc_head = __ldcg(p.cell_active + (size_t)group * p.wl_stride + cell);
             for (int tb = 0; tb < total; tb += PAIR_K * PAIR_THREADS) { /* PAIR_K candidates per thread in flight: one round trip for most cells */
                 unsigned fl[PAIR_K]; double x[PAIR_K], y[PAIR_K], z[PAIR_K]; int id[PAIR_K];
 #pragma unroll
@@ -1384,7 +1385,8 @@ __device__ __forceinline__ void gather_members(const P &p, CellShared &S, const 
 #pragma unroll
                         for (int r = 1; r < 8; r++) nb += t >= S.rcum[r];
                         int s = S.rbeg[nb] + (t - S.rcum[nb]);
-                        fl[k] = A.flag[s]; x[k] = A.x[s]; y[k] = A.y[s]; z[k] = A.z[s]; id[k] = A.id[s];
+                        /* past L1: with the fused hand-over another CTA of this launch may have updated the record */
+                        fl[k] = __ldcg(A.flag + s); x[k] = __ldcg(A.x + s); y[k] = __ldcg(A.y + s); z[k] = __ldcg(A.z + s); id[k] = __ldcg(A.id + s);
                     }
                 }
                 PHASE_MARK(11); /* gather: loads issued */
@@ -1411,21 +1413,62 @@ __device__ __forceinline__ void gather_members(const P &p, CellShared &S, const 
             PHASE_MARK(12); /* gather: members stored */
             for (int v = esc_head; v >= 2;) { /* thread PAIR_THREADS - 1 only */
                 const int e = v - 2;
-                v = p.esc_next[e * 8 + group];
-                if (p.esc_cell[e * 8 + group] != cell) continue; /* the particle moved on since it was linked here */
-                int s = p.esc_slot[e];
+                v = __ldcg(p.esc_next + e * 8 + group);
+                if (__ldcg(p.esc_cell + e * 8 + group) != cell) continue; /* the particle moved on since it was linked here */
+                int s = __ldcg(p.esc_slot + e);
                 int k = atomicAdd(&S.n, 1);
-                if (k < AMC_MAX_MEMBERS) { S.x[k] = A.x[s]; S.y[k] = A.y[s]; S.z[k] = A.z[s]; S.id[k] = A.id[s]; S.slot[k] = s; S.src[k] = e; }
+                if (k < AMC_MAX_MEMBERS) { S.x[k] = __ldcg(A.x + s); S.y[k] = __ldcg(A.y + s); S.z[k] = __ldcg(A.z + s); S.id[k] = __ldcg(A.id + s); S.slot[k] = s; S.src[k] = e; }
             }
         }
 }
 
 // one colour group (Pore:522-549): persistent CTAs walk the group's worklist
-__global__ void __launch_bounds__(PAIR_THREADS, 6) k_pairs_group(const __grid_constant__ P p, const int group)
+#define BND_HEAD_CTAS 8 /* CTAs per direction that apply the neighbours' records at the head of a fused k_pairs_group launch */
+#ifdef AMC_SLAB_PROBE
+// debug build (tools/gpu_trace.sh): wall-clock marks of a fused launch per colour group, ns since the first CTA started:
+// [g][0] first CTA in, [1]/[2] hand-over from above / below applied, [3] last cut-adjacent visit done, [4] last visit done,
+// [5] records sent, [6] hand-over records applied (count), [7] cut-adjacent visits (count)
+__device__ unsigned long long g_probe[8][8];
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define PROBE_MIN(g, k) do { if (threadIdx.x == 0) atomicMin(&g_probe[g][k], gtime()); } while (0)
+#define PROBE_MAX(g, k) do { if (threadIdx.x == 0) atomicMax(&g_probe[g][k], gtime()); } while (0)
+#define PROBE_ADD(g, k, v) do { if (threadIdx.x == 0) atomicAdd(&g_probe[g][k], (unsigned long long)(v)); } while (0)
+#else
+#define PROBE_MIN(g, k) do { } while (0)
+#define PROBE_MAX(g, k) do { } while (0)
+#define PROBE_ADD(g, k, v) do { } while (0)
+#endif
+__device__ __forceinline__ void bnd_pack_dir(const P &p, const int dir);                                                       /* slab section below */
+__device__ __forceinline__ void bnd_apply_dir(const P &p, const int dir, const uint32_t seq, const int first, const int step);
+__device__ __forceinline__ void bnd_pack_warp(const P &p, const int dir, const int lane);
+
+// `fused` (peer-to-peer slab stepping): the hand-over with the neighbouring ranks rides inside this launch.  The first
+// 2 x BND_HEAD_CTAS CTAs first apply the records the rank above / below sent after the previous group (waiting for them if need be) and then
+// publish p.applied[dir]; the visits of cells in the two layers next to a cut wait for that, all other cells are
+// processed meanwhile; the worklist may grow while the records are applied, so a CTA only leaves once both directions
+// are applied and no ticket is left; the last CTA to finish packs this group's records straight into the neighbours'
+// buffers and publishes p.bnd_seq there.
+__global__ void __launch_bounds__(PAIR_THREADS, 6) k_pairs_group(const __grid_constant__ P p, const int group, const int fused)
 {
     __shared__ CellShared S;
     const int tid = threadIdx.x;
-    const int nwork = p.wl_count[group];
+    if (fused) PROBE_MIN(group, 0);
+    if (fused && blockIdx.x < 2 * BND_HEAD_CTAS) { /* BND_HEAD_CTAS CTAs per direction share the records; the last one done publishes */
+        const int dir = blockIdx.x & 1;
+        if (p.bnd_seq_apply) bnd_apply_dir(p, dir, p.bnd_seq_apply, blockIdx.x >> 1, BND_HEAD_CTAS);
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            if (atomicAdd(p.pg_done + 1 + dir, 1) == BND_HEAD_CTAS - 1) {
+                p.pg_done[1 + dir] = 0;
+                __threadfence();
+                asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.applied + dir), "r"(p.bnd_seq) : "memory");
+                PROBE_MAX(group, 1 + dir);
+            }
+        }
+    }
+    int nwork = fused ? __ldcg(p.wl_count + group) : p.wl_count[group];
+    bool list_final = !fused;
     const int32_t *wl = p.wl + (size_t)group * p.wl_stride * AMC_WI;
     __shared__ __align__(16) int s_hdr[AMC_WI];
     if (tid == 0) { S.nexec = 0; S.nref = 0; }
@@ -1443,14 +1486,24 @@ __global__ void __launch_bounds__(PAIR_THREADS, 6) k_pairs_group(const __grid_co
         if (tid == 0) s_w = next_w;
     }
     __syncthreads();
-    while (s_w < nwork) {
+    while (true) {
+        if (s_w >= nwork) {
+            if (list_final) break;
+            // out of tickets while the hand-over may still add cells: wait until both directions are applied, then the list is final
+            if (tid == 0) { flag_wait(p.applied + 0, p.bnd_seq); flag_wait(p.applied + 1, p.bnd_seq); }
+            __syncthreads();
+            list_final = true;
+            nwork = __ldcg(p.wl_count + group);
+            if (s_w >= nwork) break;
+            if (tid < AMC_WI) next_hdr = __ldcg(wl + (size_t)s_w * AMC_WI + tid); /* this ticket was beyond the list when it was drawn */
+        }
         __syncthreads(); /* previous cell fully processed before S is reused; everyone has read s_w */
 #ifdef AMC_PHASE_CLOCK
         if (tid == 0) { S.t_last = clock64(); atomicAdd(&g_phase_clk[15], 1ull); }
 #endif
         if (tid < AMC_WI) {
             s_hdr[tid] = next_hdr;
-            if (nwork > (int)gridDim.x) { /* more items than CTAs: draw the next one */
+            if (fused || nwork > (int)gridDim.x) { /* more items than CTAs (or a list that can still grow): draw the next one */
                 if (tid == 0) next_w = (int)gridDim.x + atomicAdd(&p.wl_next[group], 1);
                 next_w = __shfl_sync(0xffffffffu, next_w, 0);
                 if (next_w < nwork) next_hdr = wl[(size_t)next_w * AMC_WI + tid];
@@ -1479,8 +1532,15 @@ __global__ void __launch_bounds__(PAIR_THREADS, 6) k_pairs_group(const __grid_co
         __syncthreads();
         PHASE_MARK(0); /* header */
         const int cell = s_hdr[0];
+        if (fused && !list_final) { /* a cell in the two layers next to a cut: its particles may be part of the hand-over being applied */
+            const bool below = s_hdr[3] <= 1 && p.srank > 0, above = s_hdr[3] >= p.nc[2] - 2 && p.srank + 1 < p.nranks;
+            if (below || above) {
+                if (tid == 0) { if (below) flag_wait(p.applied + 1, p.bnd_seq); if (above) flag_wait(p.applied + 0, p.bnd_seq); }
+                __syncthreads();
+            }
+        }
         if (tid >= PAIR_THREADS - 32 && (tid & 31) < AMC_HIT_REC) /* last warp: this item's pair list from k_detect */
-            S.hits[tid & 31] = p.wl_hit[((size_t)group * p.wl_stride + s_w) * AMC_HIT_REC + (tid & 31)];
+            S.hits[tid & 31] = __ldcg(p.wl_hit + ((size_t)group * p.wl_stride + s_w) * AMC_HIT_REC + (tid & 31));
         if (tid < 2 * AMC_MAX_HITS) S.hm[tid] = -1;
         gather_members(p, S, group, cell);
         __syncthreads();
@@ -1491,7 +1551,7 @@ __global__ void __launch_bounds__(PAIR_THREADS, 6) k_pairs_group(const __grid_co
             __syncthreads();
         }
         if (tid == 0) { /* the detection pass already counted this cell if it saw it without an overlapping pair */
-            const int raw = p.cell_n[(size_t)group * p.wl_stride + cell];
+            const int raw = __ldcg(p.cell_n + (size_t)group * p.wl_stride + cell);
             const int nA = raw & ~AMC_CELL_DIRTY;
             S.nref -= (unsigned long long)nA * (nA - 1) / 2;
             S.use_hits = S.hits[0] >= 0 && !(raw & AMC_CELL_DIRTY);
@@ -1499,6 +1559,13 @@ __global__ void __launch_bounds__(PAIR_THREADS, 6) k_pairs_group(const __grid_co
         __syncthreads();
         if (S.n >= 2) cell_process(p, S, group, cell);
         PHASE_MARK(7); /* resolution loop (cells with candidates) */
+#ifdef AMC_SLAB_PROBE
+        if (fused) {
+            const bool nearcut = (s_hdr[3] <= 1 && p.srank > 0) || (s_hdr[3] >= p.nc[2] - 2 && p.srank + 1 < p.nranks);
+            if (nearcut) { PROBE_MAX(group, 3); PROBE_ADD(group, 7, 1); }
+            PROBE_MAX(group, 4);
+        }
+#endif
         __syncthreads();
         if (tid == 0) s_w = next_w;
         __syncthreads();
@@ -1507,6 +1574,18 @@ __global__ void __launch_bounds__(PAIR_THREADS, 6) k_pairs_group(const __grid_co
     if (tid == 0) { /* one pair of global atomics per CTA instead of per cell */
         if (S.nref) atomicAdd(&p.stats->checks_ref, S.nref);
         if (S.nexec) atomicAdd(&p.stats->checks_exec, (unsigned long long)S.nexec);
+    }
+    if (fused) { /* the last CTA of the launch sends this group's records to the neighbours */
+        __shared__ int s_last;
+        if (tid == 0) { __threadfence(); s_last = atomicAdd(p.pg_done, 1) == (int)gridDim.x - 1; }
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            if (tid < 64) bnd_pack_warp(p, tid >> 5, tid & 31); /* warp 0: up, warp 1: down */
+            if (tid == 0) *p.pg_done = 0;
+            __syncthreads();
+            PROBE_MAX(group, 5);
+        }
     }
 }
 
@@ -1806,7 +1885,7 @@ __global__ void __launch_bounds__(ADVECT_THREADS) k_xfer_unpack(const __grid_con
 // the block clears its queue counter when it is done
 __device__ __forceinline__ void bnd_pack_dir(const P &p, const int dir)
 {
-    const int cnt = min(p.bnd_n[dir], p.bnd_cap);
+    const int cnt = min(__ldcg(p.bnd_n + dir), p.bnd_cap);
     const bool peer = p.peer_xf != nullptr;
     const bool has_nb = dir == 0 ? p.srank + 1 < p.nranks : p.srank > 0;
     // peer-to-peer mode: the records go straight into the neighbour's receive buffer (half = parity of the round)
@@ -1815,11 +1894,11 @@ __device__ __forceinline__ void bnd_pack_dir(const P &p, const int dir)
     if (buf == nullptr) { if (threadIdx.x == 0) p.bnd_n[dir] = 0; return; }
     if (threadIdx.x == 0) buf[0] = (double)cnt;
     for (int j = threadIdx.x; j < cnt; j += blockDim.x) {
-        int s = p.bnd_dirty[dir][j];
+        int s = __ldcg(p.bnd_dirty[dir] + j);
         double *r = buf + (size_t)(1 + j) * AMC_REC;
-        r[0] = A.x[s]; r[1] = A.y[s]; r[2] = A.z[s]; r[3] = A.vx[s]; r[4] = A.vy[s]; r[5] = A.vz[s];
-        r[6] = A.d[s]; r[7] = A.dx[s]; r[8] = A.dy[s]; r[9] = A.dz[s]; r[10] = (double)A.id[s];
-        r[11] = (double)(A.flag[s] & AMC_FLAG_PATH);
+        r[0] = __ldcg(A.x + s); r[1] = __ldcg(A.y + s); r[2] = __ldcg(A.z + s); r[3] = __ldcg(A.vx + s); r[4] = __ldcg(A.vy + s); r[5] = __ldcg(A.vz + s);
+        r[6] = __ldcg(A.d + s); r[7] = __ldcg(A.dx + s); r[8] = __ldcg(A.dy + s); r[9] = __ldcg(A.dz + s); r[10] = (double)A.id[s];
+        r[11] = (double)(__ldcg(A.flag + s) & AMC_FLAG_PATH);
         // clear this direction's "queued" bit (32-bit atomic on the word that holds the flag byte)
         unsigned bit = dir == 0 ? AMC_FLAG_DIRTY_UP : AMC_FLAG_DIRTY_DOWN;
         uintptr_t addr = (uintptr_t)(A.flag + s);
@@ -1833,28 +1912,54 @@ __device__ __forceinline__ void bnd_pack_dir(const P &p, const int dir)
     }
 }
 __global__ void __launch_bounds__(ADVECT_THREADS) k_bnd_pack(const __grid_constant__ P p) { bnd_pack_dir(p, blockIdx.x); }
+// the same by ONE WARP (peer-to-peer mode only): the tail of a fused k_pairs_group launch sends both directions side by
+// side, and only one thread per direction pays for the system-scope fence (the records are few; what costs is the fence)
+__device__ __forceinline__ void bnd_pack_warp(const P &p, const int dir, const int lane)
+{
+    const int cnt = min(__ldcg(p.bnd_n + dir), p.bnd_cap);
+    const bool has_nb = dir == 0 ? p.srank + 1 < p.nranks : p.srank > 0;
+    const Arrays &A = p.a;
+    if (!has_nb) { if (lane == 0) p.bnd_n[dir] = 0; return; }
+    double *buf = p.peer_bnd[dir] + (size_t)(p.bnd_seq & 1u) * p.bnd_stride;
+    if (lane == 0) buf[0] = (double)cnt;
+    for (int j = lane; j < cnt; j += 32) {
+        int s = __ldcg(p.bnd_dirty[dir] + j);
+        double *r = buf + (size_t)(1 + j) * AMC_REC;
+        r[0] = __ldcg(A.x + s); r[1] = __ldcg(A.y + s); r[2] = __ldcg(A.z + s); r[3] = __ldcg(A.vx + s); r[4] = __ldcg(A.vy + s); r[5] = __ldcg(A.vz + s);
+        r[6] = __ldcg(A.d + s); r[7] = __ldcg(A.dx + s); r[8] = __ldcg(A.dy + s); r[9] = __ldcg(A.dz + s); r[10] = (double)A.id[s];
+        r[11] = (double)(__ldcg(A.flag + s) & AMC_FLAG_PATH);
+        unsigned bit = dir == 0 ? AMC_FLAG_DIRTY_UP : AMC_FLAG_DIRTY_DOWN;
+        uintptr_t addr = (uintptr_t)(A.flag + s);
+        atomicAnd((unsigned *)(addr & ~(uintptr_t)3), ~(bit << (8 * (addr & 3))));
+    }
+    __syncwarp();
+    if (lane == 0) {
+        p.bnd_n[dir] = 0;
+        flag_publish(p.peer_flag[dir == 0 ? p.srank + 1 : p.srank - 1] + p.nranks + (dir == 0 ? 1 : 0), p.bnd_seq);
+    }
+}
 
 // apply the update records received from one neighbour (dir 0: from the rank above, 1: from below).
 // One CTA per record: find the particle by id among the related particles, or append it as a new
 // foreign copy; then make sure the later colour groups of this pass can find it (escaped list).
-template <bool PACK>
-__global__ void __launch_bounds__(128) k_bnd_apply(const __grid_constant__ P p)
+// the records of hand-over round `seq` from one neighbour (dir 0: the rank above, 1: below), records first, first + step, ...
+// by this CTA (128 threads)
+__device__ __forceinline__ void bnd_apply_dir(const P &p, const int dir, const uint32_t seq, const int first, const int step)
 {
     __shared__ int s_slot, s_esc;
-    const int dir = blockIdx.y;
-    // peer-to-peer mode: the same launch first sends this rank's own records (block 0 of each direction) -- nothing
-    // below depends on them: a particle is moved by exactly one rank per colour group
-    if (PACK && blockIdx.x == 0) { bnd_pack_dir(p, dir); __syncthreads(); }
     if (dir == 0 ? p.srank + 1 >= p.nranks : p.srank == 0) return; /* no neighbour on that side */
     const double *buf = p.bnd_recv[dir];
     if (p.peer_xf) { /* peer-to-peer mode: the neighbour wrote the records itself; wait for this round's sequence number */
-        buf += (size_t)(p.bnd_seq & 1u) * p.bnd_stride;
-        if (threadIdx.x == 0) flag_wait(p.flags + p.nranks + dir, p.bnd_seq);
+        buf += (size_t)(seq & 1u) * p.bnd_stride;
+        if (threadIdx.x == 0) flag_wait(p.flags + p.nranks + dir, seq);
         __syncthreads();
     }
     int cnt = (int)__ldcg(buf);
+#ifdef AMC_SLAB_PROBE
+    if (first == 0 && p.group_done >= -1 && p.group_done < 7) PROBE_ADD(p.group_done + 1, 6, cnt);
+#endif
     const int64_t n_base = cur_n(p);
-    for (int j = blockIdx.x; j < cnt; j += gridDim.x) {
+    for (int j = first; j < cnt; j += step) {
     __syncthreads();
     const double *r = buf + (size_t)(1 + j) * AMC_REC;
     const int32_t id = (int32_t)__ldcg(r + 10);
@@ -1935,6 +2040,15 @@ __global__ void __launch_bounds__(128) k_bnd_apply(const __grid_constant__ P p)
         if (dc >= 0 && dc != cc) esc_link(p, g2, dc, dx, dy, dz, -1);
     }
     }
+}
+template <bool PACK>
+__global__ void __launch_bounds__(128) k_bnd_apply(const __grid_constant__ P p)
+{
+    const int dir = blockIdx.y;
+    // peer-to-peer mode: the same launch first sends this rank's own records (block 0 of each direction) -- nothing
+    // below depends on them: a particle is moved by exactly one rank per colour group
+    if (PACK && blockIdx.x == 0) { bnd_pack_dir(p, dir); __syncthreads(); }
+    bnd_apply_dir(p, dir, p.bnd_seq, blockIdx.x, gridDim.x);
 }
 
 // device-resident stepping: the particle count after the sort (start of the bucket of the dropped particles) and,

@@ -376,6 +376,11 @@ def run_slabs(args, world, rank, local, dev, hbm_peak, peak_src, barrier, max_ov
     ms = sim.phase_ms
     barrier()
     clk = clocks.stop()
+    if os.environ.get("AMC_SLAB_TRACE"):
+        import ctypes as C
+        gm = (C.c_double * 10)()
+        sim.ranks[0].sim.lib.amc_debug_group_ms(sim.ranks[0].sim.h, gm)
+        sys.stderr.write("rank %d group launch ms (traced steps %d): %s\n" % (rank, int(gm[9]), " ".join("%.4f" % (v / max(gm[9], 1)) for v in gm[:9])))
     launches = sim.ranks[0].sim.last_timing()[1] - launches0       # counted by the library: kernels this rank launched
     launches_timed = launches * args.steps // (args.steps + args.warmup)
     digest = sim.state_digest()                                    # id-ordered state of all ranks after warmup + steps
