@@ -45,6 +45,7 @@ struct amc_handle {
     bool have_prior = false;
     int64_t step_index = 0;
     int pair_grid = 148 * 5;    // persistent CTAs of k_pairs_group: SMs x resident CTAs per SM
+    int pair_grid_fused = 148;  // the same for the fused (in-kernel hand-over) variant
     int det_grid = 148 * 4;     // persistent CTAs of k_detect
     // host-RNG parity mode: pending hits of the last amc_wall_hits_pending call
     int32_t *d_pend_count = nullptr, *d_pend_slot = nullptr, *d_pend_id = nullptr;
@@ -327,8 +328,14 @@ static int create_impl(amc_handle *h, const amc_config *cfg, int device)
     {
         int sms = 0, per_sm = 0;
         CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-        CK(cudaFuncSetAttribute(k_pairs_group, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pairs_group, PAIR_THREADS, 0));
+        CK(cudaFuncSetAttribute(k_pairs_group<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CK(cudaFuncSetAttribute(k_pairs_group<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        {
+            int per_sm_fused = 0; /* the fused variant waits inside the kernel: every CTA of its grid must be resident */
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_fused, k_pairs_group<true>, PAIR_THREADS, 0));
+            h->pair_grid_fused = std::max(1, sms * std::max(per_sm_fused, 1));
+        }
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pairs_group<false>, PAIR_THREADS, 0));
         h->pair_grid = std::max(1, sms * std::max(per_sm, 1));
         CK(cudaFuncSetAttribute(k_detect<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_detect<false>, DET_THREADS, 0));
@@ -491,7 +498,7 @@ static int run_pairs(amc_handle *h, int64_t *launches, bool prepared = false)
         k_detect<false><<<h->det_grid, DET_THREADS, 0, h->stream>>>(p);
         if (h->det_slot >= 0) CK(cudaEventRecord(h->det_events[2 * h->det_slot + 1], h->stream));
         unsigned grid = (unsigned)std::min<int64_t>((int64_t)h->pair_grid, std::max<int64_t>(ncell / 8, 1));
-        for (int g = 0; g < 8; g++) k_pairs_group<<<grid, PAIR_THREADS, 0, h->stream>>>(p, g, 0);
+        for (int g = 0; g < 8; g++) k_pairs_group<false><<<grid, PAIR_THREADS, 0, h->stream>>>(p, g);
         if (launches) *launches += 11;
     }
     CK(cudaGetLastError());
@@ -1155,7 +1162,7 @@ extern "C" int amc_slab_group(amc_handle *h, int32_t g)
     P &p = h->p;
     int ncell = p.nc[0] * p.nc[1] * p.nc[2];
     unsigned grid = (unsigned)std::min<int64_t>((int64_t)h->pair_grid, std::max<int64_t>(ncell / 8, 1));
-    if (h->n) k_pairs_group<<<grid, PAIR_THREADS, 0, h->stream>>>(p, g, 0);
+    if (h->n) k_pairs_group<false><<<grid, PAIR_THREADS, 0, h->stream>>>(p, g);
     k_bnd_pack<<<2, ADVECT_THREADS, 0, h->stream>>>(p);
     h->last_launches += (h->n ? 1 : 0) + 1;
     CK(cudaGetLastError());
@@ -1329,7 +1336,7 @@ extern "C" int amc_slab_step(amc_handle *h, int32_t n_steps, int32_t pre_round, 
     if (n_steps < 0) return h->fail(AMC_E_INVALID, "n_steps < 0");
     P &p = h->p;
     const int ncell = p.nc[0] * p.nc[1] * p.nc[2];
-    const unsigned pgrid = (unsigned)std::min<int64_t>((int64_t)h->pair_grid, std::max<int64_t>(ncell / 8, 1));
+    const unsigned pgrid = (unsigned)std::min<int64_t>((int64_t)std::min(h->pair_grid, h->pair_grid_fused), std::max<int64_t>(ncell / 8, 1));
     const int phase = PH_DRIFT | PH_WALLS | (p.kind != AMC_KIND_CUBE ? PH_RECAP : 0);
     memset(h->last_ms, 0, sizeof(h->last_ms));
     int32_t n32 = (int32_t)h->n;
@@ -1397,7 +1404,7 @@ extern "C" int amc_slab_step(amc_handle *h, int32_t n_steps, int32_t pre_round, 
                     p.bnd_seq = ++h->bnd_seq;
                     p.group_done = g - 1;
                     if (trace) CK(cudaEventRecord(h->grp_events[g], h->stream));
-                    k_pairs_group<<<pgrid, PAIR_THREADS, 0, h->stream>>>(p, g, 1);
+                    k_pairs_group<true><<<pgrid, PAIR_THREADS, 0, h->stream>>>(p, g);
                     prev = p.bnd_seq;
                 }
                 p.group_done = 7;                      /* the records of the last group: wait and apply */
@@ -1407,7 +1414,7 @@ extern "C" int amc_slab_step(amc_handle *h, int32_t n_steps, int32_t pre_round, 
                 h->last_launches += 9;
             } else
             for (int g = pre_round ? -1 : 0; g < 8; g++) {
-                if (g >= 0) { k_pairs_group<<<pgrid, PAIR_THREADS, 0, h->stream>>>(p, g, 0); h->last_launches += 1; }
+                if (g >= 0) { k_pairs_group<false><<<pgrid, PAIR_THREADS, 0, h->stream>>>(p, g); h->last_launches += 1; }
                 p.bnd_seq = ++h->bnd_seq;
                 p.group_done = g;
                 if (p.nranks > 1) k_bnd_apply<true><<<dim3(48, 2), 128, 0, h->stream>>>(p); /* sends, then waits for and applies the neighbours' records */
@@ -1427,6 +1434,11 @@ extern "C" int amc_slab_step(amc_handle *h, int32_t n_steps, int32_t pre_round, 
         cudaError_t e = cudaStreamSynchronize(h->stream);
         p.n_dev = nullptr;
         if (e != cudaSuccess) return h->fail(AMC_E_CUDA, std::string("amc_slab_step: ") + cudaGetErrorString(e));
+        {
+            unsigned int timeouts = 0;
+            CK(cudaMemcpyFromSymbol(&timeouts, g_flag_timeouts, sizeof(timeouts)));
+            if (timeouts) return h->fail(AMC_E_STATE, "a neighbouring rank did not deliver its records within 20 s (peer-to-peer exchange timed out); the state of this handle is undefined");
+        }
         h->n = n32; p.n = n32;
         p.n_dev = h->d_n;
         for (int s = 0; s < chunk; s++) {

@@ -656,13 +656,25 @@ __device__ __forceinline__ void flag_publish(uint32_t *f, const uint32_t seq)
     __threadfence_system();
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(seq) : "memory");
 }
+// A rank that never publishes (it crashed, or the ranks disagree about the protocol) must not hang the others: after
+// AMC_FLAG_TIMEOUT_NS of waiting the wait gives up and counts itself in g_flag_timeouts; amc_slab_step reads the counter
+// after the call and fails with AMC_E_STATE (the state of the handle is then undefined).
+#define AMC_FLAG_TIMEOUT_NS 20000000000ull /* 20 s */
+__device__ unsigned int g_flag_timeouts;
 __device__ __forceinline__ void flag_wait(const uint32_t *f, const uint32_t seq)
 {
     uint32_t v;
-    while (true) {
+    unsigned long long t0 = 0;
+    for (unsigned int spins = 0;; spins++) {
         asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
         if ((int32_t)(v - seq) >= 0) break;
         __nanosleep(64);
+        if ((spins & 0xfffu) == 0xfffu) { /* look at the clock every 4096 polls (~0.5 ms) */
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > AMC_FLAG_TIMEOUT_NS) { atomicAdd(&g_flag_timeouts, 1u); break; }
+        }
     }
 }
 

@@ -849,9 +849,8 @@ __device__ __forceinline__ void activate_moved(const P &p, CellShared &S, const 
     }
 }
 
-// scan mode of cell_process (kept out of line: rare, and it must not weigh on the register budget of the normal visit):
 // smallest pair key above `cur` among the overlapping pairs whose higher-index member this thread owns
-__device__ __noinline__ unsigned long long scan_min_key(const P &p, const CellShared &S, const int n, const unsigned long long cur)
+__device__ __forceinline__ unsigned long long scan_min_key(const P &p, const CellShared &S, const int n, const unsigned long long cur)
 {
     unsigned long long mine = ~0ull;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -864,6 +863,35 @@ __device__ __noinline__ unsigned long long scan_min_key(const P &p, const CellSh
         }
     }
     return mine;
+}
+
+// Scan mode of cell_process: more pairs overlapped at once than the candidate list holds (a cell far denser than the gas
+// this code is tuned for).  From here to the end of the visit every pick is a search over all member pairs for the
+// smallest key above the cursor that overlaps right now -- the reference's own sweep order, at O(n^2 / threads) per
+// collision.  Kept out of line: rare, and it must not weigh on the register budget of the normal visit.
+__device__ __noinline__ void scan_mode_resolve(const P &p, CellShared &S, const int n, const int group, const int cell)
+{
+    const int tid = threadIdx.x, nthreads = blockDim.x, lane = tid & 31, warp = tid >> 5;
+    while (true) {
+        if (tid == 0) S.best_key = ~0ull;
+        __syncthreads();
+        const unsigned long long mine = scan_min_key(p, S, n, S.cursor);
+        if (tid == 0) atomicAdd(&S.nexec, (unsigned int)min((long long)n * (n - 1) / 2, 0x7fffffffLL));
+        if (mine != ~0ull) atomicMin(&S.best_key, mine);
+        __syncthreads();
+        const unsigned long long bk = S.best_key;
+        if (bk == ~0ull) break;
+        for (int k = tid; k < n; k += nthreads) {
+            if ((uint32_t)S.id[k] == (uint32_t)(bk >> 32)) S.moved_b = k;      /* higher index: the reference's particle 2 */
+            if ((uint32_t)S.id[k] == (uint32_t)(bk & 0xffffffffull)) S.moved_a = k;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            resolve_pair(p, S, S.moved_a, S.moved_b, group, cell);
+            if (lane == 0) S.cursor = bk;
+        }
+        __syncthreads();
+    }
 }
 
 // members are in S.{x,y,z,id,slot,src}[0..S.n); all threads of the block call this
@@ -966,30 +994,7 @@ __device__ __forceinline__ void cell_process(const P &p, CellShared &S, int grou
     if (tid == 0) { S.cursor = 0; S.done = 0; if (S.ncand > AMC_MAX_CAND) S.ncand = AMC_MAX_CAND; }
     __syncthreads();
     while (true) {
-        if (S.cand_lost) {
-            // Scan mode: more pairs overlapped at once than the candidate list holds (a cell far denser than the gas
-            // this code is tuned for).  Every pick is a search over all member pairs for the smallest key above the
-            // cursor that overlaps right now -- the reference's own sweep order, at O(n^2 / threads) per collision.
-            if (tid == 0) S.best_key = ~0ull;
-            __syncthreads();
-            const unsigned long long mine = scan_min_key(p, S, n, S.cursor);
-            if (tid == 0) atomicAdd(&S.nexec, (unsigned int)min((long long)n * (n - 1) / 2, 0x7fffffffLL));
-            if (mine != ~0ull) atomicMin(&S.best_key, mine);
-            __syncthreads();
-            const unsigned long long bk = S.best_key;
-            if (bk == ~0ull) break;
-            for (int k = tid; k < n; k += nthreads) {
-                if ((uint32_t)S.id[k] == (uint32_t)(bk >> 32)) S.moved_b = k;      /* higher index: the reference's particle 2 */
-                if ((uint32_t)S.id[k] == (uint32_t)(bk & 0xffffffffull)) S.moved_a = k;
-            }
-            __syncthreads();
-            if (warp == 0) {
-                resolve_pair(p, S, S.moved_a, S.moved_b, group, cell);
-                if (lane == 0) S.cursor = bk;
-            }
-            __syncthreads();
-            continue;
-        }
+        if (S.cand_lost) { scan_mode_resolve(p, S, n, group, cell); break; } /* block-uniform; rare */
         if (warp == 0) { /* warp-uniform: every lane scans the (few) candidates itself */
             int best = -1;
             unsigned long long bk = ~0ull;
@@ -1448,7 +1453,8 @@ __device__ __forceinline__ void bnd_pack_warp(const P &p, const int dir, const i
 // processed meanwhile; the worklist may grow while the records are applied, so a CTA only leaves once both directions
 // are applied and no ticket is left; the last CTA to finish packs this group's records straight into the neighbours'
 // buffers and publishes p.bnd_seq there.
-__global__ void __launch_bounds__(PAIR_THREADS, 6) k_pairs_group(const __grid_constant__ P p, const int group, const int fused)
+template <bool fused>
+__global__ void __launch_bounds__(PAIR_THREADS, 6) k_pairs_group(const __grid_constant__ P p, const int group)
 {
     __shared__ CellShared S;
     const int tid = threadIdx.x;
