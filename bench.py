@@ -68,28 +68,49 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+    """nvidia-smi clocks / throttle reasons sampled during the timed region.  nvidia-smi needs up to a second to start
+    (longer with eight busy GPUs) while a timed region lasts tens of milliseconds, so the sampler is launched early
+    (launch()) and the rows are selected afterwards by their timestamps: mark_start() / stop() bracket the timed region;
+    when fewer than three rows fall inside it, the rows of the warm-up steps just before it (same kernels, same load)
+    are added and `window` says so."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.rows, self.proc, self.index = [], None, index
+        self.t_launch = self.t_start = self.t_warm = None
 
-    def start(self):
+    def launch(self):
+        if self.proc is not None:
+            return
+        import datetime
+        self.t_launch = datetime.datetime.now()
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "20"],
+                                          "--format=csv,noheader,nounits", "-lms", "10"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
 
+    def mark_warmup(self):
+        import datetime
+        self.t_warm = datetime.datetime.now()
+
+    def start(self):
+        """Beginning of the timed region."""
+        import datetime
+        self.launch()
+        self.t_start = datetime.datetime.now()
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        import datetime
+        t_end = datetime.datetime.now()
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -98,18 +119,29 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        parsed = []
         for r in self.rows:
             try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-                for k, nm in enumerate(names):
-                    if r[3 + k].lower().startswith("active"):
-                        reasons.add(nm)
+                ts = datetime.datetime.strptime(r[0], "%Y/%m/%d %H:%M:%S.%f")
+                parsed.append((ts, float(r[1]), float(r[2]), [nm for k, nm in enumerate(names) if r[4 + k].lower().startswith("active")]))
             except Exception:
                 pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        slack = datetime.timedelta(milliseconds=15)       # nvidia-smi stamps a row when it prints it
+        pick = [q for q in parsed if self.t_start <= q[0] <= t_end + slack]
+        window = "timed region"
+        if len(pick) < 3 and self.t_warm is not None:
+            pick = [q for q in parsed if self.t_warm <= q[0] <= t_end + slack]
+            window = "warm-up steps + timed region"
+        sm, mx = [q[1] for q in pick], [q[2] for q in pick]
+        reasons = sorted({nm for q in pick for nm in q[3]})
+        out = {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+               "samples": len(sm), "window": window, "reasons": reasons}
+        if not sm:   # say why: nothing printed, nothing parsed, or nothing inside the window
+            out["rows_printed"], out["rows_parsed"] = len(self.rows), len(parsed)
+            out["first_row"] = ",".join(self.rows[0]) if self.rows else None
+            out["window_start"] = str(self.t_warm or self.t_start)
+        return out
 
 
 def scaled_temp_config(total_particles):
@@ -238,9 +270,13 @@ def run_ours(args):
         n = len(state[0])
         sim = amc.Simulation(cfg, seed=17 + rank, device=local, max_particles=n)
         sim.set_state(*state)
+    clocks = ClockSampler(local)
+    clocks.launch()
+    sim.step_quiet(1)                       # (one extra untimed step: kernels loaded, allocations touched)
+    torch.cuda.synchronize()
+    clocks.mark_warmup()
     for _ in range(args.warmup):
         sim.step_quiet(1)
-    clocks = ClockSampler(local)
     barrier()
     clocks.start()
     t0 = time.perf_counter()
@@ -326,7 +362,7 @@ def run_ours(args):
         "collision_checks_per_s": {"reference_equivalent": checks_ref * world / (dev_ms / args.steps * 1e-3),
                                    "executed": checks_exec * world / (dev_ms / args.steps * 1e-3)},
         "collisions_per_step": collisions, "wall_s": wall,
-        "state_digest": {"digest": ["%016x" % d for d in digest[:2]], "particles_counted": digest[2], "steps": args.warmup + args.steps},
+        "state_digest": {"digest": ["%016x" % d for d in digest[:2]], "particles_counted": digest[2], "steps": 1 + args.warmup + args.steps},
     }
 
     # ---------------------------------------------------------------- config 2 beside it (rank 0, N = 1 only)
@@ -364,9 +400,13 @@ def run_slabs(args, world, rank, local, dev, hbm_peak, peak_src, barrier, max_ov
     # makes exactly its own slab and the 1-GPU replay below makes the very same job
     sim.init_synthetic(lambda kz: init_state.pore_spec(cfg, 17, keep_z=kz))
     n = sim.particles_per_rank()[0]
-    launches0 = sim.ranks[0].sim.last_timing()[1]
-    step(args.warmup)
     clocks = ClockSampler(local)
+    clocks.launch()
+    step(1)                                 # (one extra untimed step: kernels loaded, peers mapped, allocations touched)
+    launches0 = sim.ranks[0].sim.last_timing()[1]
+    barrier()
+    clocks.mark_warmup()
+    step(args.warmup)
     barrier()
     clocks.start()
     det0 = sim.ranks[0].sim.last_detect_ms()
@@ -425,13 +465,13 @@ def run_slabs(args, world, rank, local, dev, hbm_peak, peak_src, barrier, max_ov
     verify = {"skipped": "--no-verify"}
     if not args.no_verify:
         verify = {"digest": ["%016x" % d for d in digest[:2]], "particles_counted": digest[2],
-                  "steps": args.warmup + args.steps}
+                  "steps": 1 + args.warmup + args.steps}
         if rank == 0:
             try:
                 torch.cuda.empty_cache()
                 one = amc.Simulation(cfg, seed=17, device=local, max_particles=cfg.num_molecules)
                 one.init_synthetic(init_state.pore_spec(cfg, 17))
-                one.step_quiet(args.warmup + args.steps)
+                one.step_quiet(1 + args.warmup + args.steps)
                 d1 = one.state_digest()
                 one.close()
                 verify.update(digest_single_gpu=["%016x" % d for d in d1[:2]], identical_to_single_gpu=tuple(d1) == tuple(digest))
