@@ -90,7 +90,7 @@ EXPORTS = ("amc_create", "amc_destroy", "amc_last_error", "amc_abi_version", "am
            "amc_get_outputs_raw", "amc_set_outputs_raw", "amc_get_step_index",
            "amc_slab_enable", "amc_set_stream", "amc_set_ids", "amc_slab_advect", "amc_slab_sort", "amc_slab_pairs_begin",
            "amc_slab_group", "amc_slab_apply", "amc_slab_finish", "amc_slab_get_owned", "amc_state_digest",
-           "amc_slab_p2p_setup", "amc_slab_p2p_connect", "amc_slab_step", "amc_wall_operator", "amc_seed_relax")
+           "amc_slab_p2p_setup", "amc_slab_p2p_connect", "amc_slab_step", "amc_wall_operator", "amc_seed_relax", "amc_last_scatter_ms")
 
 
 def load_library():
@@ -489,6 +489,12 @@ class Simulation:
         n = C.c_int64(0)
         self._check(self.lib.amc_last_timing(self.h, ms, C.byref(n)), "amc_last_timing")
         return list(ms), int(n.value)
+
+    def last_scatter_ms(self):
+        """Device time (ms) of k_scatter_advect alone, summed over the steps of the last step() call."""
+        v = C.c_double(0.0)
+        self._check(self.lib.amc_last_scatter_ms(self.h, C.byref(v)), "amc_last_scatter_ms")
+        return float(v.value)
 
     def last_detect_ms(self):
         """Device time (ms) of the detection kernel alone, summed over the steps of the last step() call."""

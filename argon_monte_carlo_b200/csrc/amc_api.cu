@@ -62,6 +62,8 @@ struct amc_handle {
     int slab_phase = 0;                  // slab mode: PH_* bits of the step between amc_slab_advect and amc_slab_sort
     bool slab_det_pending = false;       // slab mode: events around k_detect recorded, not yet read
     double last_detect_ms = 0;
+    std::vector<cudaEvent_t> sc_events;  // two per step of the last amc_step chunk: around k_scatter_advect
+    double last_scatter_ms = 0;
     int64_t last_launches = 0;
     std::string error;
 
@@ -167,6 +169,7 @@ extern "C" int amc_destroy(amc_handle *h)
     for (void *q : h->allocs) cudaFree(q);
     for (cudaEvent_t e : h->events) cudaEventDestroy(e);
     for (cudaEvent_t e : h->det_events) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->sc_events) cudaEventDestroy(e);
     if (h->h_stats) cudaFreeHost(h->h_stats);
     if (h->aux) { cudaStreamSynchronize(h->aux); cudaStreamDestroy(h->aux); }
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
@@ -528,6 +531,7 @@ extern "C" int amc_step(amc_handle *h, int32_t n_steps, amc_step_stats *stats)
     const bool has_recap = p.kind != AMC_KIND_CUBE;
     memset(h->last_ms, 0, sizeof(h->last_ms));
     h->last_detect_ms = 0;
+    h->last_scatter_ms = 0;
     h->last_launches = 0;
     int done = 0;
     if (sweep && h->n) { // the sweep kernel addresses particles by id: keep slot == id
@@ -542,6 +546,11 @@ extern "C" int amc_step(amc_handle *h, int32_t n_steps, amc_step_stats *stats)
             cudaEvent_t e;
             CK(cudaEventCreate(&e));
             h->det_events.push_back(e);
+        }
+        while (h->sc_events.size() < (size_t)chunk * 2) {
+            cudaEvent_t e;
+            CK(cudaEventCreate(&e));
+            h->sc_events.push_back(e);
         }
         CK(cudaMemsetAsync(h->d_stats, 0, chunk * sizeof(StatsDev), h->stream));
         CK(cudaEventRecord(h->events[0], h->stream));
@@ -571,7 +580,9 @@ extern "C" int amc_step(amc_handle *h, int32_t n_steps, amc_step_stats *stats)
                     CK(cudaStreamWaitEvent(h->aux, h->ev_fork, 0));
                     if ((rc = prepare_pairs(h, h->aux)) != AMC_OK) return rc;
                     CK(cudaEventRecord(h->ev_join, h->aux));
+                    CK(cudaEventRecord(h->sc_events[2 * s], h->stream));
                     k_scatter_advect<false><<<grid_for(h->n, ADVECT_THREADS), ADVECT_THREADS, 0, h->stream>>>(p, phase);
+                    CK(cudaEventRecord(h->sc_events[2 * s + 1], h->stream));
                     CK(cudaGetLastError());
                     CK(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
                     std::swap(p.a, p.b);
@@ -604,6 +615,8 @@ extern "C" int amc_step(amc_handle *h, int32_t n_steps, amc_step_stats *stats)
                 if (!sweep) {
                     CK(cudaEventElapsedTime(&ms, h->det_events[2 * s], h->det_events[2 * s + 1]));
                     h->last_detect_ms += ms;
+                    CK(cudaEventElapsedTime(&ms, h->sc_events[2 * s], h->sc_events[2 * s + 1]));
+                    h->last_scatter_ms += ms;
                 }
             }
         for (int s = 0; s < chunk; s++) {
@@ -961,6 +974,13 @@ extern "C" int amc_last_detect_ms(amc_handle *h, double *ms)
 {
     if (!h || !ms) return AMC_E_INVALID;
     *ms = h->last_detect_ms;
+    return AMC_OK;
+}
+
+extern "C" int amc_last_scatter_ms(amc_handle *h, double *ms)
+{
+    if (!h || !ms) return AMC_E_INVALID;
+    *ms = h->last_scatter_ms;
     return AMC_OK;
 }
 

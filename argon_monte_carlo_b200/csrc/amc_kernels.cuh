@@ -19,7 +19,9 @@
 #define AMC_MV_CAP 32 /* particles one cell visit can move (reference scale: 2-6) */
 #define WALK_K 3 /* chains a thread of cell_process walks side by side */
 #define PAIR_K 3 /* candidates a thread of k_pairs_group has in flight during the gather */
+#ifndef SWEEP_THREADS
 #define SWEEP_THREADS 512
+#endif
 
 __device__ __forceinline__ void load_part(const Arrays &a, int64_t s, Part &q)
 {
@@ -267,13 +269,16 @@ __global__ void __launch_bounds__(ADVECT_THREADS) k_slab_pack(const __grid_const
 // pass 1 of the fused step: owner cell of the position each particle will have after the step, and its
 // rank inside that cell (band particles first, see k_advect).  Slab mode: also decides which rank owns
 // the particle after the step and packs the records that travel (see k_advect for the protocol).
+#ifndef KEYS_OCC
+#define KEYS_OCC 6           /* resident CTAs per SM of k_keys: latency-bound by the rank atomic, 40 registers (7 and 8 measured: see profiles/r2/summary.md) */
+#endif
 #ifndef KEYS_OCC_SLAB
 #define KEYS_OCC_SLAB 6      /* resident CTAs per SM of the slab variant of k_keys (5 at 48 registers and 4 at 64 measured slower: latency-bound) */
 #endif
 #define AUX_GHOST_UP 1u      /* kept, and copied to the rank above */
 #define AUX_STAY_AS_GHOST 2u /* owned by the rank below from now on, the local copy stays as its ghost */
 template <bool SLAB>
-__global__ void __launch_bounds__(ADVECT_THREADS, SLAB ? KEYS_OCC_SLAB : 6) k_keys(const __grid_constant__ P p, const int phase)
+__global__ void __launch_bounds__(ADVECT_THREADS, SLAB ? KEYS_OCC_SLAB : KEYS_OCC) k_keys(const __grid_constant__ P p, const int phase)
 {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= (SLAB ? p.cap : p.n)) return;

@@ -307,6 +307,14 @@ def run_ours(args):
                 "avg_launch_ms": det_ms,
                 "traffic": traffic["bytes"] if traffic else None, "traffic_source": traffic["source"] if traffic else None}
     roofline["frac"] = roofline["achieved"] / hbm_peak
+    # the longest kernel of the step, for the record: k_scatter_advect streams the whole state once (93 B read + 85 B
+    # written per particle: the 162 B of state plus sort key, rank and particle id)
+    sc_ms = sim.last_scatter_ms() / args.steps
+    sc_traffic = ncu_traffic("k_scatter_advect", n)
+    roofline_scatter = {"bound": "hbm", "kernel": "k_scatter_advect (the timestep on the way to the sorted slot, 1 launch per step)",
+                        "achieved": 178.0 * n / (sc_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s", "algorithmic_bytes_per_launch": 178.0 * n,
+                        "avg_launch_ms": sc_ms, "traffic": sc_traffic["bytes"] if sc_traffic else None}
+    roofline_scatter["frac"] = roofline_scatter["achieved"] / hbm_peak
     whole = {"achieved": B_STEP * n * args.steps / (ms[4] * 1e-3) / 1e9, "unit": "GB/s"}
     whole["frac"] = whole["achieved"] / hbm_peak
 
@@ -356,7 +364,7 @@ def run_ours(args):
                    "parallelism": "1 domain per GPU" if world == 1 else "%d independent domains (replicas)" % world,
                    "l2": "inputs larger than L2"},
         "clocks": clk, "e2e": e2e, "gpu_launches": launches,
-        "roofline": roofline, "roofline_whole_step": whole,
+        "roofline": roofline, "roofline_longest_kernel": roofline_scatter, "roofline_whole_step": whole,
         "phases_ms_per_step": {"keys": ms[0] / args.steps, "scan_scatter_advect": ms[1] / args.steps,
                                "pair_detect": det_ms, "pair_resolve": pair_ms - det_ms, "recapture": ms[3] / args.steps},
         "collision_checks_per_s": {"reference_equivalent": checks_ref * world / (dev_ms / args.steps * 1e-3),
@@ -368,6 +376,7 @@ def run_ours(args):
     # ---------------------------------------------------------------- config 2 beside it (rank 0, N = 1 only)
     if rank == 0 and world == 1 and not args.no_also:
         out["also"] = bench_pore_ref(args, hbm_peak)
+        out["also_configs"] = bench_other_configs(args)
     if rank == 0 and world == 1 and not args.no_verify:
         out["verify"] = verify_against_oracle(cfg, state if not args.device_init else None, local)
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -573,6 +582,61 @@ def reference_baseline(steps, kind="temp"):
         return stage.run(kind, steps, timeout=1500)
     except Exception as exc:
         return {"unavailable": str(exc)[-300:]}
+
+
+def bench_other_configs(args):
+    """The remaining single-GPU configurations of BASELINE.json beside the headline one, each a short measurement
+    (device time per step from CUDA events, L2 flushed between timed steps where the state fits into it):
+    cfg 1 Open_Air_Cube_MC.py as shipped (serial sweep), cfg 3 Temperature_Pore_MC.py (device RNG), cfg 4 the
+    10 M-particle cube with the colour-group schedule on one GPU."""
+    import torch
+    from argon_monte_carlo_b200 import amc, config, init_state
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
+    res = []
+
+    def timed(sim, k, do_flush):
+        sim.step_quiet(3)
+        tot = np.zeros(5)
+        for _ in range(k):
+            if do_flush:
+                flush.fill_(1)
+                torch.cuda.synchronize()
+            sim.step_quiet(1)
+            tot += np.array(sim.last_timing()[0])
+        return tot / k
+    try:
+        cfg = config.cube_config()
+        st = init_state.cube_initial_state(cfg)
+        sim = amc.Simulation(cfg)
+        sim.set_state(*st)
+        ms = timed(sim, 10, True)
+        sim.close()
+        res.append({"workload": "cfg1: Open_Air_Cube_MC.py as shipped, N=%d, serial cell sweep" % len(st[0]), "ms_per_step": ms[4],
+                    "value": len(st[0]) / (ms[4] * 1e-3), "unit": "particle-steps/s"})
+        cfg = config.pore_config(True)
+        st = init_state.pore_initial_state(cfg)
+        sim = amc.Simulation(cfg, seed=17)
+        sim.set_state(*st)
+        ms = timed(sim, 20, True)
+        sim.close()
+        res.append({"workload": "cfg3: Temperature_Pore_MC.py, N=%d, energized walls, device RNG" % len(st[0]), "ms_per_step": ms[4],
+                    "value": len(st[0]) / (ms[4] * 1e-3), "unit": "particle-steps/s"})
+        n = 10_000_000
+        base = config.cube_config()
+        scale = (n / base.num_molecules) ** (1.0 / 3.0)
+        n_sub = 2 * max(1, int(round(base.cube_x * scale / 21.43e-9 / 2)))
+        cfg = config.cube_config(scale=scale, n_sub=n_sub)
+        cfg.dt = cfg.tau / 1000
+        grid = config.Grid(nc=(n_sub,) * 3, c0=(0, 0, 0), d=(cfg.dx, cfg.dy, cfg.dz), band=(cfg.collision_range,) * 3)
+        sim = amc.Simulation(cfg, kind=amc.KIND_CUBE, pp_mode=amc.PP_GROUPS, grid=grid, max_particles=n)
+        sim.init_synthetic(init_state.cube_spec(cfg, n, 127))
+        ms = timed(sim, 10, False)
+        sim.close()
+        res.append({"workload": "cfg4: 10 M-particle Maxwellian cube, colour-group schedule, one GPU (2/4/8 GPUs: bench.py --workload cube --gpus N)",
+                    "ms_per_step": ms[4], "value": n / (ms[4] * 1e-3), "unit": "particle-steps/s"})
+    except Exception as exc:      # never lose the benchmark line over the side measurements
+        res.append({"error": str(exc)[-200:]})
+    return res
 
 
 def cpu_baseline(steps, warmup, particles=None):

@@ -240,6 +240,9 @@ int amc_last_timing(amc_handle *h, double ms[5], int64_t *launches);
  * neighbour search over every reference cell, Pore:168-174); the rest of [2] above is the ordered resolution.
  * Handles driven through the amc_slab_* entry points accumulate this time over steps instead. */
 int amc_last_detect_ms(amc_handle *h, double *ms);
+/* the same for k_scatter_advect, the kernel that carries out the timestep on the way to the sorted slot (the longest
+ * kernel of a step: reads 93 B and writes 85 B per particle) */
+int amc_last_scatter_ms(amc_handle *h, double *ms);
 
 /* ------------------------------------------------------------------------------------------------
  * Slab decomposition along z over several GPUs (one handle = one rank = the reference cells of the
