@@ -797,10 +797,14 @@ __device__ __forceinline__ void activate_moved(const P &p, CellShared &S, const 
     const int tid = threadIdx.x, nthreads = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
     const int n = S.n;
     for (int k = tid; k < n; k += nthreads)
-        if (S.mv[k]) { S.mvlist[atomicAdd(&S.nmv, 1)] = (uint16_t)k; touch_slot(p, S.slot[k]); }
+        if (S.mv[k]) S.mvlist[atomicAdd(&S.nmv, 1)] = (uint16_t)k;
     __syncthreads();
     const int nmv = S.nmv;
     const Arrays &A = p.a;
+    // the closing recapture has to look at every moved slot (touch_slot: two dependent global atomics): the last warp
+    // does that beside the activation work of the first ones instead of in front of it
+    if (warp == nwarps - 1)
+        for (int i = lane; i < nmv; i += 32) touch_slot(p, S.slot[S.mvlist[i]]);
     for (int base = 2 * warp; base < nmv; base += 2 * nwarps) {
         const int pw = (lane >> 3) & 1, g2 = lane & 7;
         int o[3] = {0, 0, 0}, q[3] = {0, 0, 0}, e = -1, e_old = -1, findable = 0, ok = 0;

@@ -28,6 +28,9 @@ def main():
     ap.add_argument("--particles", type=int, default=2_000_000)
     ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--kind", default="temp", choices=["temp", "pore"])
+    ap.add_argument("--dense", action="store_true",
+                    help="stress case: the small dense pore (overlapping start, thousands of collisions per step) with every cut "
+                         "inside an end cap, one-layer slabs included: many hand-over records per colour group, even cuts (pre-round)")
     ap.add_argument("--mode", default="p2p", choices=["p2p", "nccl"],
                     help="p2p: amc_slab_step (records written peer to peer by kernels); nccl: the step-wise entry points over torch.distributed")
     args = ap.parse_args()
@@ -37,24 +40,44 @@ def main():
     world, rank, local = int(os.environ["WORLD_SIZE"]), int(os.environ["RANK"]), int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    scale = (args.particles / 557649) ** (1.0 / 3.0)
-    cfg = config.pore_config(args.kind == "temp", scale=scale)
-    edges = cfg.grid.edge[2]
-    zs = init_state.synthetic_pore_chunk(cfg, 17, 0, 1 << 20)[3]
-    cuts = slab.balanced_cuts(zs, edges, world)
-    sim = slab.SlabSimulation(cfg, world, zs, transport=slab.DistTransport(), local_ranks=[rank], devices=[local], cuts=cuts,
-                              n_total=cfg.num_molecules, seed=17, p2p=args.mode == "p2p")
-    sim.init_synthetic(lambda kz: init_state.pore_spec(cfg, 17, keep_z=kz))
+    state = None
+    if args.dense:
+        cfg = config.pore_config(args.kind == "temp", scale=0.5)
+        state = init_state.synthetic_pore_state(cfg, seed=11)
+        nz = cfg.grid.nc[2]
+        cuts = {2: [0, 2, nz], 3: [0, 1, nz - 2, nz], 4: [0, 1, 2, nz - 1, nz]}.get(world)
+        if cuts is None:
+            cuts = [0, 1, 2, 3] + [nz - (world - 3) + k for k in range(world - 3)] if world > 4 else None
+        cuts = np.array(cuts, dtype=np.int32)
+        zs = state[2]
+        sim = slab.SlabSimulation(cfg, world, zs, transport=slab.DistTransport(), local_ranks=[rank], devices=[local], cuts=cuts,
+                                  seed=17, p2p=args.mode == "p2p")
+        layer = slab.owner_layer(zs, cfg.grid.edge[2])
+        m = (layer >= cuts[rank]) & (layer < cuts[rank + 1])
+        sim.set_local_state(np.nonzero(m)[0], *[a[m] for a in state], n_global=len(zs))
+    else:
+        scale = (args.particles / 557649) ** (1.0 / 3.0)
+        cfg = config.pore_config(args.kind == "temp", scale=scale)
+        edges = cfg.grid.edge[2]
+        zs = init_state.synthetic_pore_chunk(cfg, 17, 0, 1 << 20)[3]
+        cuts = slab.balanced_cuts(zs, edges, world)
+        sim = slab.SlabSimulation(cfg, world, zs, transport=slab.DistTransport(), local_ranks=[rank], devices=[local], cuts=cuts,
+                                  n_total=cfg.num_molecules, seed=17, p2p=args.mode == "p2p")
+        sim.init_synthetic(lambda kz: init_state.pore_spec(cfg, 17, keep_z=kz))
     dist.barrier()
     stats = sim.step_fused(args.steps, reduce=True) if args.mode == "p2p" else sim.step(args.steps, reduce=True)
     digest = sim.state_digest()
     per_rank = sim.particles_per_rank()[0]
     sim.close()
-    result = {"world": world, "particles": int(cfg.num_molecules), "steps": args.steps, "kind": args.kind, "mode": args.mode,
+    result = {"world": world, "particles": int(cfg.num_molecules if state is None else len(state[0])), "steps": args.steps, "kind": args.kind,
+              "mode": args.mode, "dense": bool(args.dense),
               "cuts": [int(c) for c in cuts], "ok": True, "mismatch": []}
     if rank == 0:
-        one = amc.Simulation(cfg, seed=17, device=local, max_particles=cfg.num_molecules)
-        one.init_synthetic(init_state.pore_spec(cfg, 17))
+        one = amc.Simulation(cfg, seed=17, device=local, max_particles=cfg.num_molecules if state is None else len(state[0]))
+        if state is None:
+            one.init_synthetic(init_state.pore_spec(cfg, 17))
+        else:
+            one.set_state(*state)
         ref = one.step(args.steps)
         ref_digest = one.state_digest()
         one.close()

@@ -39,3 +39,21 @@ def test_nccl_ranks_match_single_gpu(tmp_path, kind, mode):
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     res = json.loads(out.read_text())
     assert res["ok"] and res["digest"] == res["digest_single"] and res["digest_count"] == res["particles"]
+
+
+def test_nccl_dense_cuts_many_handovers(tmp_path):
+    """The stress case of tests/test_gpu_slab.py on real GPUs through amc_slab_step: small dense pore, every cut inside an
+    end cap (even cuts: the round before the first group is exercised), dozens of hand-over records per colour group."""
+    import torch
+    ngpu = torch.cuda.device_count()
+    if ngpu < 2:
+        pytest.skip("needs >= 2 GPUs (found %d)" % ngpu)
+    world = min(ngpu, 4)
+    out = tmp_path / "nccl_dense.json"
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr",
+           "127.0.0.1", "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "nccl_slab_worker.py"), str(out),
+           "--kind", "pore", "--mode", "p2p", "--dense", "--steps", "30"]
+    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    res = json.loads(out.read_text())
+    assert res["ok"] and res["digest"] == res["digest_single"] and res["digest_count"] == res["particles"]
