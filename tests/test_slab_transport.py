@@ -90,6 +90,12 @@ def _worker(rank, world, port, out):
         ok &= bool((r.bnd_recv_down == 0).all())
     tot = T.allreduce_sum(np.array([1.0 + rank, 2.0]))
     ok &= bool(np.allclose(tot, [sum(1.0 + k for k in range(world)), 2.0 * world]))
+    # checksum parts add up mod 2^64 (values close to 2^64 wrap), descriptors come back ordered by rank
+    big = (1 << 64) - 5
+    dg = T.allreduce_u64((big, 7 + rank, 1000 * (rank + 1)))
+    ok &= dg == ((big * world) % (1 << 64), sum(7 + k for k in range(world)), sum(1000 * (k + 1) for k in range(world)))
+    blobs = T.allgather_bytes(bytes([rank] * (3 + rank)))
+    ok &= blobs == [bytes([k] * (3 + k)) for k in range(world)]
     out[rank] = ok
     dist.destroy_process_group()
 
