@@ -47,6 +47,7 @@ struct amc_handle {
     int pair_grid = 148 * 5;    // persistent CTAs of k_pairs_group: SMs x resident CTAs per SM
     int pair_grid_fused = 148;  // the same for the fused (in-kernel hand-over) variant
     int det_grid = 148 * 4;     // persistent CTAs of k_detect
+    int32_t sweep_pass = 0;     // tag of the last pass of the event-driven cube sweep (P::sw_pass)
     // host-RNG parity mode: pending hits of the last amc_wall_hits_pending call
     int32_t *d_pend_count = nullptr, *d_pend_slot = nullptr, *d_pend_id = nullptr;
     double *d_pend_nrm = nullptr, *d_pend_colz = nullptr, *d_pend_dirs = nullptr, *d_pend_se = nullptr, *d_pend_dpz = nullptr, *d_pend_de = nullptr;
@@ -313,6 +314,20 @@ static int create_impl(amc_handle *h, const amc_config *cfg, int device)
         p.det_thr = std::nextafterf((float)thr, INFINITY);
         p.det_w = std::nextafterf((float)(1.05 * std::sqrt((double)p.det_thr)), INFINITY);
     }
+    {
+        // serial sweep of the cube stage: event-driven unless AMC_CUBE_SWEEP=serial asks for the plain one-CTA walk over
+        // every cell (kept as the cross-check and as the fall-back for a column that overflows its list)
+        const char *mode = getenv("AMC_CUBE_SWEEP");
+        if (cfg->pp_mode == AMC_PP_SWEEP && !(mode && strcmp(mode, "serial") == 0)) {
+            const int64_t ncols = (int64_t)cfg->nc[0] * cfg->nc[1];
+            p.sw_colcap = (int32_t)std::min<int64_t>(h->cap, std::max<int64_t>(512, 6 * h->cap / ncols + 64));
+            if (const char *cc = getenv("AMC_SWEEP_COLCAP")) p.sw_colcap = std::max(1, atoi(cc)); /* tests: force the hand-over to the plain sweep */
+            ALLOC(p.sw_col, (size_t)ncols * p.sw_colcap); ALLOC(p.sw_col_n, ncols);
+            ALLOC(p.sw_tag, h->cap); ALLOC(p.sw_ml, h->cap); ALLOC(p.sw_xs, h->cap); ALLOC(p.sw_ys, h->cap);
+            ALLOC(p.sw_state, 2);
+            CK(cudaMemset(p.sw_tag, 0, h->cap * sizeof(int32_t)));
+        }
+    }
     p.esc_cap = (int32_t)std::min<int64_t>(std::max<int64_t>(h->cap / 64, 4096), 1 << 22);
     ALLOC(p.esc_count, 1); ALLOC(p.esc_slot, p.esc_cap); ALLOC(p.esc_cell, (size_t)p.esc_cap * 8); ALLOC(p.esc_next, (size_t)p.esc_cap * 8);
     CK(cudaMemset(p.esc_count, 0, sizeof(int32_t)));
@@ -489,7 +504,20 @@ static int run_pairs(amc_handle *h, int64_t *launches, bool prepared = false)
 {
     P &p = h->p;
     if (p.pp_mode == AMC_PP_SWEEP) {
-        k_cube_sweep<<<1, SWEEP_THREADS, 0, h->stream>>>(p);
+        if (p.sw_col) { /* event-driven sweep: detection over all columns, then the flagged cells in sweep order */
+            if (h->sweep_pass == 0x7fffffff) { /* pass tags exhausted: start over with clean tags */
+                CK(cudaMemsetAsync(p.sw_tag, 0, h->cap * sizeof(int32_t), h->stream));
+                h->sweep_pass = 0;
+            }
+            p.sw_pass = ++h->sweep_pass;
+            const int ncell = p.nc[0] * p.nc[1] * p.nc[2];
+            CK(cudaMemsetAsync(p.cell_active, 0, (size_t)((ncell + 31) / 32) * sizeof(int32_t), h->stream));
+            CK(cudaMemsetAsync(p.sw_state, 0, 2 * sizeof(unsigned long long), h->stream));
+            k_sweep_detect<<<p.nc[0] * p.nc[1], SWD_THREADS, 0, h->stream>>>(p);
+            k_sweep_events<<<1, SWE_THREADS, 0, h->stream>>>(p);
+            if (launches) *launches += 2;
+        }
+        k_cube_sweep<<<1, SWEEP_THREADS, 0, h->stream>>>(p); /* with the event-driven sweep: only when a column list overflowed */
         if (launches) *launches += 1;
     } else {
         if (!prepared) {

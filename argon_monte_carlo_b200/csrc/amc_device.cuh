@@ -167,6 +167,15 @@ struct P {
     int32_t *esc_next; /* [esc_cap][8] next entry (+ 2) on the list of that cell, < 2 = end */
     StatsDev *stats;
     StatsDev *stats_prev; /* counters of the previous step (recapture fused into the next step's k_advect) */
+    /* ---- event-driven serial sweep of the cube stage (k_sweep_detect / k_sweep_events); null: the plain serial sweep */
+    int32_t *sw_col;      /* [columns][sw_colcap] particles inside the x and y masks of each (x layer, y layer) column before the sweep */
+    int32_t *sw_col_n;    /* [columns] */
+    int32_t sw_colcap;
+    int32_t sw_pass;      /* tag of the current pass (sw_tag) */
+    int32_t *sw_tag;      /* [cap] == sw_pass: a collision of this pass has moved the particle */
+    int32_t *sw_ml;       /* [cap] the moved particles of this pass */
+    double *sw_xs, *sw_ys; /* [cap] moved particles: the x the current layer's mask saw, the y the current column's mask saw */
+    unsigned long long *sw_state; /* [0] != 0: a column list overflowed, the plain sweep takes over; [1] pair tests of pass 1 */
 };
 
 // ---------------------------------------------------------------- deterministic accumulation

@@ -1616,6 +1616,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_cube_sweep(const __grid_const
     const int tid = threadIdx.x;
     const Arrays &A = p.a;
     int32_t *lx = p.key, *lxy = p.rank;
+    if (p.sw_col && !p.sw_state[0]) return; /* the event-driven sweep (k_sweep_detect / k_sweep_events) did this pass */
     if (tid == 0) { S.nexec = 0; S.nref = 0; }
     for (int c = tid; c < AMC_XBINS + 2; c += SWEEP_THREADS) S.head[c] = 0;
     for (int xl = 0; xl < p.nc[0]; xl++) {
@@ -1673,6 +1674,227 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_cube_sweep(const __grid_const
     }
     if (tid == 0) {
         if (S.nref) atomicAdd(&p.stats->checks_ref, S.nref);
+        if (S.nexec) atomicAdd(&p.stats->checks_exec, (unsigned long long)S.nexec);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Event-driven form of the same serial sweep.  A cell visit changes nothing unless two members overlap, and a
+// cell's members only change when a collision moves one of them, so of the 3,375 visits per timestep of the
+// shipped cube ~60 matter.  Pass 1 (k_sweep_detect, one CTA per (x layer, y layer) column, all columns side by
+// side) takes the positions as they are before the sweep: per column the particles inside the x and y masks, per
+// cell the member count n0 and whether two members overlap (exact test) -> bitmap of flagged cells.  Pass 2
+// (k_sweep_events, one CTA) walks the flagged cells in sweep order with cell_process; every particle a visit moved
+// flags the LATER cells that hold it now or held it before the visit (their member set changed: a new overlap can
+// arise and the reference-equivalent test counter needs the new count).  A skipped cell has, when the reference
+// visits it, exactly the members pass 1 saw and no overlapping pair.
+//
+// The reference takes the x mask once per x layer, the y mask once per column and the z mask per cell, each from
+// the positions live at that moment (Cube:233,235,237), so a particle moved inside a layer is still seen at its old
+// x by the rest of that layer.  Moved particles (sw_tag == sw_pass, listed in sw_ml) therefore carry snapshots:
+// sw_xs = the x the current layer's mask saw, sw_ys = the y the current column's mask saw, refreshed from the live
+// position when the walk enters a new layer / column.  Everything else has not moved: live == what the masks saw.
+// tests/cube_events_model.py is the Python restatement, checked against the oracle's serial sweep on the CPU.
+#define SWD_THREADS 256
+#define SWE_THREADS 256
+
+// cells k of axis a with lo[k] < v < edge[k+1]: the owner cell and, inside its low-side band, the next one
+__device__ __forceinline__ int axis_cells(const P &p, const int a, const double v, int out[2])
+{
+    const int nc = p.nc[a];
+    const int o = owner_axis(p.edge[a], nc, p.e0[a], p.inv_d[a], v); /* -1 below edge[0], nc at / above edge[nc] or NaN */
+    if (o >= nc) return 0;
+    int cnt = 0;
+    if (o >= 0 && p.lo[a][o] < v) out[cnt++] = o;
+    if (o + 1 < nc && p.lo[a][o + 1] < v) out[cnt++] = o + 1;
+    return cnt;
+}
+
+__global__ void __launch_bounds__(SWD_THREADS) k_sweep_detect(const __grid_constant__ P p)
+{
+    __shared__ double sx[AMC_MAX_MEMBERS], sy[AMC_MAX_MEMBERS], sz[AMC_MAX_MEMBERS];
+    __shared__ int s_n, s_m;
+    const int tid = threadIdx.x;
+    const Arrays &A = p.a;
+    const int col = blockIdx.x, xl = col / p.nc[1], yl = col % p.nc[1];
+    int32_t *list = p.sw_col + (size_t)col * p.sw_colcap;
+    if (tid == 0) s_n = 0;
+    __syncthreads();
+    {
+        const double lox = p.lo[0][xl], hix = p.edge[0][xl + 1], loy = p.lo[1][yl], hiy = p.edge[1][yl + 1];
+        for (int64_t i = tid; i < p.n; i += SWD_THREADS) {
+            const double x = A.x[i];
+            if (!(lox < x && x < hix)) continue;
+            const double y = A.y[i];
+            if (!(loy < y && y < hiy)) continue;
+            const int k = atomicAdd(&s_n, 1);
+            if (k < p.sw_colcap) list[k] = (int32_t)i;
+        }
+    }
+    __syncthreads();
+    int ncol = s_n;
+    if (ncol > p.sw_colcap) { /* more than the list holds: this pass is left to the plain sweep */
+        if (tid == 0) atomicExch(&p.sw_state[0], 1ull);
+        ncol = p.sw_colcap;
+    }
+    if (tid == 0) p.sw_col_n[col] = ncol;
+    unsigned long long nref = 0; /* thread 0 */
+    for (int zl = 0; zl < p.nc[2]; zl++) {
+        if (tid == 0) s_m = 0;
+        __syncthreads();
+        const double loz = p.lo[2][zl], hiz = p.edge[2][zl + 1];
+        for (int k = tid; k < ncol; k += SWD_THREADS) {
+            const int i = list[k];
+            const double z = A.z[i];
+            if (loz < z && z < hiz) {
+                const int m = atomicAdd(&s_m, 1);
+                if (m < AMC_MAX_MEMBERS) { sx[m] = A.x[i]; sy[m] = A.y[i]; sz[m] = z; }
+            }
+        }
+        __syncthreads();
+        const int nm = s_m;
+        const int cell = (xl * p.nc[1] + yl) * p.nc[2] + zl;
+        int hit = nm > AMC_MAX_MEMBERS; /* the visit reports the overflow */
+        if (!hit)
+            for (int a = tid; a < nm; a += SWD_THREADS)
+                for (int b = 0; b < a; b++)
+                    if (overlap(p, sx[a], sy[a], sz[a], sx[b], sy[b], sz[b])) hit = 1;
+        hit = __syncthreads_or(hit);
+        if (tid == 0) {
+            p.cell_n[cell] = nm;
+            nref += (unsigned long long)nm * (nm - 1) / 2;
+            if (hit) atomicOr(reinterpret_cast<unsigned int *>(p.cell_active) + (cell >> 5), 1u << (cell & 31));
+        }
+    }
+    if (tid == 0 && nref) atomicAdd(&p.sw_state[1], nref);
+}
+
+__global__ void __launch_bounds__(SWE_THREADS) k_sweep_events(const __grid_constant__ P p)
+{
+    __shared__ CellShared S;
+    __shared__ int s_c, s_nml;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const Arrays &A = p.a;
+    if (p.sw_state[0]) return; /* a column list overflowed: k_cube_sweep does this pass */
+    unsigned int *bits = reinterpret_cast<unsigned int *>(p.cell_active);
+    const int ncell = p.nc[0] * p.nc[1] * p.nc[2], nwords = (ncell + 31) >> 5;
+    if (tid == 0) { S.nexec = 0; S.nref = 0; s_nml = 0; s_c = 0; }
+    for (int c = tid; c < AMC_XBINS + 2; c += SWE_THREADS) S.head[c] = 0;
+    int cur_xl = -1, cur_col = -1;
+    __syncthreads();
+    while (true) {
+        // ---- the next flagged cell at or behind the cursor (warp 0: 32 bitmap words per round)
+        if (tid < 32) {
+            const int c0 = s_c;
+            int found = -1;
+            for (int w0 = c0 >> 5; w0 < nwords && found < 0; w0 += 32) {
+                const int w = w0 + lane;
+                unsigned int v = w < nwords ? __ldcg(bits + w) : 0u; /* atomics land in L2 */
+                if (w == (c0 >> 5)) v &= ~0u << (c0 & 31);
+                const unsigned int bal = __ballot_sync(0xffffffffu, v != 0u);
+                if (bal) {
+                    const int src = __ffs(bal) - 1;
+                    const unsigned int vv = __shfl_sync(0xffffffffu, v, src);
+                    found = ((w0 + src) << 5) + __ffs(vv) - 1;
+                }
+            }
+            if (lane == 0) s_c = found >= 0 && found < ncell ? found : -1;
+        }
+        __syncthreads();
+        const int cell = s_c;
+        if (cell < 0) break;
+        const int zl = cell % p.nc[2], yl = (cell / p.nc[2]) % p.nc[1], xl = cell / (p.nc[2] * p.nc[1]);
+        const int col = xl * p.nc[1] + yl;
+        // ---- a new layer / column takes its mask from the live positions (Cube:233,235)
+        if (xl != cur_xl || col != cur_col) {
+            const int nml = s_nml;
+            for (int k = tid; k < nml; k += SWE_THREADS) {
+                const int i = p.sw_ml[k];
+                if (xl != cur_xl) p.sw_xs[i] = A.x[i];
+                p.sw_ys[i] = A.y[i];
+            }
+            cur_xl = xl; cur_col = col;
+        }
+        if (tid == 0) {
+            S.n = 0; S.ncand = 0; S.cand_lost = 0; S.use_hits = 0; S.nold = 0; S.nmv = 0;
+            S.org[0] = p.lo[0][xl]; S.org[1] = p.lo[1][yl]; S.org[2] = p.lo[2][zl];
+            float wd = (float)(p.edge[0][xl + 1] - p.lo[0][xl]);
+            int nb = (int)fminf((float)AMC_XBINS, floorf(wd / p.det_w));
+            if (nb < 1) nb = 1;
+            S.nb = nb; S.inv_w = (float)nb / wd;
+        }
+        __syncthreads();
+        // ---- members: the column's particles that have not moved, and the moved ones through their snapshots
+        {
+            const double lox = p.lo[0][xl], hix = p.edge[0][xl + 1], loy = p.lo[1][yl], hiy = p.edge[1][yl + 1];
+            const double loz = p.lo[2][zl], hiz = p.edge[2][zl + 1];
+            const int ncol = p.sw_col_n[col], nml = s_nml;
+            const int32_t *list = p.sw_col + (size_t)col * p.sw_colcap;
+            for (int k = tid; k < ncol + nml; k += SWE_THREADS) {
+                const int i = k < ncol ? list[k] : p.sw_ml[k - ncol];
+                const bool tagged = p.sw_tag[i] == p.sw_pass;
+                if (k < ncol && tagged) continue; /* comes through the moved list */
+                const double z = A.z[i];
+                if (!(loz < z && z < hiz)) continue;
+                const double x = A.x[i], y = A.y[i];
+                const double mx = tagged ? p.sw_xs[i] : x, my = tagged ? p.sw_ys[i] : y;
+                if (!(lox < mx && mx < hix && loy < my && my < hiy)) continue;
+                const int m = atomicAdd(&S.n, 1);
+                if (m < AMC_MAX_MEMBERS) { S.x[m] = x; S.y[m] = y; S.z[m] = z; S.id[m] = i; S.slot[m] = i; S.src[m] = -1; }
+            }
+        }
+        __syncthreads();
+        if (S.n > AMC_MAX_MEMBERS) {
+            if (tid == 0) { atomicAdd(&p.stats->cell_overflow, 1ull); S.n = AMC_MAX_MEMBERS; }
+            __syncthreads();
+        }
+        if (tid == 0) { /* pass 1 counted this cell with the members it saw */
+            const unsigned long long n0 = (unsigned long long)p.cell_n[cell];
+            S.nref -= n0 * (n0 - 1) / 2;
+        }
+        const int n = S.n;
+        if (n >= 2) {
+            cell_process(p, S, 0, cell);
+            __syncthreads();
+            // ---- every moved member: snapshot at its first move of the pass, and the later cells that hold it now or
+            // held it before this visit
+            if (S.nold > 0) {
+                for (int k = tid; k < n; k += SWE_THREADS) {
+                    const int io = (int)S.mv[k] - 1;
+                    if (io < 0) continue;
+                    double t[2][3];
+                    if (io < AMC_MV_CAP) { t[0][0] = S.ox[io]; t[0][1] = S.oy[io]; t[0][2] = S.oz[io]; }
+                    else { const double *sp = p.mv_spill + ((size_t)blockIdx.x * AMC_MAX_MEMBERS + io) * 3; t[0][0] = sp[0]; t[0][1] = sp[1]; t[0][2] = sp[2]; }
+                    t[1][0] = S.x[k]; t[1][1] = S.y[k]; t[1][2] = S.z[k];
+                    const int i = S.id[k];
+                    if (p.sw_tag[i] != p.sw_pass) {
+                        p.sw_tag[i] = p.sw_pass;
+                        p.sw_xs[i] = t[0][0]; p.sw_ys[i] = t[0][1];
+                        p.sw_ml[atomicAdd(&s_nml, 1)] = i;
+                    }
+                    for (int w = 0; w < 2; w++) {
+                        int cx[2], cy[2], cz[2];
+                        const int nx = axis_cells(p, 0, t[w][0], cx), ny = axis_cells(p, 1, t[w][1], cy), nz = axis_cells(p, 2, t[w][2], cz);
+                        for (int c = 0; c < nz; c++) /* same column (x and y masks are this visit's), later cell */
+                            if (cz[c] > zl) { const int cc = col * p.nc[2] + cz[c]; atomicOr(bits + (cc >> 5), 1u << (cc & 31)); }
+                        for (int b = 0; b < ny; b++) /* same layer, later column */
+                            if (cy[b] > yl)
+                                for (int c = 0; c < nz; c++) { const int cc = (xl * p.nc[1] + cy[b]) * p.nc[2] + cz[c]; atomicOr(bits + (cc >> 5), 1u << (cc & 31)); }
+                        for (int a = 0; a < nx; a++) /* later layer */
+                            if (cx[a] > xl)
+                                for (int b = 0; b < ny; b++)
+                                    for (int c = 0; c < nz; c++) { const int cc = (cx[a] * p.nc[1] + cy[b]) * p.nc[2] + cz[c]; atomicOr(bits + (cc >> 5), 1u << (cc & 31)); }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (tid == 0) s_c = cell + 1;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        const unsigned long long nref = S.nref + p.sw_state[1];
+        if (nref) atomicAdd(&p.stats->checks_ref, nref);
         if (S.nexec) atomicAdd(&p.stats->checks_exec, (unsigned long long)S.nexec);
     }
 }

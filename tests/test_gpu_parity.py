@@ -117,9 +117,17 @@ def test_temp_device_rng_bit_exact(oracle, temp_cfg, temp_init):
     sim.close()
 
 
-def test_cube_steps_bit_exact(oracle, cube_cfg, cube_init):
+@pytest.mark.parametrize("sweep", ["events", "serial", "handover"])
+def test_cube_steps_bit_exact(oracle, cube_cfg, cube_init, sweep, monkeypatch):
+    """Open_Air_Cube_MC.py as shipped, serial cell sweep (Cube:232-336).  events: the event-driven sweep
+    (k_sweep_detect / k_sweep_events, the default); serial: the plain one-CTA walk over all 3,375 cells
+    (AMC_CUBE_SWEEP=serial); handover: column lists too small for the gas, so every pass is handed to the plain walk."""
     from argon_monte_carlo_b200 import amc
     from oracle import steps
+    if sweep == "serial":
+        monkeypatch.setenv("AMC_CUBE_SWEEP", "serial")
+    if sweep == "handover":
+        monkeypatch.setenv("AMC_SWEEP_COLCAP", "16")
     st = oracle.ParticleState(*cube_init)
     sim = amc.Simulation(cube_cfg, taps=amc.TAP_PAIRS | amc.TAP_PATHS)
     sim.set_state(*cube_init)

@@ -106,3 +106,31 @@ def test_clock_sampler_selects_rows_by_timestamp():
         datetime.datetime = FakeDT.__mro__[1]
     assert out["window"] == "timed region" and out["sm_mhz"] == 1965.0 and out["sm_max_mhz"] == 1965.0
     assert out["samples"] >= 19 and out["reasons"] == ["sw_power_cap"]
+
+
+def test_event_driven_cube_sweep_model_equals_the_serial_sweep(oracle, cube_cfg, cube_init):
+    """k_sweep_detect / k_sweep_events walk only the cells that can hold a collision (~60 of 3,375 per timestep) and
+    reproduce the reference's stale layer masks through per-particle snapshots.  Their Python restatement
+    (tests/cube_events_model.py) must give the oracle's serial sweep (Cube:232-336) bit for bit: state, collision
+    count, reference-equivalent test counter, completed paths, pair list."""
+    import cube_events_model as M
+    from oracle import steps
+    names = ("x", "y", "z", "vx", "vy", "vz", "dist", "dist_x", "dist_y", "dist_z", "flag")
+    st, mine = oracle.ParticleState(*cube_init), oracle.ParticleState(*cube_init)
+    visits = 0
+    for k in range(8):
+        sink, pairs = oracle.PathSink(), oracle.PairSink()
+        r = steps.cube_step(st, cube_cfg, sink, pairs)
+        oracle.drift(mine, cube_cfg.dt, False)
+        oracle.cube_walls(mine, cube_cfg.cube_x, cube_cfg.cube_y, cube_cfg.cube_z)
+        d = {nm: getattr(mine, nm) for nm in names}
+        ncol, checks, paths, prs, v = M.sweep_events(d, cube_cfg.grid, cube_cfg.collision_range, cube_cfg.argon_mass)
+        assert (ncol, checks) == (r["pp_collisions"], r["checks"]), k
+        for nm in names:
+            assert np.array_equal(getattr(mine, nm), getattr(st, nm)), (k, nm)
+        ref_paths = np.array(sink.arrays()).T.reshape(-1, 4)
+        assert np.array_equal(np.sort(np.array(paths).reshape(-1, 4), axis=0), np.sort(ref_paths, axis=0))
+        hi, lo, _, cell = pairs.arrays()
+        assert [(int(a), int(b), int(c)) for a, b, c in zip(hi, lo, cell)] == prs     # same pairs, same order, same cells
+        visits += v
+    assert visits < 8 * 150            # the point of the exercise: a few dozen cell visits per step, not 3,375
