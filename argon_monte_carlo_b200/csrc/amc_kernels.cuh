@@ -1722,13 +1722,19 @@ __global__ void __launch_bounds__(SWD_THREADS) k_sweep_detect(const __grid_const
     __syncthreads();
     {
         const double lox = p.lo[0][xl], hix = p.edge[0][xl + 1], loy = p.lo[1][yl], hiy = p.edge[1][yl + 1];
-        for (int64_t i = tid; i < p.n; i += SWD_THREADS) {
-            const double x = A.x[i];
-            if (!(lox < x && x < hix)) continue;
-            const double y = A.y[i];
-            if (!(loy < y && y < hiy)) continue;
-            const int k = atomicAdd(&s_n, 1);
-            if (k < p.sw_colcap) list[k] = (int32_t)i;
+        for (int64_t i0 = tid; i0 < p.n; i0 += 4 * SWD_THREADS) { /* four particles per thread and round: their loads travel together */
+            double x[4], y[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int64_t i = i0 + u * SWD_THREADS;
+                x[u] = i < p.n ? A.x[i] : hix; y[u] = i < p.n ? A.y[i] : hiy;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (!(lox < x[u] && x[u] < hix && loy < y[u] && y[u] < hiy)) continue;
+                const int k = atomicAdd(&s_n, 1);
+                if (k < p.sw_colcap) list[k] = (int32_t)(i0 + u * SWD_THREADS);
+            }
         }
     }
     __syncthreads();
@@ -1832,11 +1838,11 @@ __global__ void __launch_bounds__(SWE_THREADS) k_sweep_events(const __grid_const
             const int32_t *list = p.sw_col + (size_t)col * p.sw_colcap;
             for (int k = tid; k < ncol + nml; k += SWE_THREADS) {
                 const int i = k < ncol ? list[k] : p.sw_ml[k - ncol];
-                const bool tagged = p.sw_tag[i] == p.sw_pass;
+                const int tag = p.sw_tag[i];                                /* one round trip for all four */
+                const double z = A.z[i], x = A.x[i], y = A.y[i];
+                const bool tagged = tag == p.sw_pass;
                 if (k < ncol && tagged) continue; /* comes through the moved list */
-                const double z = A.z[i];
                 if (!(loz < z && z < hiz)) continue;
-                const double x = A.x[i], y = A.y[i];
                 const double mx = tagged ? p.sw_xs[i] : x, my = tagged ? p.sw_ys[i] : y;
                 if (!(lox < mx && mx < hix && loy < my && my < hiy)) continue;
                 const int m = atomicAdd(&S.n, 1);
