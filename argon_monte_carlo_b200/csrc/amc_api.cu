@@ -99,8 +99,9 @@ template <typename T> static int dev_alloc(amc_handle *h, T **ptr, size_t count)
 
 static int alloc_arrays(amc_handle *h, Arrays &a, int64_t n)
 {
-    ALLOC(a.x, n); ALLOC(a.y, n); ALLOC(a.z, n); ALLOC(a.vx, n); ALLOC(a.vy, n); ALLOC(a.vz, n);
-    ALLOC(a.d, n); ALLOC(a.dx, n); ALLOC(a.dy, n); ALLOC(a.dz, n); ALLOC(a.flag, n); ALLOC(a.id, n);
+    ALLOC(a.pos, n); /* cudaMalloc returns 256-byte aligned blocks: every record is 32-byte aligned */
+    ALLOC(a.vx, n); ALLOC(a.vy, n); ALLOC(a.vz, n);
+    ALLOC(a.d, n); ALLOC(a.dx, n); ALLOC(a.dy, n); ALLOC(a.dz, n);
     return AMC_OK;
 }
 
@@ -396,17 +397,19 @@ extern "C" int amc_set_state(amc_handle *h, int64_t n, const double *x, const do
     if (n && (!x || !y || !z || !vx || !vy || !vz)) return h->fail(AMC_E_INVALID, "null position/velocity array");
     CK(cudaSetDevice(h->device));
     Arrays &a = h->p.a;
+    // positions and flags arrive as separate arrays: staged in the SoaView over the idle b records, then packed
+    const SoaView v = soa_view(h->p.b.pos, h->cap);
     const double *src[10] = {x, y, z, vx, vy, vz, dist, dist_x, dist_y, dist_z};
-    double *dst[10] = {a.x, a.y, a.z, a.vx, a.vy, a.vz, a.d, a.dx, a.dy, a.dz};
+    double *dst[10] = {v.x, v.y, v.z, a.vx, a.vy, a.vz, a.d, a.dx, a.dy, a.dz};
     for (int k = 0; k < 10; k++) {
         if (src[k]) CK(cudaMemcpyAsync(dst[k], src[k], n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
         else CK(cudaMemsetAsync(dst[k], 0, n * sizeof(double), h->stream));
     }
-    if (flag) CK(cudaMemcpyAsync(a.flag, flag, n, cudaMemcpyHostToDevice, h->stream));
-    else CK(cudaMemsetAsync(a.flag, 0, n, h->stream));
+    if (flag) CK(cudaMemcpyAsync(v.flag, flag, n, cudaMemcpyHostToDevice, h->stream));
+    else CK(cudaMemsetAsync(v.flag, 0, n, h->stream));
     h->n = n;
     h->p.n = n;
-    if (n) k_iota<<<grid_for(n, ADVECT_THREADS), ADVECT_THREADS, 0, h->stream>>>(a.id, n); // slot == particle index
+    if (n) k_pack_pos<<<grid_for(n, ADVECT_THREADS), ADVECT_THREADS, 0, h->stream>>>(h->p, 0); // slot == particle index
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(h->stream));
     return AMC_OK;
@@ -460,11 +463,15 @@ extern "C" int amc_get_state(amc_handle *h, double *x, double *y, double *z, dou
     int rc = unsort(h);
     if (rc != AMC_OK) return rc;
     Arrays &a = h->p.a;
+    // the records leave as separate arrays: unpacked into the SoaView over the b records (scratch after the unsort)
+    const SoaView v = soa_view(h->p.b.pos, h->cap);
+    if (h->n) k_unpack_pos<<<grid_for(h->n, ADVECT_THREADS), ADVECT_THREADS, 0, h->stream>>>(h->p);
+    CK(cudaGetLastError());
     double *dst[10] = {x, y, z, vx, vy, vz, dist, dist_x, dist_y, dist_z};
-    const double *src[10] = {a.x, a.y, a.z, a.vx, a.vy, a.vz, a.d, a.dx, a.dy, a.dz};
+    const double *src[10] = {v.x, v.y, v.z, a.vx, a.vy, a.vz, a.d, a.dx, a.dy, a.dz};
     for (int k = 0; k < 10; k++)
         if (dst[k]) CK(cudaMemcpyAsync(dst[k], src[k], h->n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    if (flag) CK(cudaMemcpyAsync(flag, a.flag, h->n, cudaMemcpyDeviceToHost, h->stream));
+    if (flag) CK(cudaMemcpyAsync(flag, v.flag, h->n, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return AMC_OK;
 }
@@ -1033,7 +1040,10 @@ extern "C" int amc_set_ids(amc_handle *h, const int64_t *ids)
         if (ids[i] < 0 || ids[i] > 0x7fffffffLL) return h->fail(AMC_E_INVALID, "particle id out of range");
         v[(size_t)i] = (int32_t)ids[i];
     }
-    CK(cudaMemcpyAsync(h->p.a.id, v.data(), h->n * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    int32_t *stage = h->p.key; /* scratch until the next sort */
+    CK(cudaMemcpyAsync(stage, v.data(), h->n * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    if (h->n) k_set_ids<<<grid_for(h->n, ADVECT_THREADS), ADVECT_THREADS, 0, h->stream>>>(h->p, stage);
+    CK(cudaGetLastError());
     CK(cudaStreamSynchronize(h->stream));
     return AMC_OK;
 }
@@ -1269,13 +1279,14 @@ extern "C" int amc_slab_get_owned(amc_handle *h, int64_t cap, int64_t *n, int64_
     if (n) *n = c;
     if (c > cap) return h->fail(AMC_E_CAPACITY, "caller buffers too small for the owned particles");
     Arrays &b = p.b;
+    const SoaView v = soa_view(b.pos, h->cap); /* k_compact_owned wrote positions, ids and flags as separate arrays */
     double *dst[10] = {x, y, z, vx, vy, vz, dist, dist_x, dist_y, dist_z};
-    const double *src[10] = {b.x, b.y, b.z, b.vx, b.vy, b.vz, b.d, b.dx, b.dy, b.dz};
+    const double *src[10] = {v.x, v.y, v.z, b.vx, b.vy, b.vz, b.d, b.dx, b.dy, b.dz};
     for (int k = 0; k < 10; k++)
         if (dst[k] && c) CK(cudaMemcpyAsync(dst[k], src[k], c * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    if (flag && c) CK(cudaMemcpyAsync(flag, b.flag, c, cudaMemcpyDeviceToHost, h->stream));
+    if (flag && c) CK(cudaMemcpyAsync(flag, v.flag, c, cudaMemcpyDeviceToHost, h->stream));
     std::vector<int32_t> tmp((size_t)c);
-    if (ids && c) CK(cudaMemcpyAsync(tmp.data(), b.id, c * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    if (ids && c) CK(cudaMemcpyAsync(tmp.data(), v.id, c * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     if (ids) for (int32_t k = 0; k < c; k++) ids[k] = tmp[(size_t)k];
     return AMC_OK;

@@ -36,11 +36,51 @@
 enum { AMC_DRY = 0, AMC_LIVE = 1, AMC_QUIET = 2 };
 enum { PH_DRIFT = 1, PH_WALLS = 2, PH_RECAP = 4, PH_KEYS = 8, PH_SAVE_PRIOR = 16, PH_LOAD_PRIOR = 32, PH_RECAP_POST = 64 };
 
-struct Arrays {
-    double *x, *y, *z, *vx, *vy, *vz, *d, *dx, *dy, *dz;
-    uint8_t *flag;
-    int32_t *id;
+// Position record: what the neighbour search, the membership tests and the sort read together is stored together --
+// one 32-byte, 32-byte-aligned record per particle, moved with single 256-bit accesses (LDG.E.256 / STG.E.256) and,
+// being contiguous per owner cell, with bulk copies (cp.async.bulk) into shared memory by the detection pass.
+// Velocities and the four path accumulators stay structure-of-arrays: only the streaming passes and the (rare)
+// collisions touch them.
+struct __align__(32) PosRec {
+    double x, y, z;
+    int32_t id;    /* original particle index */
+    uint32_t flag; /* AMC_FLAG_* */
 };
+struct Arrays {
+    PosRec *pos;
+    double *vx, *vy, *vz, *d, *dx, *dy, *dz;
+};
+// separate x / y / z / id / flag arrays laid over an idle record array of `cap` records (29 of its 32 bytes per particle):
+// staging between the C ABI's arrays and the records
+struct SoaView {
+    double *x, *y, *z;
+    int32_t *id;
+    uint8_t *flag;
+};
+__host__ __device__ __forceinline__ SoaView soa_view(PosRec *base, int64_t cap)
+{
+    SoaView v;
+    v.x = reinterpret_cast<double *>(base); v.y = v.x + cap; v.z = v.y + cap;
+    v.id = reinterpret_cast<int32_t *>(v.z + cap); v.flag = reinterpret_cast<uint8_t *>(v.id + cap);
+    return v;
+}
+// the whole record with one 256-bit store (sm_100: st.global.v4.b64 -> STG.E.256; the compiler emits the 256-bit LOAD
+// for a plain record read by itself, but splits a store whose fields come from different registers)
+__device__ __forceinline__ void st_pos(PosRec *p, const double x, const double y, const double z, const int32_t id, const uint32_t flag)
+{
+    const unsigned long long w = (unsigned long long)(uint32_t)id | ((unsigned long long)flag << 32);
+    asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(x), "d"(y), "d"(z), "l"(w) : "memory");
+}
+// a position record past L1 (producer -> consumer edges inside one launch, see k_pairs_group)
+__device__ __forceinline__ PosRec ldcg_pos(const PosRec *p)
+{
+    PosRec r;
+    unsigned long long w;
+    asm volatile("ld.global.cg.v2.b64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+    asm volatile("ld.global.cg.v2.b64 {%0, %1}, [%2];" : "=d"(r.z), "=l"(w) : "l"(reinterpret_cast<const char *>(p) + 16));
+    r.id = (int32_t)(uint32_t)w; r.flag = (uint32_t)(w >> 32);
+    return r;
+}
 
 struct StatsDev {
     unsigned long long wall_hits[AMC_NUM_CASES];

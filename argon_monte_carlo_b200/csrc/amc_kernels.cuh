@@ -23,15 +23,30 @@
 #define SWEEP_THREADS 512
 #endif
 
-__device__ __forceinline__ void load_part(const Arrays &a, int64_t s, Part &q)
+// the whole particle: the position record with one 256-bit load, the seven other values from their arrays; returns the id
+__device__ __forceinline__ int32_t load_part(const Arrays &a, int64_t s, Part &q)
 {
-    q.x = a.x[s]; q.y = a.y[s]; q.z = a.z[s]; q.vx = a.vx[s]; q.vy = a.vy[s]; q.vz = a.vz[s];
-    q.d = a.d[s]; q.dx = a.dx[s]; q.dy = a.dy[s]; q.dz = a.dz[s]; q.flag = a.flag[s];
+    const PosRec r = a.pos[s];
+    q.x = r.x; q.y = r.y; q.z = r.z; q.flag = r.flag;
+    q.vx = a.vx[s]; q.vy = a.vy[s]; q.vz = a.vz[s];
+    q.d = a.d[s]; q.dx = a.dx[s]; q.dy = a.dy[s]; q.dz = a.dz[s];
+    return r.id;
 }
+// the same back, in place (the record keeps its id: one 128-bit store for x and y, z and the flag word beside it)
 __device__ __forceinline__ void store_part(const Arrays &a, int64_t s, const Part &q)
 {
-    a.x[s] = q.x; a.y[s] = q.y; a.z[s] = q.z; a.vx[s] = q.vx; a.vy[s] = q.vy; a.vz[s] = q.vz;
-    a.d[s] = q.d; a.dx[s] = q.dx; a.dy[s] = q.dy; a.dz[s] = q.dz; a.flag[s] = (uint8_t)q.flag;
+    PosRec *r = a.pos + s;
+    *reinterpret_cast<double2 *>(r) = make_double2(q.x, q.y);
+    r->z = q.z; r->flag = q.flag & 0xffu;
+    a.vx[s] = q.vx; a.vy[s] = q.vy; a.vz[s] = q.vz;
+    a.d[s] = q.d; a.dx[s] = q.dx; a.dy[s] = q.dy; a.dz[s] = q.dz;
+}
+// to another slot: the full record (one 256-bit store)
+__device__ __forceinline__ void store_part_id(const Arrays &a, int64_t s, const Part &q, const int32_t id)
+{
+    st_pos(a.pos + s, q.x, q.y, q.z, id, q.flag & 0xffu);
+    a.vx[s] = q.vx; a.vy[s] = q.vy; a.vz[s] = q.vz;
+    a.d[s] = q.d; a.dx[s] = q.dx; a.dy[s] = q.dy; a.dz[s] = q.dz;
 }
 
 // rank of this lane among all particles incrementing `counter` (identified by `tag` within the warp):
@@ -59,13 +74,12 @@ __global__ void __launch_bounds__(ADVECT_THREADS, 4) k_advect(const __grid_const
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= p.n) return;
     Part q;
-    load_part(p.a, s, q);
+    const int32_t id = load_part(p.a, s, q);
     if (p.slab && (q.flag & AMC_FLAG_GHOST)) { // last step's copy of a neighbour's particle: drop it
         if (phase & PH_KEYS) { p.key[s] = p.ncell_pad + 1; p.rank[s] = ~atomicAdd(&p.rest_count[p.ncell_pad + 1], 1); }
         return;
     }
     q.flag &= AMC_FLAG_PATH;
-    int32_t id = p.a.id[s];
     if (phase & PH_RECAP_POST) { // recapture that closes the previous step's pair pass (Pore:550 / Temp:843-845)
         int cnt = p.kind == AMC_KIND_TEMP ? temp_oob(p.g, q) : 0;
         int moved = p.kind == AMC_KIND_TEMP ? temp_recapture(p.g, q) : pore_recapture(p.g, q);
@@ -263,7 +277,7 @@ __global__ void __launch_bounds__(ADVECT_THREADS) k_slab_pack(const __grid_const
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (to == p.srank || j >= min(p.xf_count[to], p.xf_capv[to])) return;
     const int2 e = p.xf_pack[p.xf_off[to] + 1 + j];
-    slab_pack(p, e.x, p.a.id[e.x], phase, to, j, (unsigned)e.y);
+    slab_pack(p, e.x, p.a.pos[e.x].id, phase, to, j, (unsigned)e.y);
 }
 
 // pass 1 of the fused step: owner cell of the position each particle will have after the step, and its
@@ -285,11 +299,12 @@ __global__ void __launch_bounds__(ADVECT_THREADS, SLAB ? KEYS_OCC_SLAB : KEYS_OC
     // slab mode: the particle count lives on the device; its load travels together with the particle's own loads
     // (slots behind the count are allocated, their contents are ignored)
     Part q;
-    q.x = p.a.x[s]; q.y = p.a.y[s]; q.z = p.a.z[s]; q.vx = p.a.vx[s]; q.vy = p.a.vy[s]; q.vz = p.a.vz[s];
+    const PosRec r0 = p.a.pos[s]; /* position, id and flag word: one 256-bit load */
+    q.x = r0.x; q.y = r0.y; q.z = r0.z; q.vx = p.a.vx[s]; q.vy = p.a.vy[s]; q.vz = p.a.vz[s];
     q.d = q.dx = q.dy = q.dz = 0.0; q.flag = 0;
-    const int32_t id = (p.kind == AMC_KIND_TEMP || SLAB) ? p.a.id[s] : 0; /* keys the device RNG of the energized walls */
+    const int32_t id = r0.id; /* keys the device RNG of the energized walls */
     if (SLAB) {
-        const unsigned fl0 = p.a.flag[s];
+        const unsigned fl0 = r0.flag;
         if (s >= cur_n(p)) return;
         if (fl0 & AMC_FLAG_GHOST) { // last step's copy of a neighbour's particle: drop it
             p.key[s] = p.ncell_pad + 1; p.rank[s] = ~atomicAdd(&p.rest_count[p.ncell_pad + 1], 1);
@@ -334,8 +349,7 @@ __global__ void __launch_bounds__(ADVECT_THREADS, 3) k_scatter_advect(const __gr
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= (SLAB ? p.cap : p.n)) return;
     Part q;
-    load_part(p.a, s, q);
-    const int32_t id = p.a.id[s];
+    const int32_t id = load_part(p.a, s, q);
     const int32_t k = p.key[s], r = p.rank[s];
     const int64_t n0 = SLAB ? cur_n(p) : p.n; /* slab mode: on the device, loaded together with the record */
     if (SLAB && s >= n0 + *p.n_in) return;
@@ -351,8 +365,7 @@ __global__ void __launch_bounds__(ADVECT_THREADS, 3) k_scatter_advect(const __gr
     const int64_t t = (int64_t)p.cell_start[k] + (r >= 0 ? r : p.band_count[k] + ~r);
     const unsigned fl = q.flag;
     q.flag = fl & (SLAB ? AMC_FLAG_KEEP : AMC_FLAG_PATH);
-    store_part(p.b, t, q);
-    p.b.id[t] = id;
+    store_part_id(p.b, t, q, id);
     if ((phase & PH_RECAP) && k <= p.ncell_pad) { // still out of bounds after this step's recapture: the closing one must see it
         Part c = q;
         bool again = p.kind == AMC_KIND_TEMP ? (temp_oob(p.g, c) != 0) | (temp_recapture(p.g, c) != 0) : (p.kind == AMC_KIND_PORE && pore_recapture(p.g, c) != 0);
@@ -439,13 +452,12 @@ __global__ void __launch_bounds__(ADVECT_THREADS) k_scatter(const __grid_constan
     if (s >= p.n + (p.slab ? *p.n_in : 0) || s >= p.cap) return;
     int32_t k = p.key[s], r = p.rank[s];
     int64_t t = (int64_t)p.cell_start[k] + (r >= 0 ? r : p.band_count[k] + ~r);
-    p.b.x[t] = p.a.x[s]; p.b.y[t] = p.a.y[s]; p.b.z[t] = p.a.z[s];
+    const PosRec rec = p.a.pos[s];
+    const unsigned fl = rec.flag;
+    const int32_t id = rec.id;
+    st_pos(p.b.pos + t, rec.x, rec.y, rec.z, id, fl & (p.slab ? AMC_FLAG_KEEP : AMC_FLAG_PATH));
     p.b.vx[t] = p.a.vx[s]; p.b.vy[t] = p.a.vy[s]; p.b.vz[t] = p.a.vz[s];
     p.b.d[t] = p.a.d[s]; p.b.dx[t] = p.a.dx[s]; p.b.dy[t] = p.a.dy[s]; p.b.dz[t] = p.a.dz[s];
-    unsigned fl = p.a.flag[s];
-    int32_t id = p.a.id[s];
-    p.b.flag[t] = (uint8_t)(fl & (p.slab ? AMC_FLAG_KEEP : AMC_FLAG_PATH));
-    p.b.id[t] = id;
     if (p.slab) {
         if (k <= p.ncell_pad && (fl & (AMC_FLAG_GHOST | AMC_FLAG_REL_UP | AMC_FLAG_REL_DOWN))) {
             rel_insert(p, id, (int32_t)t);
@@ -462,18 +474,17 @@ __global__ void __launch_bounds__(ADVECT_THREADS) k_scatter(const __grid_constan
 __global__ void __launch_bounds__(ADVECT_THREADS) k_inverse_perm(const __grid_constant__ P p)
 {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s < p.n) p.key[p.a.id[s]] = (int32_t)s;
+    if (s < p.n) p.key[p.a.pos[s].id] = (int32_t)s;
 }
 __global__ void __launch_bounds__(ADVECT_THREADS) k_unsort(const __grid_constant__ P p)
 {
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= p.n) return;
     int64_t s = p.key[t];
-    p.b.x[t] = p.a.x[s]; p.b.y[t] = p.a.y[s]; p.b.z[t] = p.a.z[s];
+    const PosRec r = p.a.pos[s];
+    st_pos(p.b.pos + t, r.x, r.y, r.z, (int32_t)t, r.flag & AMC_FLAG_PATH);
     p.b.vx[t] = p.a.vx[s]; p.b.vy[t] = p.a.vy[s]; p.b.vz[t] = p.a.vz[s];
     p.b.d[t] = p.a.d[s]; p.b.dx[t] = p.a.dx[s]; p.b.dy[t] = p.a.dy[s]; p.b.dz[t] = p.a.dz[s];
-    p.b.flag[t] = p.a.flag[s] & AMC_FLAG_PATH;
-    p.b.id[t] = (int32_t)t;
 }
 
 // start of a pair pass: forget the escaped-particle list of the previous pass (single block, so
@@ -492,9 +503,9 @@ __global__ void __launch_bounds__(ADVECT_THREADS) k_recapture_post(const __grid_
 {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= p.n) return;
-    if (p.slab && (p.a.flag[s] & AMC_FLAG_GHOST)) return; /* the owning rank recaptures it */
+    if (p.slab && (p.a.pos[s].flag & AMC_FLAG_GHOST)) return; /* the owning rank recaptures it */
     Part q;
-    q.x = p.a.x[s]; q.y = p.a.y[s]; q.z = p.a.z[s];
+    q.x = p.a.pos[s].x; q.y = p.a.pos[s].y; q.z = p.a.pos[s].z;
     double x0 = q.x, y0 = q.y, z0 = q.z;
     int cnt = p.kind == AMC_KIND_TEMP ? temp_oob(p.g, q) : 0;
     int moved = p.kind == AMC_KIND_TEMP ? temp_recapture(p.g, q) : pore_recapture(p.g, q);
@@ -504,9 +515,9 @@ __global__ void __launch_bounds__(ADVECT_THREADS) k_recapture_post(const __grid_
         int after = temp_oob(p.g, q);
         if (after) atomicAdd(&p.stats->oob_pp_after, (unsigned long long)after);
     }
-    if (q.x != x0) p.a.x[s] = q.x;
-    if (q.y != y0) p.a.y[s] = q.y;
-    if (q.z != z0) p.a.z[s] = q.z;
+    if (q.x != x0) p.a.pos[s].x = q.x;
+    if (q.y != y0) p.a.pos[s].y = q.y;
+    if (q.z != z0) p.a.pos[s].z = q.z;
 }
 
 // Only a particle that a collision moved (or that the walls + recapture of this step left out of bounds) can be
@@ -516,9 +527,9 @@ __global__ void __launch_bounds__(ADVECT_THREADS) k_recapture_post(const __grid_
 // kernel fall back to the full pass.
 __device__ __forceinline__ void recapture_slot(const P &p, const int64_t s)
 {
-    if (p.slab && (p.a.flag[s] & AMC_FLAG_GHOST)) return; /* the owning rank recaptures it */
+    if (p.slab && (p.a.pos[s].flag & AMC_FLAG_GHOST)) return; /* the owning rank recaptures it */
     Part q;
-    q.x = p.a.x[s]; q.y = p.a.y[s]; q.z = p.a.z[s];
+    q.x = p.a.pos[s].x; q.y = p.a.pos[s].y; q.z = p.a.pos[s].z;
     double x0 = q.x, y0 = q.y, z0 = q.z;
     int cnt = p.kind == AMC_KIND_TEMP ? temp_oob(p.g, q) : 0;
     int moved = p.kind == AMC_KIND_TEMP ? temp_recapture(p.g, q) : pore_recapture(p.g, q);
@@ -528,9 +539,9 @@ __device__ __forceinline__ void recapture_slot(const P &p, const int64_t s)
         int after = temp_oob(p.g, q);
         if (after) atomicAdd(&p.stats->oob_pp_after, (unsigned long long)after);
     }
-    if (q.x != x0) p.a.x[s] = q.x;
-    if (q.y != y0) p.a.y[s] = q.y;
-    if (q.z != z0) p.a.z[s] = q.z;
+    if (q.x != x0) p.a.pos[s].x = q.x;
+    if (q.y != y0) p.a.pos[s].y = q.y;
+    if (q.z != z0) p.a.pos[s].z = q.z;
 }
 __global__ void __launch_bounds__(ADVECT_THREADS) k_recapture_list(const __grid_constant__ P p)
 {
@@ -683,7 +694,7 @@ __device__ __forceinline__ void resolve_pair(const P &p, CellShared &S, int m1, 
     }
     const double ovx = __ldcg(A.vx + so), ovy = __ldcg(A.vy + so), ovz = __ldcg(A.vz + so), od = __ldcg(A.d + so), odx = __ldcg(A.dx + so),
                  ody = __ldcg(A.dy + so), odz = __ldcg(A.dz + so);
-    uint32_t of = __ldcg(A.flag + so);
+    uint32_t of = __ldcg(&A.pos[so].flag);
     const double qvx = __shfl_xor_sync(FULL, ovx, 1), qvy = __shfl_xor_sync(FULL, ovy, 1), qvz = __shfl_xor_sync(FULL, ovz, 1);
     double x1 = S.x[m1], y1 = S.y[m1], z1 = S.z[m1], x2 = S.x[m2], y2 = S.y[m2], z2 = S.z[m2];
     const double vx1 = w ? qvx : ovx, vy1 = w ? qvy : ovy, vz1 = w ? qvz : ovz;
@@ -744,7 +755,7 @@ __device__ __forceinline__ void resolve_pair(const P &p, CellShared &S, int m1, 
     if (lane < 2) {
         const double wx = w ? wx2 : wx1, wy = w ? wy2 : wy1, wz = w ? wz2 : wz1;
         S.x[mo] = x; S.y[mo] = y; S.z[mo] = z;
-        A.x[so] = x; A.y[so] = y; A.z[so] = z;
+        A.pos[so].x = x; A.pos[so].y = y; A.pos[so].z = z;
         A.vx[so] = wx; A.vy[so] = wy; A.vz[so] = wz;
         A.d[so] = fabs(sqrt((wx * wx + wy * wy) + wz * wz) * t);
         A.dx[so] = fabs(wx * t); A.dy[so] = fabs(wy * t); A.dz[so] = fabs(wz * t);
@@ -781,7 +792,7 @@ __device__ __forceinline__ void resolve_pair(const P &p, CellShared &S, int m1, 
         else { double *sp = p.mv_spill + ((size_t)blockIdx.x * AMC_MAX_MEMBERS + i) * 3; sp[0] = oldx; sp[1] = oldy; sp[2] = oldz; }
         S.mv[mo] = (uint16_t)(i + 1);
     }
-    if (lane < 2) A.flag[so] = (uint8_t)of;
+    if (lane < 2) A.pos[so].flag = (uint8_t)of;
     __syncwarp();
 }
 
@@ -831,7 +842,7 @@ __device__ __forceinline__ void activate_moved(const P &p, CellShared &S, const 
                 if (!findable) { /* entries are never re-linked: a particle that moves again in a later visit gets a fresh one */
                     e = atomicAdd(p.esc_count, 1);
                     if (e >= p.esc_cap) { atomicAdd(&p.stats->esc_overflow, 1ull); ok = 0; }
-                    else { p.esc_slot[e] = so; A.flag[so] |= AMC_FLAG_ESC; }
+                    else { p.esc_slot[e] = so; A.pos[so].flag |= AMC_FLAG_ESC; }
                 }
             }
         }
@@ -1169,8 +1180,8 @@ __device__ __forceinline__ int det_slot(const DetShared &S, int buf, int t)
 __device__ __noinline__ void det_seed_mark(const P &p, const int sa, const int sb)
 {
     const Arrays &A = p.a;
-    if (overlap(p, A.x[sa], A.y[sa], A.z[sa], A.x[sb], A.y[sb], A.z[sb]))
-        if (atomicExch(&p.rank[A.id[sa] > A.id[sb] ? sa : sb], 1) == 0) atomicAdd(&p.stats->pp, 1ull);
+    if (overlap(p, A.pos[sa].x, A.pos[sa].y, A.pos[sa].z, A.pos[sb].x, A.pos[sb].y, A.pos[sb].z))
+        if (atomicExch(&p.rank[A.pos[sa].id > A.pos[sb].id ? sa : sb], 1) == 0) atomicAdd(&p.stats->pp, 1ull);
 }
 // A cell with more candidates than the table holds is searched pair by pair on the fp64 positions (one-time work at
 // initialisation; the timestep leaves such cells to the ordered resolution).
@@ -1180,14 +1191,14 @@ __device__ __noinline__ void det_seed_big_cell(const P &p, const DetShared &S, c
     const double *bd = reinterpret_cast<const double *>(&S.hdr[cur][20]);
     for (int i = threadIdx.x; i < total; i += DET_THREADS) {
         const int si = det_slot(S, cur, i);
-        const double xi = A.x[si], yi = A.y[si], zi = A.z[si];
+        const double xi = A.pos[si].x, yi = A.pos[si].y, zi = A.pos[si].z;
         if (!(bd[0] < xi && xi < bd[1] && bd[2] < yi && yi < bd[3] && bd[4] < zi && zi < bd[5])) continue;
         for (int j = 0; j < i; j++) {
             const int sj = det_slot(S, cur, j);
-            const double xj = A.x[sj], yj = A.y[sj], zj = A.z[sj];
+            const double xj = A.pos[sj].x, yj = A.pos[sj].y, zj = A.pos[sj].z;
             if (!(bd[0] < xj && xj < bd[1] && bd[2] < yj && yj < bd[3] && bd[4] < zj && zj < bd[5])) continue;
             if (overlap(p, xi, yi, zi, xj, yj, zj))
-                if (atomicExch(&p.rank[A.id[si] > A.id[sj] ? si : sj], 1) == 0) atomicAdd(&p.stats->pp, 1ull);
+                if (atomicExch(&p.rank[A.pos[si].id > A.pos[sj].id ? si : sj], 1) == 0) atomicAdd(&p.stats->pp, 1ull);
         }
     }
 }
@@ -1218,7 +1229,8 @@ __global__ void __launch_bounds__(DET_THREADS, DET_OCC) k_detect(const __grid_co
         int t = tid + k * DET_THREADS;
         if (t < S.rcum[0][8]) {
             int s = det_slot(S, 0, t);
-            cx[k] = A.x[s]; cy[k] = A.y[s]; cz[k] = A.z[s];
+            const PosRec r = A.pos[s];
+            cx[k] = r.x; cy[k] = r.y; cz[k] = r.z;
         }
     }
     unsigned int tests = 0;
@@ -1285,10 +1297,10 @@ __global__ void __launch_bounds__(DET_THREADS, DET_OCC) k_detect(const __grid_co
                 const int t = tid + k * DET_THREADS;
                 sl[k] = t < ntot ? det_slot(S, nxt, t) : -1;
             }
-            const double *ax = A.x, *ay = A.y, *az = A.z;
+            const PosRec *ap = A.pos;
 #pragma unroll
             for (int k = 0; k < DET_K; k++)
-                if (sl[k] >= 0) { cx[k] = ax[sl[k]]; cy[k] = ay[sl[k]]; cz[k] = az[sl[k]]; }
+                if (sl[k] >= 0) { const PosRec r = ap[sl[k]]; cx[k] = r.x; cy[k] = r.y; cz[k] = r.z; }
         }
         // ---- search: the older members of the own bin and everything in the four forward neighbour bins
 #pragma unroll
@@ -1400,7 +1412,8 @@ __device__ __forceinline__ void gather_members(const P &p, CellShared &S, const 
                         for (int r = 1; r < 8; r++) nb += t >= S.rcum[r];
                         int s = S.rbeg[nb] + (t - S.rcum[nb]);
                         /* past L1: with the fused hand-over another CTA of this launch may have updated the record */
-                        fl[k] = __ldcg(A.flag + s); x[k] = __ldcg(A.x + s); y[k] = __ldcg(A.y + s); z[k] = __ldcg(A.z + s); id[k] = __ldcg(A.id + s);
+                        const PosRec r = ldcg_pos(A.pos + s); /* the whole record: two 128-bit loads */
+                        fl[k] = r.flag; x[k] = r.x; y[k] = r.y; z[k] = r.z; id[k] = r.id;
                     }
                 }
                 PHASE_MARK(11); /* gather: loads issued */
@@ -1431,7 +1444,7 @@ __device__ __forceinline__ void gather_members(const P &p, CellShared &S, const 
                 if (__ldcg(p.esc_cell + e * 8 + group) != cell) continue; /* the particle moved on since it was linked here */
                 int s = __ldcg(p.esc_slot + e);
                 int k = atomicAdd(&S.n, 1);
-                if (k < AMC_MAX_MEMBERS) { S.x[k] = __ldcg(A.x + s); S.y[k] = __ldcg(A.y + s); S.z[k] = __ldcg(A.z + s); S.id[k] = __ldcg(A.id + s); S.slot[k] = s; S.src[k] = e; }
+                if (k < AMC_MAX_MEMBERS) { const PosRec r = ldcg_pos(A.pos + s); S.x[k] = r.x; S.y[k] = r.y; S.z[k] = r.z; S.id[k] = r.id; S.slot[k] = s; S.src[k] = e; }
             }
         }
 }
@@ -1625,7 +1638,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_cube_sweep(const __grid_const
         {
             double lo = p.lo[0][xl], hi = p.edge[0][xl + 1];
             for (int i = tid; i < p.n; i += SWEEP_THREADS) {
-                double v = A.x[i];
+                double v = A.pos[i].x;
                 if (lo < v && v < hi) lx[atomicAdd(&nx, 1)] = i;
             }
         }
@@ -1637,7 +1650,7 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_cube_sweep(const __grid_const
                 double lo = p.lo[1][yl], hi = p.edge[1][yl + 1];
                 for (int k = tid; k < nx; k += SWEEP_THREADS) {
                     int i = lx[k];
-                    double v = A.y[i];
+                    double v = A.pos[i].y;
                     if (lo < v && v < hi) lxy[atomicAdd(&nxy, 1)] = i;
                 }
             }
@@ -1655,10 +1668,10 @@ __global__ void __launch_bounds__(SWEEP_THREADS) k_cube_sweep(const __grid_const
                     double lo = p.lo[2][zl], hi = p.edge[2][zl + 1];
                     for (int k = tid; k < nxy; k += SWEEP_THREADS) {
                         int i = lxy[k];
-                        double v = A.z[i];
+                        double v = A.pos[i].z;
                         if (lo < v && v < hi) {
                             int m = atomicAdd(&S.n, 1);
-                            if (m < AMC_MAX_MEMBERS) { S.x[m] = A.x[i]; S.y[m] = A.y[i]; S.z[m] = v; S.id[m] = i; S.slot[m] = i; S.src[m] = -1; }
+                            if (m < AMC_MAX_MEMBERS) { S.x[m] = A.pos[i].x; S.y[m] = A.pos[i].y; S.z[m] = v; S.id[m] = i; S.slot[m] = i; S.src[m] = -1; }
                         }
                     }
                 }
@@ -1727,7 +1740,7 @@ __global__ void __launch_bounds__(SWD_THREADS) k_sweep_detect(const __grid_const
 #pragma unroll
             for (int u = 0; u < 4; u++) {
                 const int64_t i = i0 + u * SWD_THREADS;
-                x[u] = i < p.n ? A.x[i] : hix; y[u] = i < p.n ? A.y[i] : hiy;
+                x[u] = i < p.n ? A.pos[i].x : hix; y[u] = i < p.n ? A.pos[i].y : hiy;
             }
 #pragma unroll
             for (int u = 0; u < 4; u++) {
@@ -1751,10 +1764,10 @@ __global__ void __launch_bounds__(SWD_THREADS) k_sweep_detect(const __grid_const
         const double loz = p.lo[2][zl], hiz = p.edge[2][zl + 1];
         for (int k = tid; k < ncol; k += SWD_THREADS) {
             const int i = list[k];
-            const double z = A.z[i];
+            const double z = A.pos[i].z;
             if (loz < z && z < hiz) {
                 const int m = atomicAdd(&s_m, 1);
-                if (m < AMC_MAX_MEMBERS) { sx[m] = A.x[i]; sy[m] = A.y[i]; sz[m] = z; }
+                if (m < AMC_MAX_MEMBERS) { sx[m] = A.pos[i].x; sy[m] = A.pos[i].y; sz[m] = z; }
             }
         }
         __syncthreads();
@@ -1816,8 +1829,8 @@ __global__ void __launch_bounds__(SWE_THREADS) k_sweep_events(const __grid_const
             const int nml = s_nml;
             for (int k = tid; k < nml; k += SWE_THREADS) {
                 const int i = p.sw_ml[k];
-                if (xl != cur_xl) p.sw_xs[i] = A.x[i];
-                p.sw_ys[i] = A.y[i];
+                if (xl != cur_xl) p.sw_xs[i] = A.pos[i].x;
+                p.sw_ys[i] = A.pos[i].y;
             }
             cur_xl = xl; cur_col = col;
         }
@@ -1839,7 +1852,7 @@ __global__ void __launch_bounds__(SWE_THREADS) k_sweep_events(const __grid_const
             for (int k = tid; k < ncol + nml; k += SWE_THREADS) {
                 const int i = k < ncol ? list[k] : p.sw_ml[k - ncol];
                 const int tag = p.sw_tag[i];                                /* one round trip for all four */
-                const double z = A.z[i], x = A.x[i], y = A.y[i];
+                const double z = A.pos[i].z, x = A.pos[i].x, y = A.pos[i].y;
                 const bool tagged = tag == p.sw_pass;
                 if (k < ncol && tagged) continue; /* comes through the moved list */
                 if (!(loz < z && z < hiz)) continue;
@@ -1917,7 +1930,7 @@ __global__ void __launch_bounds__(ADVECT_THREADS) k_case_specular(const __grid_c
     q.px = p.px[s]; q.py = p.py[s]; q.pz = p.pz[s];
     if (!temp_mask(p, c, q)) return;
     atomicAdd(&p.stats->wall_hits[c], 1ull);
-    if (p.wall_bits) p.wall_bits[p.a.id[s]] |= (uint16_t)(1u << c);
+    if (p.wall_bits) p.wall_bits[p.a.pos[s].id] |= (uint16_t)(1u << c);
     temp_specular(p, c, q);
     store_part(p.a, s, q);
 }
@@ -1936,7 +1949,7 @@ __global__ void __launch_bounds__(ADVECT_THREADS) k_case_detect(const __grid_con
     if (k >= cap) return;
     double t, col[3], nrm[3];
     if (!temp_contact(p.g, c, q, t, col, nrm)) { nrm[0] = nrm[1] = nrm[2] = col[2] = __longlong_as_double(0x7ff8000000000000ll); }
-    out_slot[k] = (int32_t)s; out_id[k] = p.a.id[s];
+    out_slot[k] = (int32_t)s; out_id[k] = p.a.pos[s].id;
     out_nrm[3 * k] = nrm[0]; out_nrm[3 * k + 1] = nrm[1]; out_nrm[3 * k + 2] = nrm[2];
     out_colz[k] = col[2];
 }
@@ -1952,7 +1965,7 @@ __global__ void __launch_bounds__(ADVECT_THREADS) k_case_apply(const __grid_cons
     q.px = p.px[s]; q.py = p.py[s]; q.pz = p.pz[s];
     out_dpz[k] = 0.0; out_de[k] = 0.0;
     atomicAdd(&p.stats->wall_hits[c], 1ull);
-    if (p.wall_bits) p.wall_bits[p.a.id[s]] |= (uint16_t)(1u << c);
+    if (p.wall_bits) p.wall_bits[p.a.pos[s].id] |= (uint16_t)(1u << c);
     double t, col[3], nrm[3], dpz, dE;
     if (!temp_contact(p.g, c, q, t, col, nrm)) { atomicAdd(&p.stats->errors, 1ull); return; }
     double dir[3] = {dirs[3 * k], dirs[3 * k + 1], dirs[3 * k + 2]};
@@ -1968,7 +1981,7 @@ __global__ void __launch_bounds__(ADVECT_THREADS) k_wall_operator(const __grid_c
 {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= p.n) return;
-    if (!mask[p.a.id[s]]) return;
+    if (!mask[p.a.pos[s].id]) return;
     Part q;
     load_part(p.a, s, q);
     q.px = q.x; q.py = q.y; q.pz = q.z;
@@ -2024,9 +2037,9 @@ __global__ void __launch_bounds__(ADVECT_THREADS) k_seed_redraw(const __grid_con
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= p.n || p.rank[s] != 1) return;
     double u[4], x, y, z;
-    synthetic_uniforms(sp, p.a.id[s], attempt, 0, 2, u);
-    synthetic_position(sp, p.a.id[s], attempt, u, x, y, z);
-    p.a.x[s] = x; p.a.y[s] = y; p.a.z[s] = z;
+    synthetic_uniforms(sp, p.a.pos[s].id, attempt, 0, 2, u);
+    synthetic_position(sp, p.a.pos[s].id, attempt, u, x, y, z);
+    p.a.pos[s].x = x; p.a.pos[s].y = y; p.a.pos[s].z = z;
 }
 
 __global__ void __launch_bounds__(ADVECT_THREADS) k_init_synthetic(const __grid_constant__ P p, const __grid_constant__ amc_init_spec sp,
@@ -2048,18 +2061,34 @@ __global__ void __launch_bounds__(ADVECT_THREADS) k_init_synthetic(const __grid_
             t = atomicAdd(count, 1);
             if (t >= cap) continue; /* reported by the host from the final count */
         }
-        p.a.x[t] = x; p.a.y[t] = y; p.a.z[t] = z;
+        st_pos(p.a.pos + t, x, y, z, (int32_t)i, 0u);
         p.a.vx[t] = r1 * c1; p.a.vy[t] = r1 * s1; p.a.vz[t] = r2 * c2;
         p.a.d[t] = 0.0; p.a.dx[t] = 0.0; p.a.dy[t] = 0.0; p.a.dz[t] = 0.0;
-        p.a.flag[t] = 0;
-        p.a.id[t] = (int32_t)i;
     }
 }
 
-__global__ void k_iota(int32_t *ids, int64_t n)
+// The C ABI hands positions, ids and flags over as separate arrays (the reference's module globals); on the device they
+// live in the position records.  amc_set_state copies the host arrays into the SoaView laid over the idle b record
+// array and packs them; amc_get_state unpacks the other way before its copies.
+__global__ void __launch_bounds__(ADVECT_THREADS) k_pack_pos(const __grid_constant__ P p, const int with_ids)
 {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) ids[i] = (int32_t)i;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n) return;
+    const SoaView v = soa_view(p.b.pos, p.cap);
+    st_pos(p.a.pos + i, v.x[i], v.y[i], v.z[i], with_ids ? v.id[i] : (int32_t)i, v.flag[i]); /* slot == particle index unless ids are given */
+}
+__global__ void __launch_bounds__(ADVECT_THREADS) k_unpack_pos(const __grid_constant__ P p)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n) return;
+    const SoaView v = soa_view(p.b.pos, p.cap);
+    const PosRec r = p.a.pos[i];
+    v.x[i] = r.x; v.y[i] = r.y; v.z[i] = r.z; v.id[i] = r.id; v.flag[i] = (uint8_t)r.flag;
+}
+__global__ void __launch_bounds__(ADVECT_THREADS) k_set_ids(const __grid_constant__ P p, const int32_t *ids)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < p.n) p.a.pos[i].id = ids[i];
 }
 
 // ================================================================================================
@@ -2117,8 +2146,7 @@ __global__ void __launch_bounds__(ADVECT_THREADS) k_xfer_unpack(const __grid_con
     int32_t k = owner_key(p, q.x, q.y, q.z, o);
     if (!(q.flag & (AMC_FLAG_GHOST | AMC_FLAG_REL_UP)) && p.srank + 1 < p.nranks && q.z > p.up_thr && k != p.ncell_pad)
         q.flag |= AMC_FLAG_REL_UP | AMC_FLAG_LATE_UP; /* immigrant inside the band below the upper cut */
-    store_part(p.a, s, q);
-    p.a.id[s] = (int32_t)__ldcg(r + 10);
+    store_part_id(p.a, s, q, (int32_t)__ldcg(r + 10));
     p.key[s] = k;
     if (k != p.ncell_pad && any_band(p, q.x, q.y, q.z, o)) p.rank[s] = atomicAdd(&p.band_count[k], 1);
     else p.rank[s] = ~atomicAdd(&p.rest_count[k], 1);
@@ -2139,13 +2167,13 @@ __device__ __forceinline__ void bnd_pack_dir(const P &p, const int dir)
     for (int j = threadIdx.x; j < cnt; j += blockDim.x) {
         int s = __ldcg(p.bnd_dirty[dir] + j);
         double *r = buf + (size_t)(1 + j) * AMC_REC;
-        r[0] = __ldcg(A.x + s); r[1] = __ldcg(A.y + s); r[2] = __ldcg(A.z + s); r[3] = __ldcg(A.vx + s); r[4] = __ldcg(A.vy + s); r[5] = __ldcg(A.vz + s);
-        r[6] = __ldcg(A.d + s); r[7] = __ldcg(A.dx + s); r[8] = __ldcg(A.dy + s); r[9] = __ldcg(A.dz + s); r[10] = (double)A.id[s];
-        r[11] = (double)(__ldcg(A.flag + s) & AMC_FLAG_PATH);
+        const PosRec pr = ldcg_pos(A.pos + s);
+        r[0] = pr.x; r[1] = pr.y; r[2] = pr.z; r[3] = __ldcg(A.vx + s); r[4] = __ldcg(A.vy + s); r[5] = __ldcg(A.vz + s);
+        r[6] = __ldcg(A.d + s); r[7] = __ldcg(A.dx + s); r[8] = __ldcg(A.dy + s); r[9] = __ldcg(A.dz + s); r[10] = (double)pr.id;
+        r[11] = (double)(pr.flag & AMC_FLAG_PATH);
         // clear this direction's "queued" bit (32-bit atomic on the word that holds the flag byte)
         unsigned bit = dir == 0 ? AMC_FLAG_DIRTY_UP : AMC_FLAG_DIRTY_DOWN;
-        uintptr_t addr = (uintptr_t)(A.flag + s);
-        atomicAnd((unsigned *)(addr & ~(uintptr_t)3), ~(bit << (8 * (addr & 3))));
+        atomicAnd(&A.pos[s].flag, ~bit);
     }
     if (peer) __threadfence_system();
     __syncthreads();
@@ -2168,12 +2196,12 @@ __device__ __forceinline__ void bnd_pack_warp(const P &p, const int dir, const i
     for (int j = lane; j < cnt; j += 32) {
         int s = __ldcg(p.bnd_dirty[dir] + j);
         double *r = buf + (size_t)(1 + j) * AMC_REC;
-        r[0] = __ldcg(A.x + s); r[1] = __ldcg(A.y + s); r[2] = __ldcg(A.z + s); r[3] = __ldcg(A.vx + s); r[4] = __ldcg(A.vy + s); r[5] = __ldcg(A.vz + s);
-        r[6] = __ldcg(A.d + s); r[7] = __ldcg(A.dx + s); r[8] = __ldcg(A.dy + s); r[9] = __ldcg(A.dz + s); r[10] = (double)A.id[s];
-        r[11] = (double)(__ldcg(A.flag + s) & AMC_FLAG_PATH);
+        const PosRec pr = ldcg_pos(A.pos + s);
+        r[0] = pr.x; r[1] = pr.y; r[2] = pr.z; r[3] = __ldcg(A.vx + s); r[4] = __ldcg(A.vy + s); r[5] = __ldcg(A.vz + s);
+        r[6] = __ldcg(A.d + s); r[7] = __ldcg(A.dx + s); r[8] = __ldcg(A.dy + s); r[9] = __ldcg(A.dz + s); r[10] = (double)pr.id;
+        r[11] = (double)(pr.flag & AMC_FLAG_PATH);
         unsigned bit = dir == 0 ? AMC_FLAG_DIRTY_UP : AMC_FLAG_DIRTY_DOWN;
-        uintptr_t addr = (uintptr_t)(A.flag + s);
-        atomicAnd((unsigned *)(addr & ~(uintptr_t)3), ~(bit << (8 * (addr & 3))));
+        atomicAnd(&A.pos[s].flag, ~bit);
     }
     __syncwarp();
     if (lane == 0) {
@@ -2218,15 +2246,15 @@ __device__ __forceinline__ void bnd_apply_dir(const P &p, const int dir, const u
         else {
             int s = (int)n_base + f;
             s_slot = s;
-            A.id[s] = id;
-            A.flag[s] = (uint8_t)(AMC_FLAG_GHOST | (dir == 0 ? AMC_FLAG_REL_UP : AMC_FLAG_REL_DOWN));
+            A.pos[s].id = id;
+            A.pos[s].flag = (uint8_t)(AMC_FLAG_GHOST | (dir == 0 ? AMC_FLAG_REL_UP : AMC_FLAG_REL_DOWN));
             rel_insert(p, id, s);
         }
     }
     __syncthreads();
     const int s = s_slot;
     if (s < 0) continue;
-    const unsigned fl = A.flag[s];
+    const unsigned fl = A.pos[s].flag;
     if (fl & AMC_FLAG_ESC) { // already on the escaped list: find its (latest) entry
         int ne = min(*p.esc_count, p.esc_cap);
         for (int e = tid; e < ne; e += blockDim.x)
@@ -2245,10 +2273,10 @@ __device__ __forceinline__ void bnd_apply_dir(const P &p, const int dir, const u
         // slots below the count of the sort hold sorted particles; the ones behind it are foreign copies appended by
         // earlier hand-overs of this pass (always on the escaped list): both have a previous position here
         const bool sorted = s < n_base;
-        if (sorted || (fl & AMC_FLAG_ESC)) { ux = A.x[s]; uy = A.y[s]; uz = A.z[s]; }
+        if (sorted || (fl & AMC_FLAG_ESC)) { ux = A.pos[s].x; uy = A.pos[s].y; uz = A.pos[s].z; }
         // a sorted particle that has not escaped still sits in the owner cell it was sorted into
         const int32_t sk = owner_key(p, ux, uy, uz, q);
-        A.x[s] = x; A.y[s] = y; A.z[s] = z; A.vx[s] = __ldcg(r + 3); A.vy[s] = __ldcg(r + 4); A.vz[s] = __ldcg(r + 5);
+        A.pos[s].x = x; A.pos[s].y = y; A.pos[s].z = z; A.vx[s] = __ldcg(r + 3); A.vy[s] = __ldcg(r + 4); A.vz[s] = __ldcg(r + 5);
         A.d[s] = __ldcg(r + 6); A.dx[s] = __ldcg(r + 7); A.dy[s] = __ldcg(r + 8); A.dz[s] = __ldcg(r + 9);
         int32_t k = owner_key(p, x, y, z, o);
         if (e_old < 0)
@@ -2258,7 +2286,7 @@ __device__ __forceinline__ void bnd_apply_dir(const P &p, const int dir, const u
             if (e >= p.esc_cap) { atomicAdd(&p.stats->esc_overflow, 1ull); ok = 0; }
             else { p.esc_slot[e] = s; nf |= AMC_FLAG_ESC; }
         }
-        A.flag[s] = (uint8_t)nf;
+        A.pos[s].flag = (uint8_t)nf;
         touch_slot(p, s);
     }
     const unsigned FULL = 0xffffffffu;
@@ -2310,14 +2338,15 @@ __global__ void __launch_bounds__(ADVECT_THREADS) k_compact_owned(const __grid_c
 {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= p.n) return;
-    unsigned fl = p.a.flag[s];
+    unsigned fl = p.a.pos[s].flag;
     if (fl & AMC_FLAG_GHOST) return;
     int t = atomicAdd(count, 1);
-    p.b.x[t] = p.a.x[s]; p.b.y[t] = p.a.y[s]; p.b.z[t] = p.a.z[s];
+    // positions, ids and flags leave as separate arrays laid over the b record array (SoaView, amc_api.cu)
+    const PosRec r = p.a.pos[s];
+    const SoaView v = soa_view(p.b.pos, p.cap);
+    v.x[t] = r.x; v.y[t] = r.y; v.z[t] = r.z; v.id[t] = r.id; v.flag[t] = (uint8_t)(fl & AMC_FLAG_PATH);
     p.b.vx[t] = p.a.vx[s]; p.b.vy[t] = p.a.vy[s]; p.b.vz[t] = p.a.vz[s];
     p.b.d[t] = p.a.d[s]; p.b.dx[t] = p.a.dx[s]; p.b.dy[t] = p.a.dy[s]; p.b.dz[t] = p.a.dz[s];
-    p.b.flag[t] = fl & AMC_FLAG_PATH;
-    p.b.id[t] = p.a.id[s];
 }
 
 // Order-independent 128-bit checksum of the particles this handle owns (ghost copies excluded): for every
@@ -2340,10 +2369,10 @@ __global__ void __launch_bounds__(ADVECT_THREADS) k_state_digest(const __grid_co
     unsigned long long a0 = 0, a1 = 0, cnt = 0;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < p.n; s += stride) {
-        const unsigned fl = p.a.flag[s];
+        const unsigned fl = p.a.pos[s].flag;
         if (fl & AMC_FLAG_GHOST) continue;
-        const unsigned long long id = (unsigned long long)(uint32_t)p.a.id[s];
-        const double v[10] = {p.a.x[s], p.a.y[s], p.a.z[s], p.a.vx[s], p.a.vy[s], p.a.vz[s], p.a.d[s], p.a.dx[s], p.a.dy[s], p.a.dz[s]};
+        const unsigned long long id = (unsigned long long)(uint32_t)p.a.pos[s].id;
+        const double v[10] = {p.a.pos[s].x, p.a.pos[s].y, p.a.pos[s].z, p.a.vx[s], p.a.vy[s], p.a.vz[s], p.a.d[s], p.a.dx[s], p.a.dy[s], p.a.dz[s]};
 #pragma unroll
         for (int f = 0; f < 11; f++) {
             const unsigned long long bits = f < 10 ? (unsigned long long)__double_as_longlong(v[f < 10 ? f : 0]) : (unsigned long long)(fl & AMC_FLAG_PATH);
