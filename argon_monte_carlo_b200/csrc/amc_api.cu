@@ -47,6 +47,8 @@ struct amc_handle {
     int pair_grid = 148 * 5;    // persistent CTAs of k_pairs_group: SMs x resident CTAs per SM
     int pair_grid_fused = 148;  // the same for the fused (in-kernel hand-over) variant
     int det_grid = 148 * 4;     // persistent CTAs of k_detect
+    int det_grid_tma = 148 * 4; // persistent CTAs of k_detect_tma
+    int detect_tma = 1;         // 1 / 2: the two shapes of k_detect_tma (AMC_DETECT=tma / tma8), 0: k_detect<false> (AMC_DETECT=ldg)
     int32_t sweep_pass = 0;     // tag of the last pass of the event-driven cube sweep (P::sw_pass)
     // host-RNG parity mode: pending hits of the last amc_wall_hits_pending call
     int32_t *d_pend_count = nullptr, *d_pend_slot = nullptr, *d_pend_id = nullptr;
@@ -359,6 +361,17 @@ static int create_impl(amc_handle *h, const amc_config *cfg, int device)
         CK(cudaFuncSetAttribute(k_detect<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_detect<false>, DET_THREADS, 0));
         h->det_grid = std::max(1, sms * std::max(per_sm, 1));
+        const char *dm = getenv("AMC_DETECT");
+        h->detect_tma = dm && strcmp(dm, "ldg") == 0 ? 0 : (dm && strcmp(dm, "tma8") == 0 ? 2 : 1);
+        if (h->detect_tma == 1) {
+            CK(cudaFuncSetAttribute(k_detect_tma<192, 2, 6, 64, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_detect_tma<192, 2, 6, 64, 1>, 192, 0));
+        } else if (h->detect_tma == 2) {
+            CK(cudaFuncSetAttribute(k_detect_tma<128, 3, 8, 32, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_detect_tma<128, 3, 8, 32, 2>, 128, 0));
+        }
+        h->det_grid_tma = std::max(1, sms * std::max(per_sm, 1));
+        if (getenv("AMC_DEBUG")) fprintf(stderr, "amc: detect mode %d, %d CTAs per SM\n", h->detect_tma, per_sm);
         ALLOC(p.mv_spill, (size_t)std::max(h->pair_grid, 1) * AMC_MAX_MEMBERS * 3);
     }
     CK(cudaDeviceSynchronize());
@@ -507,6 +520,15 @@ static int prepare_pairs(amc_handle *h, cudaStream_t st)
     return AMC_OK;
 }
 
+// the detection pass of a timestep: candidates staged by bulk copies (k_detect_tma, the default) or loaded by the
+// threads (k_detect<false>, AMC_DETECT=ldg: kept as the cross-check)
+static void launch_detect(amc_handle *h)
+{
+    if (h->detect_tma == 1) k_detect_tma<192, 2, 6, 64, 1><<<h->det_grid_tma, 192, 0, h->stream>>>(h->p);
+    else if (h->detect_tma == 2) k_detect_tma<128, 3, 8, 32, 2><<<h->det_grid_tma, 128, 0, h->stream>>>(h->p);
+    else k_detect<false><<<h->det_grid, DET_THREADS, 0, h->stream>>>(h->p);
+}
+
 static int run_pairs(amc_handle *h, int64_t *launches, bool prepared = false)
 {
     P &p = h->p;
@@ -533,7 +555,7 @@ static int run_pairs(amc_handle *h, int64_t *launches, bool prepared = false)
         }
         int ncell = p.nc[0] * p.nc[1] * p.nc[2];
         if (h->det_slot >= 0) CK(cudaEventRecord(h->det_events[2 * h->det_slot], h->stream));
-        k_detect<false><<<h->det_grid, DET_THREADS, 0, h->stream>>>(p);
+        launch_detect(h);
         if (h->det_slot >= 0) CK(cudaEventRecord(h->det_events[2 * h->det_slot + 1], h->stream));
         unsigned grid = (unsigned)std::min<int64_t>((int64_t)h->pair_grid, std::max<int64_t>(ncell / 8, 1));
         for (int g = 0; g < 8; g++) k_pairs_group<false><<<grid, PAIR_THREADS, 0, h->stream>>>(p, g);
@@ -1203,7 +1225,7 @@ extern "C" int amc_slab_pairs_begin(amc_handle *h, int32_t pre_round)
         for (int k = 0; k < 2; k++) { cudaEvent_t e; CK(cudaEventCreate(&e)); h->det_events.push_back(e); }
     }
     CK(cudaEventRecord(h->det_events[0], h->stream));
-    if (h->n) k_detect<false><<<h->det_grid, DET_THREADS, 0, h->stream>>>(p);
+    if (h->n) launch_detect(h);
     CK(cudaEventRecord(h->det_events[1], h->stream));
     h->slab_det_pending = true;
     if (pre_round) k_bnd_pack<<<2, ADVECT_THREADS, 0, h->stream>>>(p); // immigrants that landed in the top band; else they travel after group 0
@@ -1444,7 +1466,7 @@ extern "C" int amc_slab_step(amc_handle *h, int32_t n_steps, int32_t pre_round, 
             p.group_done = -1;
             if ((rc = prepare_pairs(h, h->stream)) != AMC_OK) { p.n_dev = nullptr; return rc; }
             CK(cudaEventRecord(h->det_events[2 * s], h->stream));
-            k_detect<false><<<h->det_grid, DET_THREADS, 0, h->stream>>>(p);
+            launch_detect(h);
             CK(cudaEventRecord(h->det_events[2 * s + 1], h->stream));
             h->last_launches += 12;
             if (p.nranks > 1 && pgrid >= 2 * BND_HEAD_CTAS && !getenv("AMC_SLAB_UNFUSED")) {

@@ -1130,9 +1130,10 @@ __global__ void __launch_bounds__(ADVECT_THREADS) k_build_worklist(const __grid_
 #define DET_TAB ((DET_NB + 1) * DET_ROW)    /* one empty row behind the last */
 
 struct DetShared {
+    static constexpr int NBX = DET_NB, NBY = DET_NBY, ROW = DET_ROW;
+    static constexpr float YF = DET_YF;
     unsigned int head[DET_TAB];      /* (visit tag << 16) | (candidate index + 1) of the last member hashed into the bin */
-    float4 tile[DET_CAND];           /* cell-relative fp32 position by candidate index */
-    unsigned short next[DET_CAND];   /* older member of the same bin (index + 1), 0 = none */
+    float4 tile[DET_CAND];           /* by candidate index: cell-relative fp32 position; .w = older member of the same bin (index + 1 as integer bits), 0 = none */
     __align__(16) int hdr[2][AMC_WI];
     int rbeg[2][8], rcum[2][9];
     float inv_wx[2], inv_wy[2];
@@ -1142,8 +1143,9 @@ struct DetShared {
     unsigned int hit[2][AMC_MAX_HITS]; /* candidate indices of the pairs that passed the filter: (self << 16) | other */
 };
 
-// warp 0: make the work item `v` (one int per lane) the header in buffer `buf`
-__device__ __forceinline__ void det_publish(const P &p, DetShared &S, int buf, int v, int lane)
+// header warp: make the work item `v` (one int per lane) the header in buffer `buf`
+template <class SH>
+__device__ __forceinline__ void det_publish(const P &p, SH &S, int buf, int v, int lane)
 {
     S.hdr[buf][lane] = v;
     __syncwarp();
@@ -1156,7 +1158,7 @@ __device__ __forceinline__ void det_publish(const P &p, DetShared &S, int buf, i
         if (lane < 2) { /* lane 0: bins along x, lane 1: along y */
             const double *d = reinterpret_cast<const double *>(&S.hdr[buf][20]);
             float wd = (float)(d[2 * lane + 1] - d[2 * lane]);
-            int nb = lane == 0 ? (int)fminf((float)DET_NB, floorf(wd / p.det_w)) : (int)fminf((float)DET_NBY, floorf(wd / (DET_YF * p.det_w)));
+            int nb = lane == 0 ? (int)fminf((float)SH::NBX, floorf(wd / p.det_w)) : (int)fminf((float)SH::NBY, floorf(wd / (SH::YF * p.det_w)));
             if (nb < 1) nb = 1;
             if (lane == 0) { S.nbx[buf] = nb; S.inv_wx[buf] = (float)nb / wd; S.rcum[buf][0] = 0; }
             else { S.nby[buf] = nb; S.inv_wy[buf] = (float)nb / wd; }
@@ -1166,7 +1168,8 @@ __device__ __forceinline__ void det_publish(const P &p, DetShared &S, int buf, i
 
 // slot of candidate t of the work item in buffer `buf`: the owner cell's own particles first, then the
 // band prefixes of the 7 low-side neighbours
-__device__ __forceinline__ int det_slot(const DetShared &S, int buf, int t)
+template <class SH>
+__device__ __forceinline__ int det_slot(const SH &S, int buf, int t)
 {
     if (t < S.rcum[buf][1]) return S.rbeg[buf][0] + t;
     int nb = 1;
@@ -1268,10 +1271,9 @@ __global__ void __launch_bounds__(DET_THREADS, DET_OCC) k_detect(const __grid_co
                     if (t < own || (lox < x && x < hix && loy < y && y < hiy && loz < z && z < hiz)) { /* Pore:527-530 */
                         fx[k] = (float)(x - lox); fy[k] = (float)(y - loy); fz[k] = (float)(z - loz);
                         int b = min(nbx1, (int)(fx[k] * inv_wx)) * DET_ROW + min(nby1, (int)(fy[k] * inv_wy)) + 1;
-                        S.tile[t] = make_float4(fx[k], fy[k], fz[k], 0.f);
                         unsigned int prev = atomicExch(&S.head[b], tagw | (unsigned int)(t + 1)) ^ tagw;
                         prev = prev < 0x10000u ? prev : 0u;
-                        S.next[t] = (unsigned short)prev;
+                        S.tile[t] = make_float4(fx[k], fy[k], fz[k], __uint_as_float(prev));
                         bin[k] = b; older[k] = (int)prev;
                         nm++;
                     }
@@ -1331,7 +1333,7 @@ __global__ void __launch_bounds__(DET_THREADS, DET_OCC) k_detect(const __grid_co
                 float ex = q.x - ax, ey = q.y - ay, ez = q.z - az;
                 dmin = fminf(dmin, fmaf(ez, ez, fmaf(ey, ey, ex * ex)));
                 tests++;
-                e = S.next[e - 1];
+                e = __float_as_uint(q.w);
             }
             if (dmin < thr) { /* rare: walk the chains once more and remember the pairs for the ordered resolution */
                 hit = true;
@@ -1349,7 +1351,7 @@ __global__ void __launch_bounds__(DET_THREADS, DET_OCC) k_detect(const __grid_co
                         if (hh < AMC_MAX_HITS) S.hit[cur][hh] = ((unsigned int)(tid + k * DET_THREADS) << 16) | (e - 1);
                         if (SEED) det_seed_mark(p, det_slot(S, cur, tid + k * DET_THREADS), det_slot(S, cur, (int)e - 1));
                     }
-                    e = S.next[e - 1];
+                    e = __float_as_uint(q.w);
                 }
             }
         }
@@ -1385,6 +1387,244 @@ __global__ void __launch_bounds__(DET_THREADS, DET_OCC) k_detect(const __grid_co
     tests = __reduce_add_sync(0xffffffffu, tests);
     if (lane == 0 && tests) atomicAdd(&p.stats->checks_exec, (unsigned long long)tests);
     if (hw && lane == 0 && nref) atomicAdd(&p.stats->checks_ref, nref);
+}
+
+// ------------------------------------------------------------------------------------------------
+// The same detection pass with the candidates staged by the copy engine instead of by the threads.  The candidates
+// of a reference cell are 8 runs of consecutive position records (the owner cell, the band prefixes of its 7 low-side
+// neighbours), so the header warp hands each run to cp.async.bulk (one 1-D bulk copy per run, SASS UBLKCP) and the
+// records land in shared memory while the CTA searches the previous cell; an mbarrier with a transaction count
+// tells the CTA when all of them are there.  No thread computes a candidate's slot (det_slot) or issues a global
+// load any more, and nothing of the next cell lives in registers during the search: 192 threads x 2 candidates at
+// 56 registers, 6 CTAs per SM.  Everything else -- membership, fp32 filter, bin table, results -- is k_detect's.
+// Two shapes are built (amc_api.cu picks one, AMC_DETECT): 192 threads x 2 candidates with k_detect's 64 x 64 bin table
+// (37 KB of shared memory: 6 CTAs per SM), and 128 threads x 3 candidates with y bins twice as wide (28 KB: 8 CTAs).
+template <int NBY_, int YF_>
+struct DetSharedT {
+    static constexpr int NBX = DET_NB, NBY = NBY_, ROW = NBY_ + 2, TAB = (DET_NB + 1) * (NBY_ + 2);
+    static constexpr float YF = (float)YF_;
+    unsigned int head[TAB];
+    float4 tile[DET_CAND];
+    __align__(128) PosRec raw[DET_CAND]; /* records of the cell about to be searched: written by the bulk copies only */
+    __align__(16) int hdr[2][AMC_WI];
+    int rbeg[2][8], rcum[2][9];
+    float inv_wx[2], inv_wy[2];
+    int nbx[2], nby[2];
+    int nmem[2];
+    int nhit[2];
+    unsigned int hit[2][AMC_MAX_HITS];
+    __align__(8) unsigned long long bar; /* mbarrier: one arrival (the header warp's expect_tx) + the bytes of the copies */
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *q) { return (uint32_t)__cvta_generic_to_shared(q); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, const int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, const uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, const uint32_t bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// false when the phase did not complete within ~1 s (a byte count that does not match the copies): the caller reports it
+__device__ __forceinline__ bool mbar_wait(unsigned long long *bar, const uint32_t parity)
+{
+    for (unsigned int spins = 0; spins < (1u << 22); spins++) {
+        uint32_t ok;
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok)
+                     : "r"(smem_u32(bar)), "r"(parity)
+                     : "memory");
+        if (ok) return true;
+    }
+    return false;
+}
+
+// header warp: start the bulk copies of the candidates of the work item in header buffer `buf` (published and
+// barrier-separated from here).  A cell with more candidates than the tile holds is not copied: it is flagged unseen.
+template <class SH>
+__device__ __forceinline__ void det_fetch(const P &p, SH &S, const int buf, const int lane)
+{
+    const int total = S.rcum[buf][8];
+    const bool fits = total <= DET_CAND;
+    if (lane == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); /* the threads' reads of S.raw (behind a barrier) before the engine's writes */
+        mbar_expect_tx(&S.bar, fits ? (uint32_t)total * (uint32_t)sizeof(PosRec) : 0u);
+    }
+    __syncwarp();
+    if (fits && lane < 8) {
+        const int beg = S.rcum[buf][lane], len = S.rcum[buf][lane + 1] - beg;
+        if (len > 0) bulk_g2s(&S.raw[beg], p.a.pos + S.rbeg[buf][lane], (uint32_t)len * (uint32_t)sizeof(PosRec), &S.bar);
+    }
+}
+
+template <int TD_THREADS, int TD_K, int TD_OCC, int NBY_, int YF_>
+__global__ void __launch_bounds__(TD_THREADS, TD_OCC) k_detect_tma(const __grid_constant__ P p)
+{
+    static_assert(TD_THREADS * TD_K == DET_CAND, "the tile holds DET_CAND candidates");
+    typedef DetSharedT<NBY_, YF_> SH;
+    __shared__ SH S;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nwork = *p.dl_count;
+    const int stride = gridDim.x;
+    int w = blockIdx.x;
+    if (w >= nwork) return;
+    for (int c = tid; c < SH::TAB; c += TD_THREADS) S.head[c] = 0;
+    if (tid < 2) { S.nmem[tid] = 0; S.nhit[tid] = 0; }
+    if (tid == 0) mbar_init(&S.bar, 1);
+    const bool hw = warp == TD_THREADS / 32 - 1; /* header warp: the tail of the candidate list, least to do */
+    int hn = 0;
+    if (hw) {
+        det_publish(p, S, 0, p.dl[(size_t)w * AMC_WI + lane], lane);
+        if (w + stride < nwork) hn = p.dl[(size_t)(w + stride) * AMC_WI + lane];
+    }
+    __syncthreads();
+    if (hw) det_fetch(p, S, 0, lane);
+    unsigned int tests = 0;
+    unsigned long long nref = 0; /* header warp, lane 0 */
+    const float thr = p.det_thr;
+    unsigned int tagw = 0;
+    uint32_t phase = 0;
+    bool stuck = false;
+    for (int it = 0; w < nwork; it++, w += stride) {
+        const int cur = it & 1, nxt = cur ^ 1;
+        tagw += 0x10000u;
+        if (tagw == 0) { /* visit tags exhausted: start over with a clean table */
+            __syncthreads();
+            for (int c = tid; c < SH::TAB; c += TD_THREADS) S.head[c] = 0;
+            tagw = 0x10000u;
+            __syncthreads();
+        }
+        const int total = S.rcum[cur][8];
+        const bool big = total > DET_CAND;
+        bool hit = big;
+        if (!mbar_wait(&S.bar, phase)) stuck = true; /* the records of this cell are in S.raw */
+        phase ^= 1u;
+        // ---- hash the members of the current cell
+        float fx[TD_K], fy[TD_K], fz[TD_K];
+        int bin[TD_K], older[TD_K];
+        {
+            const double *bd = reinterpret_cast<const double *>(&S.hdr[cur][20]);
+            const double lox = bd[0], hix = bd[1], loy = bd[2], hiy = bd[3], loz = bd[4], hiz = bd[5];
+            const float inv_wx = S.inv_wx[cur], inv_wy = S.inv_wy[cur];
+            const int nbx1 = S.nbx[cur] - 1, nby1 = S.nby[cur] - 1;
+            const int own = p.det_own_is_member ? S.rcum[cur][1] : 0; /* the owner cell's particles are members by construction */
+            int nm = 0;
+#pragma unroll
+            for (int k = 0; k < TD_K; k++) {
+                const int t = tid + k * TD_THREADS;
+                bin[k] = -1;
+                if (t < total && !big) {
+                    const double2 xy = *reinterpret_cast<const double2 *>(&S.raw[t]);
+                    const double x = xy.x, y = xy.y, z = S.raw[t].z;
+                    if (t < own || (lox < x && x < hix && loy < y && y < hiy && loz < z && z < hiz)) { /* Pore:527-530 */
+                        fx[k] = (float)(x - lox); fy[k] = (float)(y - loy); fz[k] = (float)(z - loz);
+                        int b = min(nbx1, (int)(fx[k] * inv_wx)) * SH::ROW + min(nby1, (int)(fy[k] * inv_wy)) + 1;
+                        unsigned int prev = atomicExch(&S.head[b], tagw | (unsigned int)(t + 1)) ^ tagw;
+                        prev = prev < 0x10000u ? prev : 0u;
+                        S.tile[t] = make_float4(fx[k], fy[k], fz[k], __uint_as_float(prev));
+                        bin[k] = b; older[k] = (int)prev;
+                        nm++;
+                    }
+                }
+            }
+            nm = __reduce_add_sync(0xffffffffu, nm);
+            if (lane == 0 && nm) atomicAdd(&S.nmem[cur], nm);
+        }
+        const int wn = w + stride;
+        if (hw && wn < nwork) {
+            det_publish(p, S, nxt, hn, lane);
+            if (wn + stride < nwork) hn = p.dl[(size_t)(wn + stride) * AMC_WI + lane];
+        }
+        __syncthreads();
+        // ---- every thread is done with S.raw: the next cell's records start their trip from HBM now
+        if (hw && wn < nwork) det_fetch(p, S, nxt, lane);
+        // ---- search: the older members of the own bin and everything in the four forward neighbour bins
+#pragma unroll
+        for (int k = 0; k < TD_K; k++) {
+            if (bin[k] < 0) continue;
+            const int b = bin[k];
+            unsigned int c[5];
+            c[0] = (unsigned int)older[k];
+            c[1] = S.head[b + 1] ^ tagw; c[2] = S.head[b + SH::ROW - 1] ^ tagw;
+            c[3] = S.head[b + SH::ROW] ^ tagw; c[4] = S.head[b + SH::ROW + 1] ^ tagw;
+            if (c[0] == 0 && min(min(c[1], c[2]), min(c[3], c[4])) >= 0x10000u) continue;
+            unsigned long long pend = c[0];
+            int sh = c[0] ? 9 : 0;
+#pragma unroll
+            for (int n = 1; n < 5; n++)
+                if (c[n] < 0x10000u) { pend |= (unsigned long long)c[n] << sh; sh += 9; }
+            const unsigned long long all = pend;
+            const float ax = fx[k], ay = fy[k], az = fz[k];
+            float dmin = 3.0e38f;
+            for (unsigned int e = 0;;) {
+                if (e == 0) {
+                    if (pend == 0) break;
+                    e = (unsigned int)pend & 511u;
+                    pend >>= 9;
+                }
+                float4 q = S.tile[e - 1];
+                float ex = q.x - ax, ey = q.y - ay, ez = q.z - az;
+                dmin = fminf(dmin, fmaf(ez, ez, fmaf(ey, ey, ex * ex)));
+                tests++;
+                e = __float_as_uint(q.w);
+            }
+            if (dmin < thr) { /* rare: walk the chains once more and remember the pairs for the ordered resolution */
+                hit = true;
+                pend = all;
+                for (unsigned int e = 0;;) {
+                    if (e == 0) {
+                        if (pend == 0) break;
+                        e = (unsigned int)pend & 511u;
+                        pend >>= 9;
+                    }
+                    float4 q = S.tile[e - 1];
+                    float ex = q.x - ax, ey = q.y - ay, ez = q.z - az;
+                    if (fmaf(ez, ez, fmaf(ey, ey, ex * ex)) < thr) {
+                        const int hh = atomicAdd(&S.nhit[cur], 1);
+                        if (hh < AMC_MAX_HITS) S.hit[cur][hh] = ((unsigned int)(tid + k * TD_THREADS) << 16) | (e - 1);
+                    }
+                    e = __float_as_uint(q.w);
+                }
+            }
+        }
+        if (tid == TD_THREADS - 1) { S.nmem[nxt] = 0; S.nhit[nxt] = 0; }
+        const int any = __syncthreads_or(hit);
+        if (hw) {
+            const int *h = S.hdr[cur];
+            const int cell = h[0], kx = h[1], ky = h[2], kz = h[3];
+            const int g = ((kx & 1) << 2) | ((ky & 1) << 1) | ((kz + p.zoff) & 1);
+            const size_t ci = (size_t)g * p.wl_stride + cell;
+            if (any) {
+                int idx = 0;
+                if (lane == 0) { p.cell_active[ci] = 1; idx = atomicAdd(&p.wl_count[g], 1); }
+                idx = __shfl_sync(0xffffffffu, idx, 0);
+                p.wl[((size_t)g * p.wl_stride + idx) * AMC_WI + lane] = h[lane];
+                const int nh = S.nhit[cur];
+                const bool listed = !big && nh >= 1 && nh <= AMC_MAX_HITS;
+                int32_t *wh = p.wl_hit + ((size_t)g * p.wl_stride + idx) * AMC_HIT_REC;
+                if (lane == 0) wh[0] = listed ? nh : -1;
+                if (listed && lane < 2 * nh) {
+                    const unsigned int hv = S.hit[cur][lane >> 1];
+                    wh[1 + lane] = det_slot(S, cur, (lane & 1) ? (int)(hv & 0xffffu) : (int)(hv >> 16));
+                }
+            } else if (lane == 0) {
+                const int nm = S.nmem[cur];
+                p.cell_n[ci] = nm;
+                nref += (unsigned long long)nm * (nm - 1) / 2;
+            }
+        }
+    }
+    tests = __reduce_add_sync(0xffffffffu, tests);
+    if (lane == 0 && tests) atomicAdd(&p.stats->checks_exec, (unsigned long long)tests);
+    if (hw && lane == 0 && nref) atomicAdd(&p.stats->checks_ref, nref);
+    if (stuck) atomicAdd(&p.stats->cand_overflow, 1ull); /* reported by check_overflow: the results of this pass are not to be trusted */
 }
 
 // members of one reference cell of a colour group -> S.{x,y,z,id,slot,src}[0..S.n): its own register budget
