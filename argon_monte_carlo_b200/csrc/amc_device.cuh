@@ -728,10 +728,10 @@ __device__ __forceinline__ void flag_wait(const uint32_t *f, const uint32_t seq)
 }
 
 // see k_recapture_list (amc_kernels.cuh)
+// One round trip: the call sits at the tail of a cell visit, which is what a launch of k_pairs_group waits for.  A slot
+// moved in several visits of one step is listed several times; the reader (k_recapture_list) takes each slot once.
 __device__ __forceinline__ void touch_slot(const P &p, const int32_t s)
 {
-    const int32_t tag = 1 + (int32_t)(p.step & 0x3fffffff); /* per-slot marker: listed in this step already */
-    if (atomicExch(&p.touch_mark[s], tag) == tag) return;
     int i = atomicAdd(p.touched_n, 1);
     if (i < p.touched_cap) p.touched[i] = s;
 }

@@ -550,7 +550,11 @@ __global__ void __launch_bounds__(ADVECT_THREADS) k_recapture_list(const __grid_
     if (nt > p.touched_cap) { /* list overflowed: everything */
         for (int64_t s = first, n = cur_n(p); s < n; s += stride) recapture_slot(p, s);
     } else {
-        for (int64_t i = first; i < nt; i += stride) recapture_slot(p, p.touched[i]);
+        const int32_t tag = 1 + (int32_t)(p.step & 0x3fffffff); /* per-slot marker: handled in this step already */
+        for (int64_t i = first; i < nt; i += stride) {
+            const int32_t s = p.touched[i];
+            if (atomicExch(&p.touch_mark[s], tag) != tag) recapture_slot(p, s);
+        }
     }
 }
 
@@ -828,9 +832,25 @@ __device__ __forceinline__ void activate_moved(const P &p, CellShared &S, const 
             else { const double *sp = p.mv_spill + ((size_t)blockIdx.x * AMC_MAX_MEMBERS + io) * 3; ux = sp[0]; uy = sp[1]; uz = sp[2]; }
             if ((lane & 7) == 0 && lane < 16) { /* lanes 0 and 8: one per particle */
                 const int so = S.slot[m];
+                e_old = S.src[m];
+                // Nine moved particles out of ten never leave the plain interior of the visited cell: read from the cell's
+                // own owner segment (src == -1), inside that owner cell and outside every low-side band before and after
+                // the visit.  Such a particle is a member of no other reference cell (member_axis: cell k only, parity of
+                // the current group), nothing gains or loses it, and its sorted slot still finds it: nothing to do.
+                bool fast = e_old == -1 && p.det_own_is_member;
+                if (fast) {
+                    const int kk[3] = {S.kx, S.ky, S.kz};
+                    const double nv[3] = {x, y, z}, ov[3] = {ux, uy, uz};
+#pragma unroll
+                    for (int a = 0; a < 3; a++) {
+                        const bool last = kk[a] + 1 >= p.nc[a];
+                        const double clo = p.edge[a][kk[a]], blo = last ? 0.0 : p.lo[a][kk[a] + 1], hi = S.hi[a];
+                        fast = fast && clo <= nv[a] && nv[a] < hi && (last || nv[a] <= blo) && clo <= ov[a] && ov[a] < hi && (last || ov[a] <= blo);
+                    }
+                }
+                if (!fast) {
                 int32_t k = owner_key(p, x, y, z, o);
                 owner_key(p, ux, uy, uz, q);
-                e_old = S.src[m];
                 ok = 1;
                 if (e_old < 0) { /* found through the sorted layout: src = -1 - (low-side neighbour code) */
                     int nb = -1 - e_old;
@@ -842,7 +862,8 @@ __device__ __forceinline__ void activate_moved(const P &p, CellShared &S, const 
                 if (!findable) { /* entries are never re-linked: a particle that moves again in a later visit gets a fresh one */
                     e = atomicAdd(p.esc_count, 1);
                     if (e >= p.esc_cap) { atomicAdd(&p.stats->esc_overflow, 1ull); ok = 0; }
-                    else { p.esc_slot[e] = so; A.pos[so].flag |= AMC_FLAG_ESC; }
+                    else { p.esc_slot[e] = so; atomicOr(&A.pos[so].flag, AMC_FLAG_ESC); }
+                }
                 }
             }
         }
