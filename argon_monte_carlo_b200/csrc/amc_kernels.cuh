@@ -19,6 +19,9 @@
 #define AMC_MV_CAP 32 /* particles one cell visit can move (reference scale: 2-6) */
 #define WALK_K 3 /* chains a thread of cell_process walks side by side */
 #define PAIR_K 3 /* candidates a thread of k_pairs_group has in flight during the gather */
+#ifndef PAIR_OCC
+#define PAIR_OCC 6 /* resident CTAs per SM of k_pairs_group: a colour-group launch lasts one visit if the group's worklist fits the grid, two if not */
+#endif
 #ifndef SWEEP_THREADS
 #define SWEEP_THREADS 512
 #endif
@@ -1737,7 +1740,7 @@ __device__ __forceinline__ void bnd_pack_warp(const P &p, const int dir, const i
 // are applied and no ticket is left; the last CTA to finish packs this group's records straight into the neighbours'
 // buffers and publishes p.bnd_seq there.
 template <bool fused>
-__global__ void __launch_bounds__(PAIR_THREADS, 6) k_pairs_group(const __grid_constant__ P p, const int group)
+__global__ void __launch_bounds__(PAIR_THREADS, PAIR_OCC) k_pairs_group(const __grid_constant__ P p, const int group)
 {
     __shared__ CellShared S;
     const int tid = threadIdx.x;

@@ -52,11 +52,17 @@ def ncu_traffic(kernel, particles):
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
             for rec in json.load(f)["kernels"]:
-                if kernel.startswith(rec["kernel"]) and abs(rec["particles"] - particles) <= 1e-3 * particles:
+                if kernel == rec["kernel"] and abs(rec["particles"] - particles) <= 1e-3 * particles:
                     return {"bytes": rec["dram_bytes"], "source": rec["source"]}
     except Exception:
         pass
     return None
+
+
+def detect_kernel():
+    """name of the detection kernel libamc.so launches: candidates staged by cp.async.bulk (default) or loaded by the
+    threads (AMC_DETECT=ldg), see launch_detect in csrc/amc_api.cu"""
+    return "k_detect" if os.environ.get("AMC_DETECT") == "ldg" else "k_detect_tma"
 
 
 def measured_peaks():
@@ -300,8 +306,8 @@ def run_ours(args):
     # 32 B x particles (3 x f64 position + cell header), duration = CUDA events around the launch on the
     # handle's stream; traffic = dram read + write of one launch from the ncu --set full capture of this workload
     # (profiles/ncu_traffic.json; null when no capture of this workload is committed)
-    traffic = ncu_traffic("k_detect", n)
-    roofline = {"bound": "hbm", "kernel": "k_detect (pair detection, 1 launch per step)",
+    traffic = ncu_traffic(detect_kernel(), n)
+    roofline = {"bound": "hbm", "kernel": detect_kernel() + " (pair detection, 1 launch per step)",
                 "achieved": B_PAIR * n / (det_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": B_PAIR * n,
                 "avg_launch_ms": det_ms,
@@ -446,7 +452,7 @@ def run_slabs(args, world, rank, local, dev, hbm_peak, peak_src, barrier, max_ov
     collisions = sum_over_ranks(float(np.mean([s["collisions"] for s in stats])))
     n_max = max_over_ranks(float(n))
     det_ms = max_over_ranks((sim.ranks[0].sim.last_detect_ms() - det0) / args.steps)
-    roofline = {"bound": "hbm", "kernel": "k_detect (pair detection, 1 launch per step and rank; slowest rank)",
+    roofline = {"bound": "hbm", "kernel": detect_kernel() + " (pair detection, 1 launch per step and rank; slowest rank)",
                 "achieved": B_PAIR * n_max / (det_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "peak_source": peak_src, "avg_launch_ms": det_ms, "traffic": None}
     roofline["frac"] = roofline["achieved"] / hbm_peak

@@ -1,0 +1,13 @@
+# multi-GPU check: the N-process tests (p2p + NCCL paths against the single-GPU run) and bench.py at N GPUs.  usage: bash tools/gpu_multi_quick.sh TAG NGPU
+TAG=${1:-mq}; N=${2:-2}; D=gpurun_out/$TAG; mkdir -p $D
+timeout 900 python -m pytest tests/test_gpu_nccl_slab.py -m gpu -x -q --durations=5 > $D/tests.log 2>&1; echo "pytest exit $?" >> $D/tests.log
+tail -5 $D/tests.log
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29519 bench.py --gpus $N --steps 20 --warmup 5 > $D/bench_n$N.json 2> $D/bench_n$N.err; echo "bench exit $?"
+python - <<PY
+import json
+try:
+    d = json.loads(open("$D/bench_n$N.json").read().strip().splitlines()[-1])
+    print("N=$N ms/step %.4f value %.4g" % (d["ms_per_step"], d["value"]), d.get("phases_ms_per_step"), d.get("verify"))
+except Exception as e:
+    print("bench parse failed", e); print(open("$D/bench_n$N.err").read()[-2500:])
+PY
