@@ -15,10 +15,14 @@
 #include "amc_device.cuh"
 
 #define ADVECT_THREADS 256
+#ifndef PAIR_THREADS
 #define PAIR_THREADS 128
+#endif
 #define AMC_MV_CAP 32 /* particles one cell visit can move (reference scale: 2-6) */
 #define WALK_K 3 /* chains a thread of cell_process walks side by side */
+#ifndef PAIR_K
 #define PAIR_K 3 /* candidates a thread of k_pairs_group has in flight during the gather */
+#endif
 #ifndef PAIR_OCC
 #define PAIR_OCC 6 /* resident CTAs per SM of k_pairs_group: a colour-group launch lasts one visit if the group's worklist fits the grid, two if not */
 #endif
@@ -595,12 +599,10 @@ struct CellShared {
     long long t_last;
     double org[3];               /* low corner of the cell: origin of the fp32 coordinates below */
     double hi[3];                /* upper bounds of the cell (membership: org < v < hi, Pore:527-529) */
-    float fx[AMC_MAX_MEMBERS], fy[AMC_MAX_MEMBERS], fz[AMC_MAX_MEMBERS]; /* filter copy of the member positions */
     /* neighbour search: members chained per slab along x (>= 1.05 filter radii wide) */
     int head[AMC_XBINS + 2];     /* last member hashed into the slab (index + 1), 0 = empty; zero on entry of cell_process */
-    uint16_t nxt[AMC_MAX_MEMBERS];
+    uint16_t nxt[AMC_MAX_MEMBERS];    /* chain links of the search; afterwards (activate_moved) the list of the moved members */
     uint16_t mv[AMC_MAX_MEMBERS];     /* 0, or 1 + index of the member's pre-visit position in ox/oy/oz (beyond AMC_MV_CAP: in P::mv_spill) */
-    uint16_t mvlist[AMC_MAX_MEMBERS]; /* the moved members, compacted at the end of the visit */
     double ox[AMC_MV_CAP], oy[AMC_MV_CAP], oz[AMC_MV_CAP];
     int nmv, nold;
     int hits[AMC_HIT_REC];       /* this work item's record of wl_hit */
@@ -815,20 +817,20 @@ __device__ __forceinline__ void activate_moved(const P &p, CellShared &S, const 
     const int tid = threadIdx.x, nthreads = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nthreads >> 5;
     const int n = S.n;
     for (int k = tid; k < n; k += nthreads)
-        if (S.mv[k]) S.mvlist[atomicAdd(&S.nmv, 1)] = (uint16_t)k;
+        if (S.mv[k]) S.nxt[atomicAdd(&S.nmv, 1)] = (uint16_t)k;
     __syncthreads();
     const int nmv = S.nmv;
     const Arrays &A = p.a;
     // the closing recapture has to look at every moved slot (touch_slot: two dependent global atomics): the last warp
     // does that beside the activation work of the first ones instead of in front of it
     if (warp == nwarps - 1)
-        for (int i = lane; i < nmv; i += 32) touch_slot(p, S.slot[S.mvlist[i]]);
+        for (int i = lane; i < nmv; i += 32) touch_slot(p, S.slot[S.nxt[i]]);
     for (int base = 2 * warp; base < nmv; base += 2 * nwarps) {
         const int pw = (lane >> 3) & 1, g2 = lane & 7;
         int o[3] = {0, 0, 0}, q[3] = {0, 0, 0}, e = -1, e_old = -1, findable = 0, ok = 0;
         double x = 0, y = 0, z = 0, ux = 0, uy = 0, uz = 0;
         if (base + pw < nmv) {
-            const int m = S.mvlist[base + pw];
+            const int m = S.nxt[base + pw];
             x = S.x[m]; y = S.y[m]; z = S.z[m];
             const int io = S.mv[m] - 1;
             if (io < AMC_MV_CAP) { ux = S.ox[io]; uy = S.oy[io]; uz = S.oz[io]; }
@@ -975,11 +977,13 @@ __device__ __forceinline__ void cell_process(const P &p, CellShared &S, int grou
         // slab.  A pair goes through the fp32 filter of k_detect first (cell-relative coordinates, threshold det_thr)
         // and only the few that pass are decided by the exact test (Pore:173-174).
         {
+            // the fp32 cell-relative coordinates of the filter are formed from the fp64 members where they are needed (a
+            // copy of them would cost 6 KB of the CTA's shared memory, i.e. resident CTAs)
             const float inv_w = S.inv_w, thr = p.det_thr;
+            const double org0 = S.org[0], org1 = S.org[1], org2 = S.org[2];
             const int nb1 = S.nb - 1;
             for (int k = tid; k < n; k += nthreads) {
-                float fx = (float)(S.x[k] - S.org[0]);
-                S.fx[k] = fx; S.fy[k] = (float)(S.y[k] - S.org[1]); S.fz[k] = (float)(S.z[k] - S.org[2]);
+                float fx = (float)(S.x[k] - org0);
                 int b = min(nb1, max(0, (int)(fx * inv_w)));
                 S.nxt[k] = (uint16_t)atomicExch(&S.head[b], k + 1);
                 S.mv[k] = 0;
@@ -998,7 +1002,7 @@ __device__ __forceinline__ void cell_process(const P &p, CellShared &S, int grou
                     const int k = k0 + u * nthreads;
                     e[u] = 0; more[u] = 0; ax[u] = ay[u] = az[u] = 0.f;
                     if (k < n) {
-                        ax[u] = S.fx[k]; ay[u] = S.fy[k]; az[u] = S.fz[k];
+                        ax[u] = (float)(S.x[k] - org0); ay[u] = (float)(S.y[k] - org1); az[u] = (float)(S.z[k] - org2);
                         const int b = min(nb1, max(0, (int)(ax[u] * inv_w)));
                         e[u] = S.nxt[k]; more[u] = S.head[b + 1];
                     }
@@ -1014,7 +1018,7 @@ __device__ __forceinline__ void cell_process(const P &p, CellShared &S, int grou
 #pragma unroll
                     for (int u = 0; u < WALK_K; u++) {
                         const int q = max(e[u] - 1, 0); /* entry 0 stands in for a finished chain; its result is masked */
-                        const float ex = S.fx[q] - ax[u], ey = S.fy[q] - ay[u], ez = S.fz[q] - az[u];
+                        const float ex = (float)(S.x[q] - org0) - ax[u], ey = (float)(S.y[q] - org1) - ay[u], ez = (float)(S.z[q] - org2) - az[u];
                         const int nx = S.nxt[q];
                         const float d2 = fmaf(ez, ez, fmaf(ey, ey, ex * ex));
                         if (e[u] != 0 && d2 < thr) { /* rare */

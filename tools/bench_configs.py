@@ -48,7 +48,7 @@ def main():
         sim = amc.Simulation(cfg)
         sim.set_state(*st)
         ms, l = timed_steps(sim, steps)
-        line("cfg1 Open_Air_Cube_MC.py as shipped (serial sweep, k_cube_sweep)", len(st[0]), ms, l)
+        line("cfg1 Open_Air_Cube_MC.py as shipped (serial sweep, k_sweep_detect + k_sweep_events)", len(st[0]), ms, l)
         sim.close()
     if "cfg2" in which:
         cfg = config.pore_config(False)
