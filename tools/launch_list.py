@@ -12,7 +12,7 @@ for o in out: print("%-28s %9s %10s %10s" % o)
 if len(sys.argv) > 2:
     csv.writer(open(sys.argv[2], "w")).writerows(out)
 starts = [i for i, (n, v) in enumerate(names) if n in ("k_advect", "k_keys")]
-steps = [names[a:b] for a, b in zip(starts, starts[1:]) if any(n == "k_detect" for n, v in names[a:b])]
+steps = [names[a:b] for a, b in zip(starts, starts[1:]) if any(n.startswith("k_detect") for n, v in names[a:b])]
 if steps:
     st = min(steps, key=lambda q: sum(v for n, v in q))
     print("fastest complete timestep of the run (%d launches, %.1f us; each kernel cold after ncu's cache flush):" % (len(st), sum(v for n, v in st)))
