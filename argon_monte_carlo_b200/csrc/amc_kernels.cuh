@@ -3,11 +3,15 @@
 //   k_scan_*          exclusive scan of the owner-cell histogram                                 (tiny)
 //   k_scatter_advect  the timestep itself on the way to the sorted slot                         (HBM streaming)
 //   k_build_worklist  reference cells with >= 2 candidates -> detection list                    (tiny)
-//   k_detect          neighbour search over every reference cell, all colour groups at once     (issue; 25 B/particle)
+//   k_detect_tma      neighbour search over every reference cell, all colour groups at once; candidates staged by
+//                     cp.async.bulk + mbarrier                                                   (issue; 33 B/particle)
+//   k_detect          the same with the candidates loaded by the threads (cross-check; <true>: overlap-free seeding)
 //   k_pairs_group     ordered resolution of the flagged / activated cells of one colour group   (latency)
 //   k_recapture_list  closing recapture over the slots a collision touched                      (tiny)
 //   k_advect, k_scatter, k_recapture_post   the same step as separate in-place passes: phase-level parity entry points
-//   k_cube_sweep      the serial lexicographic cell sweep of the cube stage                     (latency)
+//   k_sweep_detect, k_sweep_events   the serial lexicographic cell sweep of the cube stage, event-driven  (latency)
+//   k_cube_sweep      the same sweep as a plain walk over every cell (cross-check, fall-back)   (latency)
+//   k_pack_pos, k_unpack_pos   the C ABI's separate arrays <-> the 32-byte position records
 //   k_case_*          per-case wall kernels for the host-RNG parity mode
 //   k_init_synthetic  synthetic Maxwellian initial state
 //   k_xfer_*, k_bnd_* slab decomposition: migration / ghost copies, per-group hand-over

@@ -95,9 +95,15 @@ def test_temp_host_rng_matches_oracle_and_shipped_csv(oracle, temp_cfg):
     sim.close()
 
 
-def test_temp_device_rng_bit_exact(oracle, temp_cfg, temp_init):
+@pytest.mark.parametrize("detect", ["default", "ldg", "tma6"])
+def test_temp_device_rng_bit_exact(oracle, temp_cfg, temp_init, detect, monkeypatch):
+    """Energized pore with the device RNG, three timesteps against the oracle.  `detect` selects the shape of the
+    detection pass (read by amc_create): default = candidates staged by cp.async.bulk, 8 CTAs per SM; tma6 = the 6-CTA
+    shape with the full bin table; ldg = candidates loaded by the threads.  All three must give the oracle's state."""
     from argon_monte_carlo_b200 import amc, config
     from oracle import steps
+    if detect != "default":
+        monkeypatch.setenv("AMC_DETECT", detect)
     cheb = config.gap_energy_chebyshev(temp_cfg, 16)
     st = oracle.ParticleState(*temp_init)
     sim = amc.Simulation(temp_cfg, taps=amc.TAP_WALL_BITS | amc.TAP_PAIRS, seed=17, cheb=cheb)
