@@ -617,7 +617,7 @@ def bench_other_configs(args):
         sim.set_state(*st)
         ms = timed(sim, 10, True)
         sim.close()
-        res.append({"workload": "cfg1: Open_Air_Cube_MC.py as shipped, N=%d, serial cell sweep" % len(st[0]), "ms_per_step": ms[4],
+        res.append({"workload": "cfg1: Open_Air_Cube_MC.py as shipped, N=%d, serial cell sweep (reference order, event-driven: k_sweep_detect + k_sweep_events)" % len(st[0]), "ms_per_step": ms[4],
                     "value": len(st[0]) / (ms[4] * 1e-3), "unit": "particle-steps/s"})
         cfg = config.pore_config(True)
         st = init_state.pore_initial_state(cfg)
