@@ -44,6 +44,7 @@ struct amc_handle {
     int n_buckets = 0;          // padded owner cells + OUT
     bool have_prior = false;
     int64_t step_index = 0;
+    int pdl = 3;                // programmatic dependent launches (launch_pdl; AMC_PDL=0 turns them off)
     int pair_grid = 148 * 5;    // persistent CTAs of k_pairs_group: SMs x resident CTAs per SM
     int pair_grid_fused = 148;  // the same for the fused (in-kernel hand-over) variant
     int det_grid = 148 * 4;     // persistent CTAs of k_detect
@@ -357,10 +358,12 @@ static int create_impl(amc_handle *h, const amc_config *cfg, int device)
             h->pair_grid_fused = std::max(1, sms * std::max(per_sm_fused, 1));
         }
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pairs_group<false>, PAIR_THREADS, 0));
+        if (const char *pc = getenv("AMC_PAIR_CTAS")) per_sm = std::max(1, std::min(per_sm, atoi(pc))); /* experiments: fewer CTAs per SM than fit */
         h->pair_grid = std::max(1, sms * std::max(per_sm, 1));
         CK(cudaFuncSetAttribute(k_detect<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_detect<false>, DET_THREADS, 0));
         h->det_grid = std::max(1, sms * std::max(per_sm, 1));
+        if (const char *pd = getenv("AMC_PDL")) h->pdl = atoi(pd); /* bit 0: colour groups 1-7 behind the group before, bit 1: k_scan_sums / k_scan_add behind k_scan_tiles; 0 = plain launches (A/B) */
         const char *dm = getenv("AMC_DETECT");
         h->detect_tma = dm && strcmp(dm, "ldg") == 0 ? 0 : (dm && strcmp(dm, "tma6") == 0 ? 1 : 2);
         if (h->detect_tma == 1) {
@@ -530,6 +533,20 @@ static void launch_detect(amc_handle *h)
     else k_detect<false><<<h->det_grid, DET_THREADS, 0, h->stream>>>(h->p);
 }
 
+// launch `kernel` programmatically dependent on the kernel before it in the stream (griddepcontrol, see pdl_trigger /
+// pdl_wait in amc_kernels.cuh): its CTAs may become resident while that kernel still runs
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t stream, Args &&...args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 static int run_pairs(amc_handle *h, int64_t *launches, bool prepared = false)
 {
     P &p = h->p;
@@ -559,7 +576,10 @@ static int run_pairs(amc_handle *h, int64_t *launches, bool prepared = false)
         launch_detect(h);
         if (h->det_slot >= 0) CK(cudaEventRecord(h->det_events[2 * h->det_slot + 1], h->stream));
         unsigned grid = (unsigned)std::min<int64_t>((int64_t)h->pair_grid, std::max<int64_t>(ncell / 8, 1));
-        for (int g = 0; g < 8; g++) k_pairs_group<false><<<grid, PAIR_THREADS, 0, h->stream>>>(p, g);
+        for (int g = 0; g < 8; g++) {
+            if (g > 0 && (h->pdl & 1)) CK(launch_pdl(k_pairs_group<false>, dim3(grid), dim3(PAIR_THREADS), h->stream, p, g));
+            else k_pairs_group<false><<<grid, PAIR_THREADS, 0, h->stream>>>(p, g);
+        }
         if (launches) *launches += 11;
     }
     CK(cudaGetLastError());
@@ -631,8 +651,13 @@ extern "C" int amc_step(amc_handle *h, int32_t n_steps, amc_step_stats *stats)
                     CK(cudaEventRecord(h->events[4 * s + 1], h->stream));
                     int m = h->n_buckets, ntiles = (m + SCAN_TILE - 1) / SCAN_TILE;
                     k_scan_tiles<<<ntiles, SCAN_THREADS, 0, h->stream>>>(p.band_count, p.rest_count, p.cell_start, h->d_tile_sums, m);
-                    k_scan_sums<<<1, SCAN_THREADS, 0, h->stream>>>(h->d_tile_sums, ntiles);
-                    k_scan_add<<<ntiles, SCAN_THREADS, 0, h->stream>>>(p.cell_start, h->d_tile_sums, m, (int32_t)h->n);
+                    if (h->pdl & 2) {
+                        CK(launch_pdl(k_scan_sums, dim3(1), dim3(SCAN_THREADS), h->stream, h->d_tile_sums, ntiles));
+                        CK(launch_pdl(k_scan_add, dim3(ntiles), dim3(SCAN_THREADS), h->stream, p.cell_start, (const int32_t *)h->d_tile_sums, m, (int32_t)h->n));
+                    } else {
+                        k_scan_sums<<<1, SCAN_THREADS, 0, h->stream>>>(h->d_tile_sums, ntiles);
+                        k_scan_add<<<ntiles, SCAN_THREADS, 0, h->stream>>>(p.cell_start, h->d_tile_sums, m, (int32_t)h->n);
+                    }
                     // the bookkeeping of the pair pass needs the scan, not the scattered particles: it runs beside the scatter
                     CK(cudaEventRecord(h->ev_fork, h->stream));
                     CK(cudaStreamWaitEvent(h->aux, h->ev_fork, 0));
