@@ -41,7 +41,9 @@
 // Both are no-ops in a launch without the attribute.  Used where launches follow one another without anything in
 // between (launch_pdl in amc_api.cu): colour group g + 1 behind group g, k_scan_sums / k_scan_add behind k_scan_tiles --
 // about 2 us per kernel boundary (measured on B200: 12.5 M particles 1.0005 -> 0.9813 ms per step, 557,649 particles
-// 0.2556 -> 0.2381 ms).  With an event record between two launches the attribute gains nothing (measured as well).
+// 0.2556 -> 0.2381 ms).  The same attribute on k_scan_tiles behind k_keys, on k_scatter_advect behind the scan and on group 0
+// behind the detection pass (each with a timing event recorded in between, and a predecessor that fills every SM until
+// it ends) changed nothing and is not used.
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
