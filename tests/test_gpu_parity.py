@@ -176,3 +176,29 @@ def test_multi_step_call_equals_single_steps(oracle, temp_cfg, temp_init):
     for k in KEYS:
         assert np.array_equal(ga[k], gb[k]) and np.array_equal(ga[k], getattr(st, k)), k
     a.close(); b.close()
+
+
+def test_dependent_launches_do_not_change_results(temp_cfg, temp_init, monkeypatch):
+    """The colour-group launches and the scan kernels are launched programmatically dependent on the kernel before
+    them (AMC_PDL, read by amc_create).  Plain stream-ordered launches (AMC_PDL=0) must give the same
+    counters and the same state, bit for bit, over a multi-step call."""
+    from argon_monte_carlo_b200 import amc, config
+    cheb = config.gap_energy_chebyshev(temp_cfg, 16)
+    runs = []
+    for pdl in (None, "0"):
+        if pdl is None:
+            monkeypatch.delenv("AMC_PDL", raising=False)
+        else:
+            monkeypatch.setenv("AMC_PDL", pdl)
+        sim = amc.Simulation(temp_cfg, seed=11, cheb=cheb)
+        sim.set_state(*temp_init)
+        stats = sim.step(6)
+        runs.append((stats, sim.get_state(), sim.state_digest()))
+        sim.close()
+    (sa, ga, da), (sb, gb, db) = runs
+    for x, y in zip(sa, sb):
+        for k in ("collisions", "oob_after_walls", "oob_after_pp", "completed_paths", "dpz", "e_cold", "e_hot"):
+            assert x[k] == y[k], k
+    assert da == db
+    for k in KEYS:
+        assert np.array_equal(ga[k], gb[k]), k
